@@ -1,0 +1,112 @@
+"""ctypes binding of libhan_sm100.so (include/han_b200.h).  No fallback: if the CUDA library is
+missing or a call fails, this raises."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_int, c_int32, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "libhan_sm100.so"
+
+ACT_IDENTITY, ACT_ELU = 0, 1
+SEM_REFERENCE, SEM_PAPER = 0, 1
+DENSE_ADJ, DENSE_BIAS, DENSE_POSITIVE = 0, 1, 2
+F32, F64 = 0, 1
+
+P = c_void_p
+I64 = c_int64
+I = c_int
+SZ = c_size_t
+
+# name -> (restype, argtypes); mirrors include/han_b200.h one to one
+_SIGNATURES = {
+    "han_version": (c_int, []),
+    "han_last_error": (c_char_p, []),
+    "han_attn_shape_supported": (c_int, [I, I]),
+    "han_table_stride": (c_int, [I, I]),
+    "han_record_stride": (c_int, [I, I]),
+    "han_dense_row_counts": (c_int, [P, I, I, I64, I64, P, P, P]),
+    "han_scan_workspace_bytes": (SZ, [I64]),
+    "han_scan_counts": (c_int, [P, I64, P, P, SZ, P]),
+    "han_dense_fill_indices": (c_int, [P, I, I, I64, I64, P, P, P]),
+    "han_transpose_workspace_bytes": (SZ, [I64, I64, I64]),
+    "han_csr_transpose": (c_int, [I64, I64, I64, P, P, P, P, P, P, SZ, P]),
+    "han_csr_sort_rows": (c_int, [I64, P, P, P, P, P, P]),
+    "han_project_fwd": (c_int, [P, I64, I64, I64, P, I, I, I, P, P, P, P, P, P, I, P]),
+    "han_project_bwd_workspace_bytes": (SZ, [I64, I64, I, I]),
+    "han_project_bwd": (c_int, [P, I64, I64, I64, P, I, I, P, P, SZ, I, P]),
+    "han_attn_fwd": (c_int, [P, P, I64, P, P, P, I, I, I, P, I64, P, P, P]),
+    "han_attn_coefs": (c_int, [P, P, I64, P, P, I, I, P, P]),
+    "han_reduce_blocks": (c_int, []),
+    "han_attn_bwd_prep": (c_int, [P, I64, P, I64, P, P, I64, I, I, I, P, P]),
+    "han_attn_bwd_src": (c_int, [P, P, P, I64, P, P, I, I, P, P, P, P]),
+    "han_attn_bwd_dst": (c_int, [P, I64, P, I, P, P]),
+    "han_attn_bwd_finish": (c_int, [P, I64, I, I, P, P, P, P, P, P, P]),
+    "han_reduce_partials": (c_int, [P, I, I64, P, P]),
+    "han_semantic_shape_supported": (c_int, [I, I]),
+    "han_semantic_fwd": (c_int, [P, I64, I, I, I, P, P, P, I, P, P, P, P, P]),
+    "han_semantic_combine": (c_int, [P, I64, I, I, P, P, P, P]),
+    "han_semantic_bwd_workspace_bytes": (SZ, [I, I, I]),
+    "han_semantic_bwd": (c_int, [P, P, P, P, I64, I, I, I, P, P, I, P, P, P, P, P, P, SZ, P]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def load() -> ctypes.CDLL:
+    """Loads the library (does not need a GPU; no CUDA call happens at load time)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python -m han_b200.build` "
+            "(han_b200 has no CPU or PyTorch fallback)")
+    lib = ctypes.CDLL(str(_LIB_PATH))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class HanError(RuntimeError):
+    pass
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name: str, *args):
+    """Calls an int-returning entry point; non-zero -> HanError(han_last_error())."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.han_last_error()
+        raise HanError(f"{name} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def query(name: str, *args):
+    """Calls a value-returning entry point (sizes, strides, flags)."""
+    return getattr(load(), name)(*args)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise HanError("han_b200 ops run on CUDA tensors only (no CPU fallback)")

@@ -1,0 +1,347 @@
+// K-D: backward of the fused edge-softmax-aggregate (autodiff of utils/layers.py:26-35,46 as
+// TF would build it via models/base_gattn.py:22, restricted to edges).
+//
+//   dV_i   = dO_i * act'(V_i + bias)                     delta_i = <dV_i, V_i> per head
+//   alpha  = exp(leaky(f1_i + f2_j) - m_i) * rinv_i      (recomputed, never stored)
+//   dl_ij  = alpha_ij (dV_i . S_j - delta_i) * leaky'(f1_i + f2_j)
+//   dS_j   = sum_i alpha_ij dV_i ;  df2_j = sum_i dl_ij   (by source  : transposed structure)
+//   df1_i  = sum_j dl_ij                                  (by destination: CSR order)
+//
+// Design: ONE gather pass, by source.  Everything an edge needs from its destination row lives in
+// one contiguous row record R_i = [dV | f1 | m | rinv | delta] (384 B for K=H=8), so the by-source
+// kernel gathers exactly one record per edge, keeps S_j / f2_j in registers, and emits dl_ij (32 B)
+// to the edge's CSR slot; df1 is then a streaming segmented sum.  No atomics anywhere, so the
+// backward is deterministic.  Algorithmic bytes: 4+4+384+32 per edge by source, 32 per edge by
+// destination, vs 292+328+64 for a two-gather formulation.
+#include "han_common.cuh"
+
+namespace han {
+
+// ---- prep: row-local ---------------------------------------------------------------------------
+template <int K, int H>
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_kernel(const float* __restrict__ dout, int64_t dout_stride, const float* __restrict__ out,
+                     int64_t out_stride, const float* __restrict__ vsave, float* __restrict__ R,
+                     int64_t n_dst, int act, float* __restrict__ dbias_partial) {
+  constexpr int D = K * H;
+  constexpr int RS = D + 4 * K;
+  // thread = (row, head); a block covers 256/K consecutive rows; grid-stride over row tiles
+  const int head = threadIdx.x % K;
+  const int rsub = threadIdx.x / K;
+  constexpr int ROWS = 256 / K;
+  float colsum[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) colsum[h] = 0.f;
+  for (int64_t r0 = (int64_t)blockIdx.x * ROWS; r0 < n_dst; r0 += (int64_t)gridDim.x * ROWS) {
+    const int64_t row = r0 + rsub;
+    if (row < n_dst) {
+      float delta = 0.f;
+#pragma unroll
+      for (int q = 0; q < H / 4; ++q) {
+        float4 g = ldg4_stream(dout + row * dout_stride + head * H + 4 * q);
+        if (act == HAN_ACT_ELU) {
+          // TF EluGrad: outputs < 0 ? grad * (outputs + 1) : grad
+          const float4 o = ldg4_stream(out + row * out_stride + head * H + 4 * q);
+          g.x = o.x < 0.f ? g.x * (o.x + 1.f) : g.x;
+          g.y = o.y < 0.f ? g.y * (o.y + 1.f) : g.y;
+          g.z = o.z < 0.f ? g.z * (o.z + 1.f) : g.z;
+          g.w = o.w < 0.f ? g.w * (o.w + 1.f) : g.w;
+        }
+        const float4 v = ldg4_stream(vsave + row * D + head * H + 4 * q);
+        delta += g.x * v.x + g.y * v.y + g.z * v.z + g.w * v.w;
+        *reinterpret_cast<float4*>(R + row * RS + head * H + 4 * q) = g;
+        colsum[4 * q] += g.x; colsum[4 * q + 1] += g.y; colsum[4 * q + 2] += g.z; colsum[4 * q + 3] += g.w;
+      }
+      R[row * RS + D + 3 * K + head] = delta;
+    }
+  }
+  // block reduce of column sums over the ROWS sub-rows -> dbias_partial[block][D]
+  __shared__ float red[256 * H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) red[(rsub * K + head) * H + h] = colsum[h];
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += 256) {
+    float s = 0.f;
+    for (int r = 0; r < ROWS; ++r) s += red[r * D + c];
+    dbias_partial[(int64_t)blockIdx.x * D + c] = s;
+  }
+}
+
+// ---- by-source gather pass ---------------------------------------------------------------------
+template <int K, int H, int UNROLL>
+__global__ void __launch_bounds__(256)
+attn_bwd_src_kernel(const int64_t* __restrict__ t_indptr, const int32_t* __restrict__ t_indices,
+                    const int32_t* __restrict__ perm, int64_t n_src, const float* __restrict__ Tsrc,
+                    const float* __restrict__ R, float* __restrict__ dS_agg, float* __restrict__ df2,
+                    float* __restrict__ dl_edge) {
+  constexpr int D = K * H;
+  constexpr int TS = ((D + K + 3) / 4) * 4;
+  constexpr int RS = D + 4 * K;
+  constexpr int SLOTS = 32 / K;
+  constexpr int HV = H / 4;
+  const int lane = threadIdx.x & 31;
+  const int head = lane % K, slot = lane / K;
+  const int64_t src = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (src >= n_src) return;
+
+  const int64_t start = t_indptr[src], end = t_indptr[src + 1];
+  float sj[H];
+#pragma unroll
+  for (int q = 0; q < HV; ++q) {
+    const float4 s4 = ldg4(Tsrc + src * TS + head * H + 4 * q);
+    sj[4 * q] = s4.x; sj[4 * q + 1] = s4.y; sj[4 * q + 2] = s4.z; sj[4 * q + 3] = s4.w;
+  }
+  const float f2 = __ldg(Tsrc + src * TS + D + head);
+  float acc[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) acc[h] = 0.f;
+  float df2acc = 0.f;
+
+  for (int64_t base = start; base < end; base += 32) {
+    const int cnt = (int)min((int64_t)32, end - base);
+    const int my_row = (lane < cnt) ? ldg_stream_i32(t_indices + base + lane) : 0;
+    const int my_perm = (lane < cnt) ? ldg_stream_i32(perm + base + lane) : 0;
+    for (int t = 0; t < cnt; t += SLOTS * UNROLL) {
+      float4 g[UNROLL][HV];
+      float f1[UNROLL], mm[UNROLL], ri[UNROLL], de[UNROLL];
+      int pe[UNROLL];
+      bool ok[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int ei = t + u * SLOTS + slot;
+        const int i = __shfl_sync(0xffffffffu, my_row, ei & 31);
+        pe[u] = __shfl_sync(0xffffffffu, my_perm, ei & 31);
+        ok[u] = ei < cnt;
+        if (ok[u]) {
+          const float* rp = R + (int64_t)i * RS;
+#pragma unroll
+          for (int q = 0; q < HV; ++q) g[u][q] = ldg4(rp + head * H + 4 * q);
+          f1[u] = __ldg(rp + D + head);
+          mm[u] = __ldg(rp + D + K + head);
+          ri[u] = __ldg(rp + D + 2 * K + head);
+          de[u] = __ldg(rp + D + 3 * K + head);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (ok[u]) {
+          const float lg = f1[u] + f2;
+          const float a = __expf(leaky(lg) - mm[u]) * ri[u];
+          float da = 0.f;
+#pragma unroll
+          for (int q = 0; q < HV; ++q) {
+            da = fmaf(g[u][q].x, sj[4 * q], da);
+            da = fmaf(g[u][q].y, sj[4 * q + 1], da);
+            da = fmaf(g[u][q].z, sj[4 * q + 2], da);
+            da = fmaf(g[u][q].w, sj[4 * q + 3], da);
+            acc[4 * q] = fmaf(a, g[u][q].x, acc[4 * q]);
+            acc[4 * q + 1] = fmaf(a, g[u][q].y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(a, g[u][q].z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(a, g[u][q].w, acc[4 * q + 3]);
+          }
+          const float dl = a * (da - de[u]) * (lg > 0.f ? 1.f : kLeakySlope);
+          df2acc += dl;
+          dl_edge[(int64_t)pe[u] * K + head] = dl;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int off = K; off < 32; off <<= 1) {
+    df2acc += __shfl_xor_sync(0xffffffffu, df2acc, off);
+#pragma unroll
+    for (int h = 0; h < H; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], off);
+  }
+  if (slot == 0) {
+    df2[src * K + head] = df2acc;
+#pragma unroll
+    for (int q = 0; q < HV; ++q)
+      *reinterpret_cast<float4*>(dS_agg + src * D + head * H + 4 * q) =
+          make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  }
+}
+
+// ---- by-destination segmented sum of dl ---------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256)
+attn_bwd_dst_kernel(const int64_t* __restrict__ indptr, int64_t n_dst, const float* __restrict__ dl_edge,
+                    float* __restrict__ df1) {
+  constexpr int SLOTS = 32 / K;
+  const int lane = threadIdx.x & 31;
+  const int head = lane % K, slot = lane / K;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_dst) return;
+  const int64_t start = indptr[row], end = indptr[row + 1];
+  float s0 = 0.f, s1 = 0.f;
+  int64_t e = start + slot;
+  for (; e + SLOTS < end; e += 2 * SLOTS) {  // 32 lanes read 128 contiguous bytes, 2 in flight
+    s0 += __ldg(dl_edge + e * K + head);
+    s1 += __ldg(dl_edge + (e + SLOTS) * K + head);
+  }
+  if (e < end) s0 += __ldg(dl_edge + e * K + head);
+  float s = s0 + s1;
+#pragma unroll
+  for (int off = K; off < 32; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (slot == 0) df1[row * K + head] = s;
+}
+
+// ---- finish: row-local; dS_tot = dS_agg + df1 a1^T + df2 a2^T and parameter-gradient partials ----
+template <int K, int H>
+__global__ void __launch_bounds__(256)
+attn_bwd_finish_kernel(const float* __restrict__ T, int64_t n, const float* __restrict__ a1,
+                       const float* __restrict__ a2, const float* __restrict__ df1,
+                       const float* __restrict__ df2, float* __restrict__ dS, float* __restrict__ part) {
+  constexpr int D = K * H;
+  constexpr int TS = ((D + K + 3) / 4) * 4;
+  constexpr int ROWS = 256 / K;
+  const int head = threadIdx.x % K;
+  const int rsub = threadIdx.x / K;
+  float a1v[H], a2v[H], da1[H], da2[H];
+  float db1 = 0.f, db2 = 0.f;
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    a1v[h] = a1[head * H + h];
+    a2v[h] = a2[head * H + h];
+    da1[h] = 0.f;
+    da2[h] = 0.f;
+  }
+  for (int64_t r0 = (int64_t)blockIdx.x * ROWS; r0 < n; r0 += (int64_t)gridDim.x * ROWS) {
+    const int64_t row = r0 + rsub;
+    if (row < n) {
+      const float g1 = df1[row * K + head], g2 = df2[row * K + head];
+      db1 += g1;
+      db2 += g2;
+#pragma unroll
+      for (int q = 0; q < H / 4; ++q) {
+        const float4 s = ldg4_stream(T + row * TS + head * H + 4 * q);
+        float4 d = *reinterpret_cast<const float4*>(dS + row * D + head * H + 4 * q);
+        d.x += g1 * a1v[4 * q] + g2 * a2v[4 * q];
+        d.y += g1 * a1v[4 * q + 1] + g2 * a2v[4 * q + 1];
+        d.z += g1 * a1v[4 * q + 2] + g2 * a2v[4 * q + 2];
+        d.w += g1 * a1v[4 * q + 3] + g2 * a2v[4 * q + 3];
+        *reinterpret_cast<float4*>(dS + row * D + head * H + 4 * q) = d;
+        da1[4 * q] += s.x * g1; da1[4 * q + 1] += s.y * g1; da1[4 * q + 2] += s.z * g1; da1[4 * q + 3] += s.w * g1;
+        da2[4 * q] += s.x * g2; da2[4 * q + 1] += s.y * g2; da2[4 * q + 2] += s.z * g2; da2[4 * q + 3] += s.w * g2;
+      }
+    }
+  }
+  // block reduce over rsub -> part[block][ da1 (D) | da2 (D) | db1 (K) | db2 (K) ]
+  constexpr int W = 2 * H + 2;
+  __shared__ float red[256 * W];
+  float* mine = red + (size_t)(rsub * K + head) * W;
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    mine[h] = da1[h];
+    mine[H + h] = da2[h];
+  }
+  mine[2 * H] = db1;
+  mine[2 * H + 1] = db2;
+  __syncthreads();
+  float* dst = part + (int64_t)blockIdx.x * (2 * D + 2 * K);
+  for (int c = threadIdx.x; c < 2 * D + 2 * K; c += 256) {
+    int hd, w;
+    if (c < D) { hd = c / H; w = c % H; }
+    else if (c < 2 * D) { hd = (c - D) / H; w = H + (c - D) % H; }
+    else if (c < 2 * D + K) { hd = c - 2 * D; w = 2 * H; }
+    else { hd = c - 2 * D - K; w = 2 * H + 1; }
+    float s = 0.f;
+    for (int r = 0; r < ROWS; ++r) s += red[(size_t)(r * K + hd) * W + w];
+    dst[c] = s;
+  }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nblocks, int64_t cols,
+                                       float* __restrict__ outv) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * cols + c];
+  outv[c] = s;
+}
+
+}  // namespace han
+
+using namespace han;
+
+#define HAN_FOR_SHAPES(X) X(8, 8) X(4, 8) X(2, 8) X(1, 8) X(8, 4) X(4, 4) X(1, 4) X(8, 16) X(4, 16) X(1, 16) X(16, 4) X(16, 8)
+
+extern "C" {
+
+int han_reduce_blocks(void) { return kReduceBlocks; }
+
+int han_attn_bwd_prep(const float* dout, int64_t dout_stride, const float* out, int64_t out_stride,
+                      const float* vsave, float* R, int64_t n_dst, int K, int H, int act,
+                      float* dbias_partial, han_stream_t stream) {
+  HAN_REQUIRE(dout && out && vsave && R && dbias_partial, "null pointer");
+  HAN_REQUIRE(n_dst > 0, "n_dst > 0 required");
+  HAN_REQUIRE(dout_stride % 4 == 0 && out_stride % 4 == 0, "strides must be multiples of 4 floats");
+#define X(k, h)                                                                                        \
+  if (K == k && H == h) {                                                                              \
+    attn_bwd_prep_kernel<k, h><<<kReduceBlocks, 256, 0, as_stream(stream)>>>(                          \
+        dout, dout_stride, out, out_stride, vsave, R, n_dst, act, dbias_partial);                      \
+    return check_launch(__func__);                                                                     \
+  }
+  HAN_FOR_SHAPES(X)
+#undef X
+  return fail_arg(__func__, "unsupported (K,H)");
+}
+
+int han_attn_bwd_src(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
+                     int64_t n_src, const float* Tsrc, const float* R, int K, int H, float* dS_agg,
+                     float* df2, float* dl_edge, han_stream_t stream) {
+  HAN_REQUIRE(t_indptr && Tsrc && R && dS_agg && df2 && dl_edge, "null pointer");
+  HAN_REQUIRE(n_src > 0, "n_src > 0 required");
+  unsigned grid = (unsigned)ceil_div64(n_src, 8);
+#define X(k, h)                                                                                        \
+  if (K == k && H == h) {                                                                              \
+    constexpr int U = (k >= 8) ? 4 : (k >= 4 ? 2 : 1);                                                 \
+    attn_bwd_src_kernel<k, h, U><<<grid, 256, 0, as_stream(stream)>>>(                                 \
+        t_indptr, t_indices, perm, n_src, Tsrc, R, dS_agg, df2, dl_edge);                              \
+    return check_launch(__func__);                                                                     \
+  }
+  HAN_FOR_SHAPES(X)
+#undef X
+  return fail_arg(__func__, "unsupported (K,H)");
+}
+
+int han_attn_bwd_dst(const int64_t* indptr, int64_t n_dst, const float* dl_edge, int K, float* df1,
+                     han_stream_t stream) {
+  HAN_REQUIRE(indptr && dl_edge && df1, "null pointer");
+  HAN_REQUIRE(n_dst > 0, "n_dst > 0 required");
+  unsigned grid = (unsigned)ceil_div64(n_dst, 8);
+  cudaStream_t st = as_stream(stream);
+  switch (K) {
+    case 1: attn_bwd_dst_kernel<1><<<grid, 256, 0, st>>>(indptr, n_dst, dl_edge, df1); break;
+    case 2: attn_bwd_dst_kernel<2><<<grid, 256, 0, st>>>(indptr, n_dst, dl_edge, df1); break;
+    case 4: attn_bwd_dst_kernel<4><<<grid, 256, 0, st>>>(indptr, n_dst, dl_edge, df1); break;
+    case 8: attn_bwd_dst_kernel<8><<<grid, 256, 0, st>>>(indptr, n_dst, dl_edge, df1); break;
+    case 16: attn_bwd_dst_kernel<16><<<grid, 256, 0, st>>>(indptr, n_dst, dl_edge, df1); break;
+    default: return fail_arg(__func__, "unsupported K");
+  }
+  return check_launch(__func__);
+}
+
+int han_attn_bwd_finish(const float* T, int64_t n, int K, int H, const float* a1, const float* a2,
+                        const float* df1, const float* df2, float* dS, float* part,
+                        han_stream_t stream) {
+  HAN_REQUIRE(T && a1 && a2 && df1 && df2 && dS && part, "null pointer");
+  HAN_REQUIRE(n > 0, "n > 0 required");
+#define X(k, h)                                                                                        \
+  if (K == k && H == h) {                                                                              \
+    attn_bwd_finish_kernel<k, h><<<kReduceBlocks, 256, 0, as_stream(stream)>>>(T, n, a1, a2, df1, df2, \
+                                                                               dS, part);              \
+    return check_launch(__func__);                                                                     \
+  }
+  HAN_FOR_SHAPES(X)
+#undef X
+  return fail_arg(__func__, "unsupported (K,H)");
+}
+
+int han_reduce_partials(const float* part, int nblocks, int64_t cols, float* outv, han_stream_t stream) {
+  HAN_REQUIRE(part && outv, "null pointer");
+  HAN_REQUIRE(nblocks > 0 && cols > 0, "sizes");
+  reduce_partials_kernel<<<(unsigned)ceil_div64(cols, 128), 128, 0, as_stream(stream)>>>(part, nblocks, cols, outv);
+  return check_launch(__func__);
+}
+
+}  // extern "C"

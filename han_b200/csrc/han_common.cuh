@@ -1,0 +1,67 @@
+// Shared helpers for libhan_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "han_b200.h"
+
+namespace han {
+
+constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs
+constexpr int kReduceBlocks = 148 * 4;  // fixed grid for deterministic two-stage reductions
+constexpr float kLeakySlope = 0.2f;   // tf.nn.leaky_relu default (utils/layers.py:27)
+
+extern thread_local char g_last_error[512];
+
+inline int fail_arg(const char* fn, const char* what) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s: invalid argument: %s", fn, what);
+  return -1;
+}
+
+inline int check_launch(const char* fn) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_last_error, sizeof(g_last_error), "%s: CUDA error %d (%s)", fn, (int)e,
+             cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+#define HAN_REQUIRE(cond, what)                  \
+  do {                                           \
+    if (!(cond)) return han::fail_arg(__func__, what); \
+  } while (0)
+
+inline cudaStream_t as_stream(han_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers --------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+// streaming (read-once) 128-bit load that does not allocate in L1
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int ldg_stream_i32(const int* p) {
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeakySlope * x; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace han

@@ -1,0 +1,191 @@
+"""Meta-path graph handle: the CSR (and lazily its transpose) that replaces the reference's dense
+``bias_mat`` (utils/process.py:14-25, fed as (1,N,N) fp32 every step at ex_acm3025.py:180-181).
+
+Built on the device by the K-0 kernels; bit-exact against ``np.nonzero(bias == 0)``.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, query, stream_ptr
+
+
+def _dev(device=None) -> torch.device:
+    if device is not None:
+        return torch.device(device)
+    if not torch.cuda.is_available():
+        raise _lib.HanError("han_b200 needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _as_device_tensor(a, device, dtype=None) -> torch.Tensor:
+    if isinstance(a, np.ndarray):
+        a = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and a.dtype != dtype:
+        a = a.to(dtype)
+    return a.to(device, non_blocking=True).contiguous()
+
+
+class MetaPathGraph:
+    """CSR of one meta-path mask.  Rows = destination nodes i (softmax rows of
+    utils/layers.py:27), columns = source nodes j; columns ascending within a row.
+
+    ``row_offset``: global id of local row 0 when this is a destination-row shard.
+    """
+
+    def __init__(self, indptr: torch.Tensor, indices: torch.Tensor, n_rows: int, n_cols: int,
+                 nnz: Optional[int] = None, row_offset: int = 0):
+        assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
+        assert indptr.is_cuda and indices.is_cuda
+        self.indptr = indptr
+        self.indices = indices
+        self.n_rows = int(n_rows)
+        self.n_cols = int(n_cols)
+        self.nnz = int(indices.numel() if nnz is None else nnz)
+        self.row_offset = int(row_offset)
+        self._t: Optional["MetaPathGraph"] = None
+        self.perm: Optional[torch.Tensor] = None  # set on the transposed view
+        self._empty_rows: Optional[bool] = None
+
+    # the reference hands around a (1,N,N) array; keep that visible for call-site compatibility
+    @property
+    def shape(self):
+        return (1, self.n_rows, self.n_cols)
+
+    @property
+    def device(self):
+        return self.indptr.device
+
+    def has_empty_rows(self) -> bool:
+        """Rows without any edge (the dense path turns those into uniform 1/N rows)."""
+        if self._empty_rows is None:
+            d = self.indptr[1:] - self.indptr[:-1]
+            self._empty_rows = bool((d == 0).any().item())
+        return self._empty_rows
+
+    # ---- constructors -----------------------------------------------------------------------
+    @staticmethod
+    def _from_dense(dense, kind: int, device=None) -> "MetaPathGraph":
+        device = _dev(device)
+        if isinstance(dense, np.ndarray):
+            dense = torch.from_numpy(np.ascontiguousarray(dense))
+        if dense.dim() == 3:
+            if dense.shape[0] != 1:
+                raise ValueError("one graph per call: expected (1,N,N) or (N,N)")
+            dense = dense[0]
+        if dense.dim() != 2 or dense.shape[0] != dense.shape[1]:
+            raise ValueError(f"expected a square matrix, got {tuple(dense.shape)}")
+        if dense.dtype not in (torch.float32, torch.float64):
+            dense = dense.to(torch.float64)
+        dense = dense.to(device).contiguous()
+        dt = _lib.F32 if dense.dtype == torch.float32 else _lib.F64
+        n = dense.shape[0]
+        with torch.cuda.device(device):
+            counts = torch.empty(n, dtype=torch.int32, device=device)
+            bad = torch.zeros(1, dtype=torch.int32, device=device)
+            call("han_dense_row_counts", ptr(dense), dt, kind, n, n, ptr(counts), ptr(bad), stream_ptr())
+            indptr = torch.empty(n + 1, dtype=torch.int64, device=device)
+            ws_bytes = query("han_scan_workspace_bytes", n)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            call("han_scan_counts", ptr(counts), n, ptr(indptr), ptr(ws), ws_bytes, stream_ptr())
+            nnz, nbad = int(indptr[-1].item()), int(bad.item())  # build-time sync (not in the step)
+            if kind == _lib.DENSE_BIAS and nbad:
+                raise ValueError(
+                    f"bias_mat has {nbad} entries that are neither 0 nor <= -1e8: only the reference's "
+                    "mask biases (utils/process.py:25) are supported")
+            indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=device)[:nnz]
+            if nnz:
+                call("han_dense_fill_indices", ptr(dense), dt, kind, n, n, ptr(indptr), ptr(indices),
+                     stream_ptr())
+        return MetaPathGraph(indptr, indices, n, n, nnz)
+
+    @staticmethod
+    def from_dense_adj(adj, nhood: int = 1, device=None) -> "MetaPathGraph":
+        """``adj_to_bias(adj, [N], nhood)`` semantics (utils/process.py:14-25): edge (i,j) iff
+        ((adj + I)^nhood)_ij > 0.  nhood == 1 is evaluated in one pass by the K-0 kernels; for
+        nhood > 1 the fp64 matrix power of the reference (:19-20) is taken on the device first."""
+        if nhood < 1:
+            # reference: zero loop iterations leave mt = I -> only self-loops
+            raise ValueError("nhood must be >= 1")
+        if nhood == 1:
+            return MetaPathGraph._from_dense(adj, _lib.DENSE_ADJ, device)
+        device = _dev(device)
+        a = _as_device_tensor(adj, device, torch.float64)
+        if a.dim() == 3:
+            a = a[0]
+        eye = torch.eye(a.shape[0], dtype=torch.float64, device=device)
+        mt = eye.clone()
+        for _ in range(nhood):
+            mt = mt @ (a + eye)
+        return MetaPathGraph._from_dense(mt, _lib.DENSE_POSITIVE, device)  # :21-24: mt > 0
+
+    @staticmethod
+    def from_dense_bias(bias, device=None) -> "MetaPathGraph":
+        """From a reference bias matrix (values 0 / -1e9, (1,N,N) or (N,N))."""
+        return MetaPathGraph._from_dense(bias, _lib.DENSE_BIAS, device)
+
+    @staticmethod
+    def from_csr(indptr, indices, n_cols: Optional[int] = None, device=None, sort: bool = False,
+                 row_offset: int = 0) -> "MetaPathGraph":
+        """From host or device CSR arrays.  ``sort=True`` sorts columns within rows on the device
+        and rejects duplicate edges."""
+        device = _dev(device)
+        indptr = _as_device_tensor(indptr, device, torch.int64)
+        indices = _as_device_tensor(indices, device, torch.int32)
+        n_rows = indptr.numel() - 1
+        if n_cols is None:
+            n_cols = n_rows
+        g = MetaPathGraph(indptr, indices, n_rows, n_cols, row_offset=row_offset)
+        if sort and g.nnz:
+            with torch.cuda.device(device):
+                scratch = torch.zeros(n_rows + 64, dtype=torch.int32, device=device)
+                dup = torch.zeros(1, dtype=torch.int32, device=device)
+                call("han_csr_sort_rows", n_rows, ptr(indptr), ptr(indices), None, ptr(scratch), ptr(dup),
+                     stream_ptr())
+                if int(dup.item()):
+                    raise ValueError(f"{int(dup.item())} duplicate edges in CSR input")
+        return g
+
+    # ---- derived structures -----------------------------------------------------------------
+    def transpose(self) -> "MetaPathGraph":
+        """By-source view: row j lists the destinations i of edges (i,j), ascending, with
+        ``perm`` = position of that edge in this CSR.  Built once, cached."""
+        if self._t is None:
+            device = self.device
+            with torch.cuda.device(device):
+                t_indptr = torch.empty(self.n_cols + 1, dtype=torch.int64, device=device)
+                t_indices = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=device)[:self.nnz]
+                perm = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=device)[:self.nnz]
+                ws_bytes = query("han_transpose_workspace_bytes", self.n_rows, self.n_cols, self.nnz)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+                call("han_csr_transpose", self.n_rows, self.n_cols, self.nnz, ptr(self.indptr),
+                     ptr(self.indices), ptr(t_indptr), ptr(t_indices), ptr(perm), ptr(ws), ws_bytes,
+                     stream_ptr())
+            t = MetaPathGraph(t_indptr, t_indices, self.n_cols, self.n_rows, self.nnz)
+            t.perm = perm
+            self._t = t
+        return self._t
+
+    def row_slice(self, lo: int, hi: int) -> "MetaPathGraph":
+        """Destination-row shard [lo, hi) (column ids stay global)."""
+        base = int(self.indptr[lo].item())
+        end = int(self.indptr[hi].item())
+        indptr = (self.indptr[lo:hi + 1] - base).contiguous()
+        indices = self.indices[base:end].contiguous()
+        return MetaPathGraph(indptr, indices, hi - lo, self.n_cols, end - base, row_offset=lo)
+
+    # ---- host views (tests / debugging) -------------------------------------------------------
+    def to_host(self):
+        return self.indptr.cpu().numpy(), self.indices.cpu().numpy()
+
+    def to_dense_bias(self, dtype=np.float32) -> np.ndarray:
+        """The (1,N,N) bias matrix the reference would feed: 0 on edges, -1e9 elsewhere."""
+        indptr, indices = self.to_host()
+        b = np.full((self.n_rows, self.n_cols), -1e9, dtype=dtype)
+        rows = np.repeat(np.arange(self.n_rows), np.diff(indptr))
+        b[rows, indices] = 0.0
+        return b[None]

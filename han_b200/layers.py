@@ -1,0 +1,137 @@
+"""Drop-in counterparts of the reference's ``utils/layers.py`` operators, on CUDA tensors.
+
+``attn_head`` (utils/layers.py:7-46) and ``SimpleAttLayer`` (utils/layers.py:132-164) keep the
+reference's names, positional order and argument meaning.  Differences forced by the move from a
+TF1 graph to eager PyTorch are keyword-only: ``params=`` (the variables TF would create
+implicitly) and, for ``bias_mat``, that a ``MetaPathGraph`` (from ``process.adj_to_bias``) is
+accepted next to the dense (1,N,N) reference bias.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .graph import MetaPathGraph
+
+
+def elu(x):
+    """Marker for tf.nn.elu (the kernel applies it in its epilogue)."""
+    return torch.nn.functional.elu(x)
+
+
+def identity(x):
+    return x
+
+
+class EdgeCoefs:
+    """Attention coefficients restricted to edges: what ``return_coef=True`` yields
+    (utils/layers.py:43-44) without the N x N zeros.  ``to_dense()`` gives the reference layout."""
+
+    def __init__(self, graph: MetaPathGraph, alpha: torch.Tensor):
+        self.graph = graph
+        self.alpha = alpha  # (nnz, K)
+
+    def to_dense(self, head: int = 0) -> torch.Tensor:
+        n, m = self.graph.n_rows, self.graph.n_cols
+        deg = (self.graph.indptr[1:] - self.graph.indptr[:-1])
+        rows = torch.repeat_interleave(torch.arange(n, device=self.alpha.device), deg)
+        out = torch.zeros(n, m, dtype=self.alpha.dtype, device=self.alpha.device)
+        out[rows, self.graph.indices.long()] = self.alpha[:, head]
+        return out.unsqueeze(0)
+
+
+def as_graph(bias_mat, device=None) -> MetaPathGraph:
+    """Accepts what reference call sites pass as ``bias_mat``: a MetaPathGraph, or a dense
+    (1,N,N)/(N,N) bias (numpy or torch) with 0 on edges and -1e9 elsewhere."""
+    if isinstance(bias_mat, MetaPathGraph):
+        return bias_mat
+    return MetaPathGraph.from_dense_bias(bias_mat, device=device)
+
+
+def _squeeze_batch(seq: torch.Tensor) -> torch.Tensor:
+    if seq.dim() == 3:
+        if seq.shape[0] != 1:
+            raise ValueError("batch_size must be 1 (the whole graph), as in ex_acm3025.py:21")
+        return seq[0]
+    return seq
+
+
+def new_head_params(F: int, H: int, device, generator=None) -> Dict[str, torch.nn.Parameter]:
+    """The variables one ``attn_head`` call creates (layers.py:20,23,24,35) with TF's default
+    initialisers: glorot-uniform kernels, zero biases."""
+    def glorot(shape, fi, fo):
+        lim = math.sqrt(6.0 / (fi + fo))
+        return torch.empty(shape).uniform_(-lim, lim, generator=generator).to(device)
+    mk = torch.nn.Parameter
+    return {"W": mk(glorot((F, H), F, H)), "a1": mk(glorot((H,), H, 1)), "b1": mk(torch.zeros((), device=device)),
+            "a2": mk(glorot((H,), H, 1)), "b2": mk(torch.zeros((), device=device)),
+            "bias": mk(torch.zeros(H, device=device))}
+
+
+def attn_head(seq, out_sz, bias_mat, activation, in_drop=0.0, coef_drop=0.0, residual=False,
+              return_coef=False, *, params: Optional[Dict[str, torch.Tensor]] = None):
+    """One attention head (utils/layers.py:7-46): ``activation(softmax(leaky_relu(f1 + f2^T) +
+    bias_mat) @ (seq W) + bias)``, evaluated over the edges of ``bias_mat`` only.
+
+    seq (1,N,F) fp32 CUDA; returns (1,N,out_sz) [and EdgeCoefs when ``return_coef``].
+    ``params``: dict W (F,H), a1 (H,), b1 (), a2 (H,), b2 (), bias (H,); created with the
+    reference initialisers when omitted and returned as ``attn_head.last_params``.
+    """
+    if in_drop != 0.0 or coef_drop != 0.0:
+        raise NotImplementedError("dropout inside attn_head (layers.py:18-19,29-32) is not built yet; "
+                                  "run with in_drop = coef_drop = 0.0")
+    if residual:
+        raise NotImplementedError("residual=True (layers.py:38-42) needs the input-gradient path; not built yet")
+    x = _squeeze_batch(seq)
+    _lib.require_cuda(x)
+    graph = as_graph(bias_mat, x.device)
+    H = int(out_sz)
+    if params is None:
+        params = new_head_params(x.shape[1], H, x.device)
+    attn_head.last_params = params
+    plan = ops.NodeAttentionPlan(graphs=[graph], K=1, H=H, act=ops.activation_code(activation),
+                                 want_coefs=bool(return_coef))
+    Z = ops.node_attention(plan, x, params["W"], params["a1"].reshape(1, 1, H), params["b1"].reshape(1, 1),
+                           params["a2"].reshape(1, 1, H), params["b2"].reshape(1, 1),
+                           params["bias"].reshape(1, H))
+    ret = Z.reshape(1, x.shape[0], H)
+    if return_coef:
+        return ret, EdgeCoefs(graph, plan.coefs[0])
+    return ret
+
+
+attn_head.last_params = None
+
+
+def SimpleAttLayer(inputs, attention_size, time_major=False, return_alphas=False, *,
+                   params: Optional[Dict[str, torch.Tensor]] = None, mode: str = "reference", dist=None):
+    """Semantic-level attention (utils/layers.py:132-164).  inputs (N,P,D) -> (N,D) [+ alphas (N,P)].
+
+    ``mode="reference"`` is the shipped per-node softmax over meta-paths (:156);
+    ``mode="paper"`` averages the scores over all nodes first (han.pdf Eq. 7-9).
+    """
+    if isinstance(inputs, tuple):                       # :134-136
+        inputs = torch.cat(inputs, 2)
+    if time_major:                                      # :138-140
+        inputs = inputs.transpose(0, 1)
+    _lib.require_cuda(inputs)
+    D = inputs.shape[2]
+    if params is None:
+        dev = inputs.device
+        params = {"w_omega": torch.nn.Parameter((torch.randn(D, attention_size) * 0.1).to(dev)),   # :145
+                  "b_omega": torch.nn.Parameter((torch.randn(attention_size) * 0.1).to(dev)),      # :146
+                  "u_omega": torch.nn.Parameter((torch.randn(attention_size) * 0.1).to(dev))}      # :147
+    SimpleAttLayer.last_params = params
+    assert params["w_omega"].shape == (D, attention_size)
+    out, alphas = ops.semantic_attention(inputs, params["w_omega"], params["b_omega"], params["u_omega"],
+                                         mode=mode, dist=dist)
+    if not return_alphas:
+        return out
+    return out, alphas
+
+
+SimpleAttLayer.last_params = None

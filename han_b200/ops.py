@@ -1,0 +1,234 @@
+"""PyTorch ``autograd.Function`` wrappers over the C-ABI kernels (include/han_b200.h).
+
+PyTorch supplies device memory, streams and autograd plumbing only; every arithmetic step of the
+hot path runs in libhan_sm100.so.  Nothing here falls back to PyTorch math.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, query, stream_ptr
+from .graph import MetaPathGraph
+
+_ACT = {"elu": _lib.ACT_ELU, "identity": _lib.ACT_IDENTITY}
+
+
+def _empty(shape, device, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+@dataclass
+class NodeAttentionPlan:
+    """Static description of one group of G meta-paths that share the input features X."""
+    graphs: Sequence[MetaPathGraph]        # G destination-row CSRs (local rows, global column ids)
+    K: int
+    H: int
+    act: int = _lib.ACT_ELU
+    project_mode: int = 0                  # 0 fp32 FFMA, 1 tcgen05 3xTF32, 2 tcgen05 TF32
+    dist: Optional[object] = None          # han_b200.dist.RowShard when sharded over GPUs
+    want_coefs: bool = False
+    coefs: List[torch.Tensor] = field(default_factory=list)   # filled by forward when want_coefs
+
+    @property
+    def G(self):
+        return len(self.graphs)
+
+    @property
+    def D(self):
+        return self.K * self.H
+
+
+class NodeAttentionFn(torch.autograd.Function):
+    """Z[n, g, :] = concat_k attn_head_k(X, graph_g)  (utils/layers.py:7-46 x K heads, and the
+    concat / stack of models/gat.py:46,58,60) for the G meta-paths of one plan.
+
+    Inputs: X (n,F); W (F, G*D); a1,a2 (G,K,H); b1,b2 (G,K); bias (G,D).  Output Z (n,G,D).
+    Dropout-free (ffd_drop = attn_drop = 0), residual=False: the shipped HAN configuration.
+    """
+
+    @staticmethod
+    def forward(ctx, plan: NodeAttentionPlan, X, W, a1, b1, a2, b2, bias):
+        _lib.require_cuda(X, W, a1, b1, a2, b2, bias)
+        G, K, H, D = plan.G, plan.K, plan.H, plan.D
+        if not query("han_attn_shape_supported", K, H):
+            raise _lib.HanError(f"(K,H)=({K},{H}) is not instantiated in libhan_sm100.so")
+        X = X.contiguous()
+        W, a1, b1, a2, b2, bias = (t.contiguous() for t in (W, a1, b1, a2, b2, bias))
+        n, F = X.shape
+        assert W.shape == (F, G * D) and a1.shape == (G, K, H) and bias.shape == (G, D)
+        dev = X.device
+        TS, RS = query("han_table_stride", K, H), query("han_record_stride", K, H)
+        dist = plan.dist
+        with torch.cuda.device(dev):
+            T = _empty((G, n, TS), dev)
+            R = _empty((G, n, RS), dev)
+            call("han_project_fwd", ptr(X), n, F, X.stride(0), ptr(W), G, K, H, ptr(a1), ptr(b1), ptr(a2),
+                 ptr(b2), ptr(T), ptr(R), plan.project_mode, stream_ptr())
+            # sources of every local destination row: all-gather the node tables when sharded
+            T_src = dist.all_gather_rows(T) if dist is not None else T
+            Z = _empty((n, G, D), dev)
+            V = _empty((G, n, D), dev)
+            plan.coefs = []
+            for g, graph in enumerate(plan.graphs):
+                assert graph.n_rows == n, "graph rows must match the local rows of X"
+                colmean = None
+                if graph.has_empty_rows():
+                    # dense-path semantics of an all -1e9 row: uniform 1/N over all nodes
+                    colmean = T_src[g][:, :D].mean(0).contiguous()
+                call("han_attn_fwd", ptr(graph.indptr), ptr(graph.indices), n, ptr(T_src[g]), ptr(R[g]),
+                     ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D, ptr(V[g]), ptr(colmean),
+                     stream_ptr())
+                if plan.want_coefs:
+                    alpha = _empty((graph.nnz, K), dev)
+                    if graph.nnz:
+                        call("han_attn_coefs", ptr(graph.indptr), ptr(graph.indices), n, ptr(T_src[g]),
+                             ptr(R[g]), K, H, ptr(alpha), stream_ptr())
+                    plan.coefs.append(alpha)
+        ctx.plan = plan
+        ctx.save_for_backward(X, a1, a2, T, R, V, Z)
+        ctx.mark_non_differentiable()
+        return Z
+
+    @staticmethod
+    def backward(ctx, dZ):
+        plan: NodeAttentionPlan = ctx.plan
+        X, a1, a2, T, R, V, Z = ctx.saved_tensors
+        G, K, H, D = plan.G, plan.K, plan.H, plan.D
+        n, F = X.shape
+        dev = X.device
+        dist = plan.dist
+        dZ = dZ.contiguous()
+        NB = query("han_reduce_blocks")
+        with torch.cuda.device(dev):
+            dS = _empty((G, n, D), dev)
+            df2 = _empty((n, K), dev)
+            part_bias = _empty((NB, D), dev)
+            part_par = _empty((NB, 2 * D + 2 * K), dev)
+            dbias = _empty((G, D), dev)
+            dpar = _empty((G, 2 * D + 2 * K), dev)
+            max_nnz = max([g.nnz for g in plan.graphs] + [1])
+            for g, graph in enumerate(plan.graphs):
+                if graph.has_empty_rows():
+                    raise _lib.HanError("backward through rows without any edge is not supported "
+                                        "(adj_to_bias always inserts self-loops)")
+                call("han_attn_bwd_prep", ptr(dZ[:, g, :]), G * D, ptr(Z[:, g, :]), G * D, ptr(V[g]),
+                     ptr(R[g]), n, K, H, plan.act, ptr(part_bias), stream_ptr())
+                call("han_reduce_partials", ptr(part_bias), NB, D, ptr(dbias[g]), stream_ptr())
+                if dist is None:
+                    gt = graph.transpose()
+                    dl = _empty((max(graph.nnz, 1), K), dev)
+                    df1 = _empty((n, K), dev)
+                    call("han_attn_bwd_src", ptr(gt.indptr), ptr(gt.indices), ptr(gt.perm), n, ptr(T[g]),
+                         ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(dl), stream_ptr())
+                    call("han_attn_bwd_dst", ptr(graph.indptr), n, ptr(dl), K, ptr(df1), stream_ptr())
+                    del dl
+                else:
+                    df1 = dist.backward_edges(plan, g, T[g], R[g], dS[g], df2)
+                call("han_attn_bwd_finish", ptr(T[g]), n, K, H, ptr(a1[g]), ptr(a2[g]), ptr(df1), ptr(df2),
+                     ptr(dS[g]), ptr(part_par), stream_ptr())
+                call("han_reduce_partials", ptr(part_par), NB, 2 * D + 2 * K, ptr(dpar[g]), stream_ptr())
+            dW = _empty((F, G * D), dev)
+            ws_bytes = query("han_project_bwd_workspace_bytes", n, F, G, D)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            call("han_project_bwd", ptr(X), n, F, X.stride(0), ptr(dS), G, D, ptr(dW), ptr(ws), ws_bytes,
+                 plan.project_mode, stream_ptr())
+        da1 = dpar[:, :D].reshape(G, K, H)
+        da2 = dpar[:, D:2 * D].reshape(G, K, H)
+        db1 = dpar[:, 2 * D:2 * D + K]
+        db2 = dpar[:, 2 * D + K:]
+        if ctx.needs_input_grad[1]:
+            raise _lib.HanError("gradient w.r.t. the input features is not implemented "
+                                "(single attention layer: hid_units=[8], models/gat.py:48-57 unused)")
+        return None, None, dW, da1, db1, da2, db2, dbias
+
+
+class SemanticAttentionFn(torch.autograd.Function):
+    """``SimpleAttLayer`` (utils/layers.py:132-164): (out (n,D), beta (n,P)) from Z (n,P,D)."""
+
+    @staticmethod
+    def forward(ctx, Z, w, b, u, mode: int, dist):
+        _lib.require_cuda(Z, w, b, u)
+        Z, w, b, u = Z.contiguous(), w.contiguous(), b.contiguous(), u.contiguous()
+        n, P, D = Z.shape
+        A = w.shape[1]
+        if not query("han_semantic_shape_supported", D, A):
+            raise _lib.HanError(f"(D,A)=({D},{A}) is not instantiated in libhan_sm100.so")
+        dev = Z.device
+        with torch.cuda.device(dev):
+            out = _empty((n, D), dev)
+            beta = _empty((n, P), dev)
+            vsave = _empty((n * P, A), dev)
+            if mode == _lib.SEM_REFERENCE:
+                call("han_semantic_fwd", ptr(Z), n, P, D, A, ptr(w), ptr(b), ptr(u), mode, ptr(out),
+                     ptr(beta), ptr(vsave), None, stream_ptr())
+                beta_vec = None
+            else:
+                scores = _empty((n, P), dev)
+                call("han_semantic_fwd", ptr(Z), n, P, D, A, ptr(w), ptr(b), ptr(u), mode, None, None,
+                     ptr(vsave), ptr(scores), stream_ptr())
+                ssum = scores.sum(0)
+                n_total = n
+                if dist is not None:
+                    ssum, n_total = dist.all_reduce_sum(ssum), dist.n_total
+                beta_vec = torch.softmax(ssum / n_total, dim=0).contiguous()   # han.pdf Eq. 8 (P scalars)
+                call("han_semantic_combine", ptr(Z), n, P, D, ptr(beta_vec), ptr(out), ptr(beta),
+                     stream_ptr())
+                ctx.n_total = n_total
+        ctx.mode, ctx.dist = mode, dist
+        ctx.save_for_backward(Z, w, u, beta, vsave, beta_vec if beta_vec is not None else beta)
+        ctx.mark_non_differentiable(beta)
+        return out, beta
+
+    @staticmethod
+    def backward(ctx, dout, _dbeta):
+        Z, w, u, beta, vsave, beta_vec = ctx.saved_tensors
+        n, P, D = Z.shape
+        A = w.shape[1]
+        dev = Z.device
+        dout = dout.contiguous()
+        with torch.cuda.device(dev):
+            dsbar = None
+            if ctx.mode == _lib.SEM_PAPER:
+                # d s_bar_p = beta_p (g_p - sum_q beta_q g_q), g_p = sum_n <dout[n], Z[n,p]>; P scalars
+                gp = torch.einsum("nd,npd->p", dout, Z)
+                if ctx.dist is not None:
+                    gp = ctx.dist.all_reduce_sum(gp)
+                dsbar = (beta_vec * (gp - (beta_vec * gp).sum()) / ctx.n_total).contiguous()
+            dZ = _empty((n, P, D), dev)
+            dw, db, du = _empty((D, A), dev), _empty((A,), dev), _empty((A,), dev)
+            ws_bytes = query("han_semantic_bwd_workspace_bytes", P, D, A)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            call("han_semantic_bwd", ptr(dout), ptr(Z), ptr(beta), ptr(vsave), n, P, D, A, ptr(w), ptr(u),
+                 ctx.mode, ptr(dsbar), ptr(dZ), ptr(dw), ptr(db), ptr(du), ptr(ws), ws_bytes, stream_ptr())
+        return dZ, dw, db, du, None, None
+
+
+def node_attention(plan: NodeAttentionPlan, X, W, a1, b1, a2, b2, bias) -> torch.Tensor:
+    return NodeAttentionFn.apply(plan, X, W, a1, b1, a2, b2, bias)
+
+
+def semantic_attention(Z, w, b, u, mode: str = "reference", dist=None):
+    m = {"reference": _lib.SEM_REFERENCE, "paper": _lib.SEM_PAPER}[mode]
+    return SemanticAttentionFn.apply(Z, w, b, u, m, dist)
+
+
+def activation_code(activation) -> int:
+    """Maps the reference's ``activation`` argument (tf.nn.elu or ``lambda x: x``,
+    models/gat.py:10,28) to the kernel's epilogue selector."""
+    if activation is None:
+        return _lib.ACT_IDENTITY
+    if isinstance(activation, str):
+        return _ACT[activation]
+    name = getattr(activation, "__name__", "")
+    if name in ("elu", "elu_"):
+        return _lib.ACT_ELU
+    if name in ("identity", "<lambda>"):
+        # the reference's only lambda is the identity (models/gat.py:28); verify on a probe
+        probe = torch.tensor([-1.5, 0.0, 2.0])
+        if torch.equal(activation(probe), probe):
+            return _lib.ACT_IDENTITY
+    raise _lib.HanError(f"unsupported activation {activation!r}: elu or identity")

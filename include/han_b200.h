@@ -1,0 +1,162 @@
+/*
+ * han_b200.h — C-ABI of libhan_sm100.so: the B200 (sm_100a) implementation of the HAN
+ * node-level + semantic-level attention hot path.
+ *
+ * The reference (CG-Labs/HAN) has no FFI: its "operator API" is four Python callables that build
+ * TF1 graph nodes.  Each entry point below names the reference lines it replaces; the Python host
+ * (han_b200/) binds these through ctypes and exposes the reference's own names.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes.  All pointers are DEVICE pointers unless named host_*.
+ *  - The caller owns every buffer; the library never allocates, frees or synchronises.
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*).
+ *  - Return value: 0 = ok, <0 = invalid argument, >0 = cudaError_t.  han_last_error() returns a
+ *    thread-local message for the last non-zero return.
+ *  - fp32 row-major everywhere; CSR = int64 indptr[n+1] + int32 indices[nnz], columns ascending.
+ *  - K = heads, H = hidden units per head, D = K*H.  Supported (K,H): see han_attn_shape_supported.
+ *  - Node table T: [n][TS] fp32, TS = han_table_stride(K,H) = roundup(D + K, 4):
+ *        T[j][0:D]   = S_j  = X_j W           (utils/layers.py:20)
+ *        T[j][D:D+K] = f2_j = S_j a2 + b2     (utils/layers.py:24)
+ *  - Row record R: [n][RS] fp32, RS = D + 4K:  [ dV (D) | f1 (K) | m (K) | rinv (K) | delta (K) ]
+ *        f1 = S a1 + b1 (utils/layers.py:23), m/rinv = softmax row max / 1/rowsum (:27),
+ *        dV, delta are filled by the backward.
+ */
+#ifndef HAN_B200_H
+#define HAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* han_stream_t; /* cudaStream_t */
+
+enum { HAN_ACT_IDENTITY = 0, HAN_ACT_ELU = 1 };          /* models/gat.py:10,28 */
+enum { HAN_SEM_REFERENCE = 0, HAN_SEM_PAPER = 1 };        /* utils/layers.py:156 vs han.pdf Eq.7-9 */
+enum { HAN_DENSE_ADJ = 0, HAN_DENSE_BIAS = 1, HAN_DENSE_POSITIVE = 2 }; /* meaning of a dense N x N input */
+enum { HAN_F32 = 0, HAN_F64 = 1 };
+
+int han_version(void);
+const char* han_last_error(void);
+int han_attn_shape_supported(int K, int H);
+int han_table_stride(int K, int H);
+int han_record_stride(int K, int H);
+
+/* ---- K-0: graph builder. Replaces utils/process.py:14-25 (adj_to_bias) --------------------- */
+
+/* Row counts of the mask of a dense n x n matrix (leading dimension ld, dtype HAN_F32/HAN_F64).
+ *   HAN_DENSE_ADJ : entry (i,j) is an edge iff adj[i][j] + (i==j) > 0   (process.py:20,23 with nhood=1)
+ *   HAN_DENSE_BIAS: entry is an edge iff bias[i][j] == 0 (what -1e9*(1-mt) leaves, process.py:25);
+ *                   *bad_count receives the number of entries that are neither 0 nor <= -1e8.
+ *   HAN_DENSE_POSITIVE: entry is an edge iff value > 0 (an already-formed mt, process.py:21-24; nhood > 1)
+ * row_counts[n] int32.  bad_count may be NULL for HAN_DENSE_ADJ. */
+int han_dense_row_counts(const void* dense, int dtype, int kind, int64_t n, int64_t ld,
+                         int32_t* row_counts, int32_t* bad_count, han_stream_t stream);
+
+/* Exclusive scan int32 counts[n] -> int64 indptr[n+1].  ws: han_scan_workspace_bytes(n). */
+size_t han_scan_workspace_bytes(int64_t n);
+int han_scan_counts(const int32_t* counts, int64_t n, int64_t* indptr, void* ws, size_t ws_bytes,
+                    han_stream_t stream);
+
+/* Column indices in ascending order per row == np.nonzero(mask) order. */
+int han_dense_fill_indices(const void* dense, int dtype, int kind, int64_t n, int64_t ld,
+                           const int64_t* indptr, int32_t* indices, han_stream_t stream);
+
+/* Transposed structure (CSC of the same pattern) + edge permutation: for transposed edge t,
+ * t_indices[t] = destination row i, perm[t] = position of edge (i,j) in the CSR.  Rows ascending
+ * within each column, so the result is deterministic.  ws: han_transpose_workspace_bytes. */
+size_t han_transpose_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t nnz);
+int han_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr,
+                      const int32_t* indices, int64_t* t_indptr, int32_t* t_indices, int32_t* perm,
+                      void* ws, size_t ws_bytes, han_stream_t stream);
+
+/* Sort helper for COO-built graphs: sorts each row's columns ascending in place (payload, nullable,
+ * follows its key) and writes to *dup_count the number of adjacent duplicates (callers dedupe on
+ * their side).  scratch: int32[n_rows + 64]. */
+int han_csr_sort_rows(int64_t n_rows, const int64_t* indptr, int32_t* indices, int32_t* payload,
+                      int32_t* scratch, int32_t* dup_count, han_stream_t stream);
+
+/* ---- K-A: projection. Replaces utils/layers.py:20,23,24 for G groups of K heads at once ----- */
+/* X [n][ldx] (F columns used), W [F][G*D] (meta-path g, head k in columns g*D + k*H ...),
+ * a1,a2 [G][K][H], b1,b2 [G][K].  Writes T [G][n][TS] and f1 into R[g][:, D:D+K] (R [G][n][RS]).
+ * mode: 0 = fp32 CUDA-core FFMA; 1 = tcgen05 3xTF32 (fp32-grade); 2 = tcgen05 1xTF32. */
+int han_project_fwd(const float* X, int64_t n, int64_t F, int64_t ldx, const float* W, int G, int K,
+                    int H, const float* a1, const float* b1, const float* a2, const float* b2,
+                    float* T, float* R, int mode, han_stream_t stream);
+
+/* dW [F][G*D] = X^T dS  (split over rows + deterministic reduce).  dS [G][n][D].
+ * ws: han_project_bwd_workspace_bytes. */
+size_t han_project_bwd_workspace_bytes(int64_t n, int64_t F, int G, int D);
+int han_project_bwd(const float* X, int64_t n, int64_t F, int64_t ldx, const float* dS, int G, int D,
+                    float* dW, void* ws, size_t ws_bytes, int mode, han_stream_t stream);
+
+/* ---- K-B: fused CSR edge-softmax-aggregate. Replaces utils/layers.py:26-35,46 for K heads ---- */
+/* For destination rows [0,n_dst): alpha_ij = softmax_j(leaky_relu_0.2(f1_i + f2_j)), V_i = sum_j
+ * alpha_ij S_j, out_i = act(V_i + bias).  T is indexed by the CSR's column ids; f1 is read from
+ * R[:, D:D+K]; m and rinv are written to R[:, D+K:D+3K]; V to vsave [n_dst][D]; out to
+ * out + i*out_stride (so K-B writes straight into Z[n][P][D], models/gat.py:46,58,60).
+ * colmean (nullable) [D]: value used for rows with no edge at all (dense-path uniform 1/N row). */
+int han_attn_fwd(const int64_t* indptr, const int32_t* indices, int64_t n_dst, const float* T,
+                 float* R, const float* bias, int K, int H, int act, float* out, int64_t out_stride,
+                 float* vsave, const float* colmean, han_stream_t stream);
+
+/* Per-edge coefficients alpha [nnz][K] (utils/layers.py:43-44 return_coef), from saved m/rinv. */
+int han_attn_coefs(const int64_t* indptr, const int32_t* indices, int64_t n_dst, const float* T,
+                   const float* R, int K, int H, float* alpha, han_stream_t stream);
+
+/* ---- K-D: backward of K-B ----------------------------------------------------------------- */
+/* prep (row-local): dV = dout * act'(.), delta = <dV, V> per head -> R[:, 0:D], R[:, D+3K:D+4K];
+ * dbias_partial [han_reduce_blocks()][D] per-block column sums of dV. */
+int han_reduce_blocks(void);
+int han_attn_bwd_prep(const float* dout, int64_t dout_stride, const float* out, int64_t out_stride,
+                      const float* vsave, float* R, int64_t n_dst, int K, int H, int act,
+                      float* dbias_partial, han_stream_t stream);
+
+/* by-source pass over the transposed structure: for source rows [0,n_src):
+ *   dS_agg_j = sum_i alpha_ij dV_i ; df2_j = sum_i dl_ij ; dl_edge[perm[t]][K] = dl_ij
+ * where dl_ij = alpha_ij (dV_i.S_j - delta_i) * leaky'(f1_i + f2_j).  Tsrc rows = local sources. */
+int han_attn_bwd_src(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
+                     int64_t n_src, const float* Tsrc, const float* R, int K, int H, float* dS_agg,
+                     float* df2, float* dl_edge, han_stream_t stream);
+
+/* by-destination pass: df1_i = sum_j dl_edge[e] over CSR row i -> df1 [n_dst][K]. */
+int han_attn_bwd_dst(const int64_t* indptr, int64_t n_dst, const float* dl_edge, int K, float* df1,
+                     han_stream_t stream);
+
+/* finish (row-local): dS_tot = dS_agg + df1 a1^T + df2 a2^T (in place into dS_agg);
+ * partial sums for da1,da2 [K][H], db1,db2 [K]: part [han_reduce_blocks()][2*D + 2*K]. */
+int han_attn_bwd_finish(const float* T, int64_t n, int K, int H, const float* a1, const float* a2,
+                        const float* df1, const float* df2, float* dS, float* part,
+                        han_stream_t stream);
+
+/* Deterministic column sums of partial buffers: outv[c] = sum_b part[b][c]. */
+int han_reduce_partials(const float* part, int nblocks, int64_t cols, float* outv, han_stream_t stream);
+
+/* ---- K-C / K-F: semantic attention. Replaces utils/layers.py:152-159 ------------------------ */
+/* Z [n][P][D], w [D][A], b [A], u [A].  Supported (D,A): han_semantic_shape_supported.
+ * HAN_SEM_REFERENCE: writes out [n][D] and beta [n][P] (per-node softmax over meta-paths, :156).
+ * HAN_SEM_PAPER    : writes only scores [n][P]; the caller averages them over nodes (all-reduce when
+ *                    sharded), takes one softmax, then calls han_semantic_combine.
+ * vsave [n*P][A] (nullable) keeps tanh(Zw+b) for the backward; scores (nullable in reference mode). */
+int han_semantic_shape_supported(int D, int A);
+int han_semantic_fwd(const float* Z, int64_t n, int P, int D, int A, const float* w, const float* b,
+                     const float* u, int mode, float* out, float* beta, float* vsave, float* scores,
+                     han_stream_t stream);
+/* out[n] = sum_p beta_vec[p] Z[n,p]; beta (nullable) [n][P] receives the broadcast (han.pdf Eq. 9). */
+int han_semantic_combine(const float* Z, int64_t n, int P, int D, const float* beta_vec, float* out,
+                         float* beta, han_stream_t stream);
+
+size_t han_semantic_bwd_workspace_bytes(int P, int D, int A);
+/* dout [n][D] -> dZ [n][P][D], dw [D][A], db [A], du [A] (deterministic two-stage reduce).
+ * dsbar [P] (paper mode only): d(loss)/d(s_bar_p) / N, the per-row score gradient. */
+int han_semantic_bwd(const float* dout, const float* Z, const float* beta, const float* vsave,
+                     int64_t n, int P, int D, int A, const float* w, const float* u, int mode,
+                     const float* dsbar, float* dZ, float* dw, float* db, float* du, void* ws,
+                     size_t ws_bytes, han_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAN_B200_H */

@@ -1,0 +1,166 @@
+"""K-A/K-B/K-D parity: projection + fused CSR edge-softmax-aggregate, forward and backward, against
+the fp64 dense oracle (utils/layers.py:7-46 restated) on the same seeded inputs, through the same
+autograd.Function -> ctypes -> C-ABI route the model uses."""
+import numpy as np
+import pytest
+import torch
+
+from han_b200 import synth
+from oracle import han_oracle as O
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_params(rng, F, G, K, H):
+    D = K * H
+    t = lambda *s: torch.from_numpy(rng.normal(size=s) * 0.3)
+    return {"W": t(F, G * D), "a1": t(G, K, H), "b1": t(G, K), "a2": t(G, K, H), "b2": t(G, K), "bias": t(G, D)}
+
+
+def _oracle_node_attention(cfg, par, K, H, act, upstream):
+    """fp64 dense oracle: Z (N,G,D) from G*K attn_head calls, and grads of sum(Z * upstream)."""
+    G, D = cfg.P, K * H
+    p = {k: v.clone().double().requires_grad_(True) for k, v in par.items()}
+    X = torch.from_numpy(cfg.X).double().unsqueeze(0)
+    biases = [torch.from_numpy(O.adj_to_bias(a, [cfg.N], 1)) for a in cfg.adjs()]
+    cols, coefs = [], []
+    for g in range(G):
+        heads = []
+        for k in range(K):
+            hp = {"W": p["W"][:, g * D + k * H: g * D + (k + 1) * H], "a1": p["a1"][g, k], "b1": p["b1"][g, k],
+                  "a2": p["a2"][g, k], "b2": p["b2"][g, k], "bias": p["bias"][g, k * H:(k + 1) * H]}
+            o, c = O.attn_head(X, H, biases[g], act, hp, return_coef=True)
+            heads.append(o[0]); coefs.append(c[0].detach())
+        cols.append(torch.cat(heads, -1))
+    Z = torch.stack(cols, 1)
+    (Z * upstream.double()).sum().backward()
+    return Z.detach(), {k: v.grad for k, v in p.items()}, coefs
+
+
+def _product_node_attention(cfg, par, K, H, act_name, upstream, want_coefs=False):
+    import han_b200 as hb
+    from han_b200 import ops
+    dev = torch.device("cuda")
+    p = {k: v.float().to(dev).requires_grad_(True) for k, v in par.items()}
+    X = torch.from_numpy(cfg.X).to(dev)
+    graphs = [hb.process.adj_to_bias(a, [cfg.N]) for a in cfg.adjs()]
+    plan = ops.NodeAttentionPlan(graphs=graphs, K=K, H=H, act=ops.activation_code(act_name), want_coefs=want_coefs)
+    Z = ops.node_attention(plan, X, p["W"], p["a1"], p["b1"], p["a2"], p["b2"], p["bias"])
+    (Z * upstream.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    return Z.detach(), {k: v.grad for k, v in p.items()}, plan
+
+
+SHAPES = [(8, 8), (4, 8), (1, 8), (8, 4), (2, 8), (8, 16), (16, 4), (1, 4), (4, 16)]
+
+
+@pytest.mark.parametrize("K,H", SHAPES)
+def test_node_attention_fwd_bwd_parity(K, H):
+    cfg = synth.tiny(seed=K * 31 + H, n=131, f=37, p=2, deg=7.0)   # N, F not multiples of 32/4
+    rng = np.random.default_rng(K * 100 + H)
+    par = _rand_params(rng, cfg.F, cfg.P, K, H)
+    up = torch.from_numpy(rng.normal(size=(cfg.N, cfg.P, K * H)))
+    Zo, go, _ = _oracle_node_attention(cfg, par, K, H, O.elu, up)
+    Zp, gp, _ = _product_node_attention(cfg, par, K, H, "elu", up.float())
+    assert_close(Zp, Zo, "Z")
+    for k in go:
+        assert_close(gp[k], go[k], "d" + k)
+
+
+def test_identity_activation_and_three_metapaths():
+    cfg = synth.tiny(seed=5, n=64, f=16, p=3, deg=4.0)
+    rng = np.random.default_rng(55)
+    par = _rand_params(rng, cfg.F, cfg.P, 8, 8)
+    up = torch.from_numpy(rng.normal(size=(cfg.N, cfg.P, 64)))
+    Zo, go, _ = _oracle_node_attention(cfg, par, 8, 8, O.identity, up)
+    Zp, gp, _ = _product_node_attention(cfg, par, 8, 8, "identity", up.float())
+    assert_close(Zp, Zo, "Z")
+    for k in go:
+        assert_close(gp[k], go[k], "d" + k)
+
+
+def test_degenerate_rows_and_long_rows():
+    """single-neighbour rows (alpha == 1 exactly), a full row, a source every node attends to (long
+    transposed row), rows longer than one 32-edge chunk, no-self-loop rows."""
+    cfg = synth.tiny(seed=9, n=200, f=24, p=2, deg=3.0)
+    m0, m1 = cfg.masks
+    m0[3, :] = False; m0[3, 3] = True
+    m0[7, :] = True
+    m0[50:60, :150] = True
+    m1[:, 11] = True
+    m1[20, :] = False; m1[20, 5] = True
+    rng = np.random.default_rng(99)
+    par = _rand_params(rng, cfg.F, cfg.P, 8, 8)
+    up = torch.from_numpy(rng.normal(size=(cfg.N, cfg.P, 64)))
+    Zo, go, coefs_o = _oracle_node_attention(cfg, par, 8, 8, O.elu, up)
+    Zp, gp, plan = _product_node_attention(cfg, par, 8, 8, "elu", up.float(), want_coefs=True)
+    assert_close(Zp, Zo, "Z")
+    for k in go:
+        assert_close(gp[k], go[k], "d" + k)
+    # return_coef: alpha on edges == dense coefs on edges; single-neighbour rows exactly 1
+    for g in range(cfg.P):
+        indptr, indices = plan.graphs[g].to_host()
+        rows = np.repeat(np.arange(cfg.N), np.diff(indptr))
+        alpha = plan.coefs[g].cpu()
+        for k in range(8):
+            ref = coefs_o[g * 8 + k][rows, indices]
+            assert_close(alpha[:, k], ref, f"alpha[{g}][{k}]")
+        rowsum = torch.zeros(cfg.N, 8).index_add_(0, torch.from_numpy(rows), alpha)
+        assert torch.allclose(rowsum, torch.ones_like(rowsum), atol=2e-6)     # softmax rows sum to 1
+    a0 = plan.coefs[0].cpu()
+    ip0 = plan.graphs[0].to_host()[0]
+    assert torch.equal(a0[ip0[3]], torch.ones(8))                                # alpha == 1 exactly
+
+
+def test_row_without_any_edge_matches_fp32_dense_forward():
+    """an all -1e9 bias row degenerates to uniform attention over ALL nodes in the
+    reference's fp32 arithmetic; compare with the fp32 oracle (fp64 does not absorb the logits)."""
+    import han_b200 as hb
+    from han_b200 import ops
+    cfg = synth.tiny(seed=12, n=90, f=10, p=1, deg=4.0)
+    cfg.masks[0][17, :] = False          # with adj = mask - I this row has adj_ii = -1 -> no self-loop
+    rng = np.random.default_rng(3)
+    par = _rand_params(rng, cfg.F, 1, 8, 8)
+    bias32 = torch.from_numpy(O.adj_to_bias(cfg.adjs()[0], [cfg.N], 1)).float()
+    X32 = torch.from_numpy(cfg.X).unsqueeze(0)
+    heads = []
+    for k in range(8):
+        hp = {"W": par["W"][:, k * 8:(k + 1) * 8].float(), "a1": par["a1"][0, k].float(), "b1": par["b1"][0, k].float(),
+              "a2": par["a2"][0, k].float(), "b2": par["b2"][0, k].float(), "bias": par["bias"][0, k * 8:(k + 1) * 8].float()}
+        heads.append(O.attn_head(X32, 8, bias32, O.elu, hp)[0])
+    Zo = torch.cat(heads, -1)
+    dev = torch.device("cuda")
+    g = hb.process.adj_to_bias(cfg.adjs()[0], [cfg.N])
+    assert g.has_empty_rows()
+    plan = ops.NodeAttentionPlan(graphs=[g], K=8, H=8)
+    p = {k: v.float().to(dev) for k, v in par.items()}
+    with torch.no_grad():
+        Z = ops.node_attention(plan, torch.from_numpy(cfg.X).to(dev), p["W"], p["a1"], p["b1"], p["a2"], p["b2"], p["bias"])
+    assert_close(Z[:, 0], Zo, "Z", rel=5e-6)
+
+
+def test_attn_head_reference_signature():
+    """layers.attn_head keeps the reference's positional signature (utils/layers.py:7-8)."""
+    import han_b200 as hb
+    cfg = synth.tiny(seed=2, n=77, f=19, p=1, deg=5.0)
+    rng = np.random.default_rng(8)
+    H = 8
+    hp64 = {"W": torch.from_numpy(rng.normal(size=(cfg.F, H)) * 0.3), "a1": torch.from_numpy(rng.normal(size=H)),
+            "b1": torch.tensor(0.1, dtype=torch.float64), "a2": torch.from_numpy(rng.normal(size=H)),
+            "b2": torch.tensor(-0.3, dtype=torch.float64), "bias": torch.from_numpy(rng.normal(size=H))}
+    bias = O.adj_to_bias(cfg.adjs()[0], [cfg.N], 1)
+    ref, coefs = O.attn_head(torch.from_numpy(cfg.X).double()[None], H, torch.from_numpy(bias), O.elu, hp64,
+                             return_coef=True)
+    dev = torch.device("cuda")
+    hp = {k: v.float().to(dev) for k, v in hp64.items()}
+    seq = torch.from_numpy(cfg.X).to(dev)[None]
+    # dense fp32 bias, exactly what the reference driver feeds (ex_acm3025.py:127,180)
+    out, ec = hb.layers.attn_head(seq, H, torch.from_numpy(bias.astype(np.float32)), hb.layers.elu, 0.0, 0.0, False,
+                                  True, params=hp)
+    assert out.shape == (1, cfg.N, H)
+    assert_close(out, ref, "attn_head")
+    assert_close(ec.to_dense(), coefs, "coefs")
+    assert (ec.to_dense()[0].cpu()[torch.from_numpy(bias[0]) < 0] == 0).all()    # masked coefficients exactly 0
+    with pytest.raises(NotImplementedError):
+        hb.layers.attn_head(seq, H, bias, hb.layers.elu, 0.6, 0.6, params=hp)

@@ -1,0 +1,178 @@
+"""End-to-end parity of HeteGAT_multi.inference + masked CE + L2 (the driver's training objective,
+ex_acm3025.py:139-152) against the fp64 oracle: outputs, loss and every gradient; the committed
+golden fixtures; and size-independent properties at larger sizes."""
+import numpy as np
+import pytest
+import torch
+
+from han_b200 import synth
+from oracle import han_oracle as O
+from tests.golden import make_golden
+from tests.util import assert_close, compare_step, oracle_step, product_step
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["tiny_p2_k8h8", "tiny_p3_k4h8_paper", "degenerate_rows"])
+def test_golden_fixture(name):
+    cfg, params, stored, meta = make_golden.load_case(name)
+    out_p, grads_p, _ = product_step(cfg, params, (meta["hid"],), (meta["heads"], 1), meta["mode"])
+    for k in ("logits", "final_embed", "att_val", "ce", "total"):
+        assert_close(out_p[k], stored[k], k)
+    for k in make_golden.LIST_KEYS:
+        for i, g in enumerate(grads_p[k]):
+            assert_close(g, stored[f"g_{k}{i}"], f"d{k}[{i}]")
+    for k in make_golden.VEC_KEYS:
+        assert_close(grads_p[k], stored[f"g_{k}"], "d" + k)
+
+
+@pytest.mark.parametrize("which,scale", [("acm", 0.25), ("dblp", 0.15), ("imdb", 0.2)])
+def test_config_shaped_step_parity(which, scale):
+    """ACM/DBLP/IMDB-shaped synthetic inputs (binary features, clique / sparse / near-dense
+    meta-paths) at a reduced node count the dense fp64 oracle finishes in seconds."""
+    cfg = synth.SMALL[which](scale=scale)
+    rng = np.random.default_rng(17)
+    params = O.init_params(rng, [cfg.F] * cfg.P, cfg.C)
+    out_o, grads_o = oracle_step(cfg, params)
+    out_p, grads_p, _ = product_step(cfg, params)
+    compare_step(out_o, grads_o, out_p, grads_p)
+
+
+def test_separate_feature_tensors_per_metapath():
+    """models/gat.py:39 allows a different feature tensor per meta-path (no shared projection)."""
+    import han_b200 as hb
+    cfg = synth.tiny(seed=31, n=80, f=20, p=2, deg=5.0)
+    rng = np.random.default_rng(32)
+    params = O.init_params(rng, [cfg.F] * 2, cfg.C)
+    X2 = rng.normal(size=cfg.X.shape).astype(np.float32)
+    biases = [torch.from_numpy(O.adj_to_bias(a, [cfg.N], 1)) for a in cfg.adjs()]
+    lo, fe, av = O.HeteGAT_multi_inference(
+        [torch.from_numpy(cfg.X).double()[None], torch.from_numpy(X2).double()[None]], cfg.C, cfg.N, False, 0.0, 0.0,
+        biases, [8], [8, 1], params)
+    dev = torch.device("cuda")
+    hp = hb.HANParams([cfg.F] * 2, cfg.C, device=dev).load_dict(params)
+    graphs = [hb.process.adj_to_bias(a, [cfg.N]) for a in cfg.adjs()]
+    with torch.no_grad():
+        lp, fp, ap = hb.HeteGAT_multi.inference([torch.from_numpy(cfg.X).to(dev)[None], torch.from_numpy(X2).to(dev)[None]],
+                                                cfg.C, cfg.N, False, 0.0, 0.0, graphs, [8], [8, 1], params=hp)
+    assert_close(lp, lo, "logits"); assert_close(fp, fe, "final_embed"); assert_close(ap, av, "att_val")
+
+
+def test_default_store_and_zip_truncation():
+    """Like TF's default graph, variables are created on first use and reused; the reference feeds 3
+    feature placeholders and 2 biases and zip() drops the third (ex_acm3025.py:86 vs :61)."""
+    import han_b200 as hb
+    hb.variables.reset_default_graph()
+    cfg = synth.tiny(seed=41, n=60, f=12, p=2, deg=4.0)
+    dev = torch.device("cuda")
+    X = torch.from_numpy(cfg.X).to(dev)[None]
+    graphs = [hb.process.adj_to_bias(a, [cfg.N]) for a in cfg.adjs()]
+    with torch.no_grad():
+        l1, e1, a1 = hb.HeteGAT_multi.inference([X, X, X], cfg.C, cfg.N, True, 0.0, 0.0, graphs, [8], [8, 1])
+        l2, e2, a2 = hb.HeteGAT_multi.inference([X, X, X], cfg.C, cfg.N, False, 0.0, 0.0, graphs, [8], [8, 1])
+    assert l1.shape == (1, cfg.N, cfg.C) and e1.shape == (cfg.N, 64) and a1.shape == (cfg.N, 2)
+    assert torch.equal(l1, l2)                       # same variables, deterministic kernels
+    store = hb.variables.get_default_store()
+    assert store is not None and store.P == 2
+    assert store.tf_variable_names()["a2[1][3]"] == "conv1d_35/kernel"
+    hb.variables.reset_default_graph()
+
+
+def test_properties_at_bench_scale():
+    """Size-independent checks on a graph too large for the dense oracle: softmax rows of alpha sum
+    to 1, per-node beta sums to 1, determinism, node-permutation equivariance, and agreement with
+    the fp64 edge-list twin on a row sample."""
+    import han_b200 as hb
+    dev = torch.device("cuda")
+    N, F, P = 200_000, 64, 2
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    hp = hb.HANParams([F] * P, 5, device=dev, generator=gen)
+    X = synth.device_features(N, F, 77, dev)
+    graphs = []
+    for p in range(P):
+        ip, ix = synth.device_random_csr(N, N, 20, 900 + p, dev)
+        graphs.append(hb.MetaPathGraph.from_csr(ip, ix, n_cols=N))
+    with torch.no_grad():
+        lo, fe, av, coefs = hb.HeteGAT_multi.inference([X[None]] * P, 5, N, False, 0.0, 0.0, graphs, [8], [8, 1],
+                                                       params=hp, return_coef=True)
+        lo2, fe2, av2 = hb.HeteGAT_multi.inference([X[None]] * P, 5, N, False, 0.0, 0.0, graphs, [8], [8, 1], params=hp)
+    assert torch.equal(lo, lo2) and torch.equal(fe, fe2)                       # bitwise deterministic
+    assert torch.allclose(av.sum(1), torch.ones(N, device=dev), atol=1e-6)
+    for p in range(P):
+        deg = graphs[p].indptr[1:] - graphs[p].indptr[:-1]
+        rows = torch.repeat_interleave(torch.arange(N, device=dev), deg)
+        rs = torch.zeros(N, 8, device=dev).index_add_(0, rows, coefs[p].alpha)
+        assert torch.allclose(rs, torch.ones_like(rs), atol=5e-6)
+    # fp64 edge-list twin on the first 2000 rows (needs S for all sources: project on the CPU in fp64)
+    params64 = {k: ([t.double().cpu() for t in v] if isinstance(v, list) else v.double().cpu())
+                for k, v in hp.to_dict().items()}
+    Xc = X.double().cpu()
+    sub = 2000
+    embeds = []
+    for p in range(P):
+        ip, ix = graphs[p].to_host()
+        heads = []
+        for k in range(8):
+            h = O.head_params(params64, p, k)
+            S = Xc @ h["W"]
+            f1, f2 = S @ h["a1"] + h["b1"], S @ h["a2"] + h["b2"]
+            rows = torch.from_numpy(np.repeat(np.arange(sub), np.diff(ip[:sub + 1])))
+            cols = torch.from_numpy(ix[:ip[sub]].astype(np.int64))
+            e = torch.nn.functional.leaky_relu(f1[rows] + f2[cols], 0.2)
+            m = torch.full((sub,), -float("inf"), dtype=torch.float64).scatter_reduce(0, rows, e, reduce="amax")
+            ex = torch.exp(e - m[rows])
+            den = torch.zeros(sub, dtype=torch.float64).index_add(0, rows, ex)
+            vals = torch.zeros(sub, 8, dtype=torch.float64).index_add(0, rows, (ex / den[rows])[:, None] * S[cols])
+            heads.append(torch.nn.functional.elu(vals + h["bias"]))
+        embeds.append(torch.cat(heads, -1)[:, None])
+    fe_ref, av_ref = O.SimpleAttLayer(torch.cat(embeds, 1), 128, params64, return_alphas=True)
+    assert_close(fe[:sub], fe_ref, "final_embed[:2000]")
+    assert_close(av[:sub], av_ref, "att_val[:2000]")
+    # permutation equivariance: relabel nodes, outputs permute with them
+    perm = torch.randperm(N, generator=torch.Generator().manual_seed(1)).to(dev)
+    inv = torch.empty_like(perm); inv[perm] = torch.arange(N, device=dev)
+    Xp = X[perm]
+    graphs_p = []
+    for p in range(P):
+        ip, ix = graphs[p].indptr, graphs[p].indices
+        deg = (ip[1:] - ip[:-1])[perm]
+        ipp = torch.zeros(N + 1, dtype=torch.int64, device=dev); ipp[1:] = torch.cumsum(deg, 0)
+        starts = ip[:-1][perm]
+        offs = torch.arange(int(ipp[-1]), device=dev) - torch.repeat_interleave(ipp[:-1], deg)
+        src = torch.repeat_interleave(starts, deg) + offs
+        ixp = inv[ix[src].long()].to(torch.int32)
+        graphs_p.append(hb.MetaPathGraph.from_csr(ipp, ixp, n_cols=N, sort=True))
+    with torch.no_grad():
+        _, fe_p, _ = hb.HeteGAT_multi.inference([Xp[None]] * P, 5, N, False, 0.0, 0.0, graphs_p, [8], [8, 1], params=hp)
+    assert_close(fe_p, fe[perm], "permuted final_embed", rel=1e-5)
+
+
+def test_training_step_reduces_loss_and_matches_oracle_adam():
+    """BaseGAttN.training: L2 on every variable + TF1-style Adam (models/base_gattn.py:12-24).
+    One step must match the oracle's update; a few steps must lower the loss."""
+    import han_b200 as hb
+    cfg = synth.tiny(seed=51, n=120, f=30, p=2, deg=6.0)
+    rng = np.random.default_rng(52)
+    params = O.init_params(rng, [cfg.F] * cfg.P, cfg.C, zero_bias=True)
+    out_o, grads_o = oracle_step(cfg, params)
+    dev = torch.device("cuda")
+    hp = hb.HANParams([cfg.F] * cfg.P, cfg.C, device=dev).load_dict(params)
+    X = torch.from_numpy(cfg.X).to(dev)[None]
+    graphs = [hb.process.adj_to_bias(a, [cfg.N]) for a in cfg.adjs()]
+    labels = torch.from_numpy(cfg.labels).to(dev)
+    mask = torch.from_numpy(cfg.train_mask.astype(np.float32)).to(dev)
+    train_op = hb.BaseGAttN.training(hp, 0.005, 0.001)
+    losses = []
+    for step in range(5):
+        logits, _, _ = hb.HeteGAT_multi.inference([X] * cfg.P, cfg.C, cfg.N, True, 0.0, 0.0, graphs, [8], [8, 1], params=hp)
+        loss = hb.BaseGAttN.masked_softmax_cross_entropy(logits.reshape(-1, cfg.C), labels, mask)
+        acc = hb.BaseGAttN.masked_accuracy(logits.reshape(-1, cfg.C), labels, mask)
+        losses.append(float(train_op.run(loss)))
+        if step == 0:
+            w0 = params["W"][0].double()
+            g0 = grads_o["W"][0]
+            ref, _, _ = O.adam_step_tf1(w0, g0, torch.zeros_like(w0), torch.zeros_like(w0), 1)
+            # step 1 of Adam moves by ~lr*sign(g): compare where |g| is not tiny
+            big = g0.abs() > 1e-4 * g0.abs().max()
+            assert torch.allclose(hp.W[0].detach().double().cpu()[big], ref[big], atol=2e-5)
+    assert losses[-1] < losses[0] and 0.0 <= float(acc) <= 1.0
