@@ -92,10 +92,52 @@ def stream_ptr():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def call(name: str, *args):
+# kernels launched by one call of each entry point (for bench.py's `gpu_launches` count)
+KERNELS_PER_CALL = {
+    "han_dense_row_counts": 1, "han_scan_counts": 3, "han_dense_fill_indices": 1, "han_csr_transpose": 7,
+    "han_csr_sort_rows": 2, "han_project_fwd": None, "han_project_bwd": 2, "han_attn_fwd": 1,
+    "han_attn_coefs": 1, "han_attn_bwd_prep": 1, "han_attn_bwd_src": 1, "han_attn_bwd_dst": 1,
+    "han_attn_bwd_finish": 1, "han_reduce_partials": 1, "han_semantic_fwd": 1, "han_semantic_combine": 1,
+    "han_semantic_bwd": 2,
+}
+
+
+class CallRecorder:
+    """Optional per-entry-point CUDA-event timing and launch counting (used by bench.py only).
+    Events are recorded on torch's current stream, the stream every kernel is launched on."""
+
+    def __init__(self, time_events: bool = True):
+        self.time_events = time_events
+        self.events = {}      # name -> list of (start, end)
+        self.launches = 0
+
+    def summary(self):
+        """name -> (calls, total_ms); call after a device synchronize."""
+        return {k: (len(v), sum(s.elapsed_time(e) for s, e in v)) for k, v in self.events.items()}
+
+
+_recorder = None
+
+
+def set_recorder(rec):
+    global _recorder
+    _recorder = rec
+
+
+def call(name: str, *args, kernels: int = None):
     """Calls an int-returning entry point; non-zero -> HanError(han_last_error())."""
     lib = load()
+    rec = _recorder
+    if rec is not None:
+        k = KERNELS_PER_CALL.get(name) if kernels is None else kernels
+        rec.launches += k if k is not None else 1
+        if rec.time_events:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
     rc = getattr(lib, name)(*args)
+    if rec is not None and rec.time_events:
+        e.record()
+        rec.events.setdefault(name, []).append((s, e))
     if rc != 0:
         msg = lib.han_last_error()
         raise HanError(f"{name} failed (rc={rc}): {msg.decode() if msg else ''}")

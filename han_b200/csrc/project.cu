@@ -119,13 +119,14 @@ attn_scores_kernel(float* __restrict__ T, float* __restrict__ R, int64_t n, cons
 __global__ void __launch_bounds__(kGemmThreads)
 sgemm_tn_splitk_kernel(const float* __restrict__ A, int64_t n, int64_t F, int64_t lda,
                        const float* __restrict__ G, int64_t Dn, int64_t g_stride, int64_t rows_per_split,
-                       float* __restrict__ part, int64_t NC) {
+                       float* __restrict__ part, int64_t NC, int ctiles) {
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
   const int64_t f0 = (int64_t)blockIdx.x * BM;
-  const int g = blockIdx.y;
+  const int g = blockIdx.y / ctiles;
+  const int64_t c0 = (int64_t)(blockIdx.y % ctiles) * BN;   // column tile inside group g
   const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
   const int64_t r_end = min(n, r_begin + rows_per_split);
   const float* Gg = G + (int64_t)g * g_stride;
@@ -142,7 +143,7 @@ sgemm_tn_splitk_kernel(const float* __restrict__ A, int64_t n, int64_t F, int64_
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int64_t r = k0 + b_k + 4 * i;
-      rb[i] = (r < r_end && b_c < Dn) ? __ldg(Gg + r * Dn + b_c) : 0.f;
+      rb[i] = (r < r_end && c0 + b_c < Dn) ? __ldg(Gg + r * Dn + c0 + b_c) : 0.f;
     }
   };
   auto store_tiles = [&](int buf) {
@@ -190,7 +191,7 @@ sgemm_tn_splitk_kernel(const float* __restrict__ A, int64_t n, int64_t F, int64_
     if (f < F) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int64_t c = (int64_t)tx * 4 + j;
+        const int64_t c = c0 + (int64_t)tx * 4 + j;
         if (c < Dn) P[f * NC + (int64_t)g * Dn + c] = acc[i][j];
       }
     }
@@ -206,8 +207,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
   outv[i] = s;
 }
 
-static int pick_splits(int64_t n, int64_t F, int G) {
-  int64_t tiles = ceil_div64(F, BM) * G;
+static int pick_splits(int64_t n, int64_t F, int G, int D) {
+  int64_t tiles = ceil_div64(F, BM) * G * ceil_div64(D, BN);
   int64_t want = (kNumSMs * 4 + tiles - 1) / tiles;
   int64_t maxs = ceil_div64(n, 4 * BK);
   if (want > maxs) want = maxs;
@@ -272,23 +273,23 @@ int han_project_fwd(const float* X, int64_t n, int64_t F, int64_t ldx, const flo
 }
 
 size_t han_project_bwd_workspace_bytes(int64_t n, int64_t F, int G, int D) {
-  return (size_t)pick_splits(n, F, G) * (size_t)F * G * D * sizeof(float);
+  return (size_t)pick_splits(n, F, G, D) * (size_t)F * G * D * sizeof(float);
 }
 
 int han_project_bwd(const float* X, int64_t n, int64_t F, int64_t ldx, const float* dS, int G, int D,
                     float* dW, void* ws, size_t ws_bytes, int mode, han_stream_t stream) {
   HAN_REQUIRE(X && dS && dW && ws, "null pointer");
   HAN_REQUIRE(n > 0 && F > 0 && G > 0 && D > 0 && ldx >= F, "sizes");
-  HAN_REQUIRE(D <= BN, "D <= 64 per group in this library version");
   HAN_REQUIRE(mode == 0, "only mode 0 (fp32 FFMA) is built into this library version");
-  const int splits = pick_splits(n, F, G);
+  const int splits = pick_splits(n, F, G, D);
   HAN_REQUIRE(ws_bytes >= (size_t)splits * F * G * D * sizeof(float), "workspace too small");
   cudaStream_t st = as_stream(stream);
   int64_t rows_per_split = ceil_div64(ceil_div64(n, splits), BK) * BK;
-  dim3 grid((unsigned)ceil_div64(F, BM), (unsigned)G, (unsigned)splits);
+  const int ctiles = (int)ceil_div64(D, BN);
+  dim3 grid((unsigned)ceil_div64(F, BM), (unsigned)(G * ctiles), (unsigned)splits);
   float* part = reinterpret_cast<float*>(ws);
   sgemm_tn_splitk_kernel<<<grid, kGemmThreads, 0, st>>>(X, n, F, ldx, dS, D, (int64_t)n * D, rows_per_split,
-                                                       part, (int64_t)G * D);
+                                                       part, (int64_t)G * D, ctiles);
   int64_t elems = F * (int64_t)G * D;
   splitk_reduce_kernel<<<(unsigned)ceil_div64(elems, 256), 256, 0, st>>>(part, splits, elems, dW);
   return check_launch(__func__);

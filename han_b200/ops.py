@@ -170,11 +170,11 @@ class SemanticAttentionFn(torch.autograd.Function):
                 scores = _empty((n, P), dev)
                 call("han_semantic_fwd", ptr(Z), n, P, D, A, ptr(w), ptr(b), ptr(u), mode, None, None,
                      ptr(vsave), ptr(scores), stream_ptr())
-                ssum = scores.sum(0)
+                ssum = scores.sum(0, dtype=torch.float64)      # P scalars: reduce over nodes in fp64
                 n_total = n
                 if dist is not None:
                     ssum, n_total = dist.all_reduce_sum(ssum), dist.n_total
-                beta_vec = torch.softmax(ssum / n_total, dim=0).contiguous()   # han.pdf Eq. 8 (P scalars)
+                beta_vec = torch.softmax(ssum / n_total, dim=0).float().contiguous()   # han.pdf Eq. 8
                 call("han_semantic_combine", ptr(Z), n, P, D, ptr(beta_vec), ptr(out), ptr(beta),
                      stream_ptr())
                 ctx.n_total = n_total
@@ -194,10 +194,12 @@ class SemanticAttentionFn(torch.autograd.Function):
             dsbar = None
             if ctx.mode == _lib.SEM_PAPER:
                 # d s_bar_p = beta_p (g_p - sum_q beta_q g_q), g_p = sum_n <dout[n], Z[n,p]>; P scalars
-                gp = torch.einsum("nd,npd->p", dout, Z)
+                # (the difference below cancels heavily: per-row dots in fp32, node sum and softmax-grad in fp64)
+                gp = torch.einsum("nd,npd->np", dout, Z).sum(0, dtype=torch.float64)
                 if ctx.dist is not None:
                     gp = ctx.dist.all_reduce_sum(gp)
-                dsbar = (beta_vec * (gp - (beta_vec * gp).sum()) / ctx.n_total).contiguous()
+                bv = beta_vec.double()
+                dsbar = (bv * (gp - (bv * gp).sum()) / ctx.n_total).float().contiguous()
             dZ = _empty((n, P, D), dev)
             dw, db, du = _empty((D, A), dev), _empty((A,), dev), _empty((A,), dev)
             ws_bytes = query("han_semantic_bwd_workspace_bytes", P, D, A)

@@ -66,7 +66,8 @@ def product_step(cfg, params64, hid_units=(8,), n_heads=(8, 1), semantic_mode="r
     m = torch.from_numpy((cfg.train_mask if mask is None else mask).astype(np.float32)).to(dev)
     logits, final_embed, att_val = hb.HeteGAT_multi.inference(
         [X] * cfg.P, cfg.C, cfg.N, True, 0.0, 0.0, graphs, list(hid_units), list(n_heads),
-        params=hp, semantic_mode=semantic_mode, project_mode=project_mode)
+        mp_att_size=params64["w_omega"].shape[1], params=hp, semantic_mode=semantic_mode,
+        project_mode=project_mode)
     ce = hb.BaseGAttN.masked_softmax_cross_entropy(logits.reshape(-1, cfg.C), labels, m)
     train = hb.BaseGAttN.training(hp, 0.005, l2_coef)
     total = ce + train.l2_loss()
