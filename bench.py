@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""Benchmark of the HAN hot path (BASELINE.json metric: fused HAN forward+backward meta-path edges/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload syn2m|acm|dblp|imdb|mag]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's dense algorithm on the host cores
+
+A step = one forward + backward of HeteGAT_multi.inference + masked CE + L2 over the whole synthetic
+graph (projection, node attention, semantic attention, classifier, loss, every gradient; optimizer
+excluded).  edges = sum_p nnz(meta-path mask p), self-loops included, counted once per step.
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "han_fwd_bwd_metapath_edges_per_s"
+UNIT = "edges/s"
+K_HEADS, HID, ATT = 8, 8, 128
+
+WORKLOADS = {
+    "syn2m": "synthetic 2M-node heterograph, 4 meta-paths, avg degree 50, 256-d feats",
+    "mag": "OGB-MAG-scale synthetic (736k papers, 2 power-law meta-paths)",
+    "acm": "ACM3025-shaped synthetic graph (3025 papers, 1870-d feats, PAP+PLP)",
+    "dblp": "DBLP four-area-shaped synthetic (4057 authors, 334-d feats, APA/APCPA/APTPA)",
+    "imdb": "IMDB-shaped synthetic (4780 movies, MAM/MDM meta-paths, 3 classes)",
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def mark(self):
+        return len(self.lines)
+
+    def stop(self, lo=0, hi=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines[lo:hi]:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        hi = [s for s in sm if mx and s > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(hi) if hi else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# workloads
+# --------------------------------------------------------------------------------------------------
+def build_workload(name, dev, dist):
+    """-> dict(N, F, C, P, X (local rows, device), graphs (local dst rows), labels, mask, edges (global),
+    host (pinned host copies for the e2e leg), working_set_bytes)."""
+    import han_b200 as hb
+    from han_b200 import synth
+    lo, hi = (0, None)
+    if name in synth.SMALL:
+        cfg = synth.SMALL[name]()
+        N, F, C, P = cfg.N, cfg.F, cfg.C, cfg.P
+        lo, hi = dist.row_range(N) if dist else (0, N)
+        full = [hb.process.adj_to_bias(a, [N]) for a in cfg.adjs()]
+        X = torch.from_numpy(cfg.X[lo:hi]).to(dev)
+        labels = torch.from_numpy(cfg.labels[lo:hi]).to(dev)
+        mask = torch.from_numpy(cfg.train_mask[lo:hi].astype(np.float32)).to(dev)
+        edges = cfg.n_edges()
+        host = {"X": torch.from_numpy(cfg.X[lo:hi]).pin_memory(),
+                "bias": [torch.from_numpy(hb_bias(m[lo:hi])).pin_memory() for m in cfg.masks] if dist is None else None}
+    else:
+        spec = synth.LARGE[name]
+        N, F, C, P = spec.N, spec.F, spec.C, spec.P
+        lo, hi = dist.row_range(N) if dist else (0, N)
+        X = synth.device_features(hi - lo, F, spec.seed, dev, row_lo=lo)
+        labels, mask = synth.device_labels(hi - lo, C, spec.seed, dev, row_lo=lo)
+        full = None
+        graphs_local, edges = [], 0
+        for p in range(P):
+            ip, ix = synth.device_random_csr(hi - lo, N, spec.mean_degree, spec.seed + 17 * (p + 1), dev, row_lo=lo,
+                                             powerlaw=spec.powerlaw)
+            graphs_local.append(hb.MetaPathGraph.from_csr(ip, ix, n_cols=N, row_offset=lo))
+            edges += graphs_local[-1].nnz
+        if dist:
+            edges = int(dist.all_reduce_sum(torch.tensor([edges], dtype=torch.float64, device=dev)).item())
+        host = None
+    if name in synth.SMALL:
+        graphs_local = [g.row_slice(lo, hi) if dist else g for g in full]
+    ws = X.numel() * 4 + sum(g.nnz * 4 * 3 for g in graphs_local) + (hi - lo) * P * (72 + 96 + 64 * 3) * 4
+    return dict(N=N, F=F, C=C, P=P, X=X, graphs=graphs_local, labels=labels, mask=mask, edges=edges, host=host,
+                lo=lo, hi=hi, working_set_bytes=ws, full_graphs=full)
+
+
+def hb_bias(mask_rows: np.ndarray) -> np.ndarray:
+    """Reference-style dense fp32 bias rows (0 on edges, -1e9 elsewhere): what ex_acm3025.py feeds."""
+    return np.where(mask_rows, np.float32(0.0), np.float32(-1e9)).astype(np.float32)
+
+
+def algorithmic_bytes(name, wl):
+    """ALGORITHMIC bytes of one launch set (all P meta-paths) of the two gather kernels:
+       han_attn_fwd    : (4 + 4*TS) B/edge + (8 + 4K + 4D + 4D + 8K) B/row
+       han_attn_bwd_src: (4 + 4 + 4*RS + 4K) B/edge + (8 + 4*TS + 4D + 4K) B/source row"""
+    K, D = K_HEADS, K_HEADS * HID
+    TS, RS = 72, 96
+    E = sum(g.nnz for g in wl["graphs"])
+    n = wl["hi"] - wl["lo"]
+    P = wl["P"]
+    if name == "han_attn_fwd":
+        return (4 + 4 * TS) * E + (8 + 4 * K + 8 * D + 8 * K) * n * P
+    if name == "han_attn_bwd_src":
+        return (8 + 4 * RS + 4 * K) * E + (8 + 4 * TS + 4 * D + 4 * K) * n * P
+    return None
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import han_b200 as hb
+    from han_b200 import _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        from han_b200 import dist as hd
+        dist = hd.RowShard.init_process_group()
+    if args.gpus != world:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+
+    wl = build_workload(args.workload, dev, dist)
+    N, F, C, P = wl["N"], wl["F"], wl["C"], wl["P"]
+    gen = torch.Generator(device="cpu").manual_seed(1234)
+    hp = hb.HANParams([F] * P, C, (HID,), (K_HEADS, 1), ATT, device=dev, generator=gen)
+    train = hb.BaseGAttN.training(hp, 0.005, 0.001)
+    if dist:
+        dist.bind(wl["graphs"], N)
+        for g in wl["graphs"]:
+            pass
+    else:
+        for g in wl["graphs"]:
+            g.transpose()          # built once per graph (like adj_to_bias, outside the step)
+    X1 = wl["X"].unsqueeze(0)
+
+    def step(Xin, graphs):
+        hp.zero_grad(set_to_none=True)
+        logits, _, _ = hb.HeteGAT_multi.inference([Xin] * P, C, N, True, 0.0, 0.0, graphs, [HID], [K_HEADS, 1],
+                                                  params=hp, dist=dist)
+        if dist is None:
+            ce = hb.BaseGAttN.masked_softmax_cross_entropy(logits.reshape(-1, C), wl["labels"], wl["mask"])
+            total = ce + train.l2_loss()
+        else:
+            total = dist.masked_loss(logits.reshape(-1, C), wl["labels"], wl["mask"], train)
+        total.backward()
+        if dist is not None:
+            dist.all_reduce_grads(hp)
+        return total
+
+    flush = None
+    if wl["working_set_bytes"] < (1 << 30):
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step(X1, wl["graphs"])
+    barrier()
+    # keep the GPU busy until nvidia-smi has produced its first samples, so the timed region is covered
+    t_wait = time.perf_counter()
+    while rank == 0 and sampler.proc is not None and sampler.mark() < 2 and time.perf_counter() - t_wait < 5.0:
+        step(X1, wl["graphs"])
+        torch.cuda.synchronize()
+    barrier()
+
+    rec = _lib.CallRecorder(time_events=True)
+    _lib.set_recorder(rec)
+    mark_lo = sampler.mark()
+    torch.cuda.nvtx.range_push("han_timed")
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s, e in ev:
+        if flush is not None:
+            flush.zero_()
+        s.record()
+        loss = step(X1, wl["graphs"])
+        e.record()
+    barrier()
+    torch.cuda.nvtx.range_pop()
+    _lib.set_recorder(None)
+    if rank == 0:
+        time.sleep(0.25)     # let the sampler flush the samples taken during the region
+    clocks = sampler.stop(max(0, mark_lo - 1), None) if rank == 0 else None
+    step_ms = [s.elapsed_time(e) for s, e in ev]
+    ms = sum(step_ms) / len(step_ms)
+    if dist:
+        ms = dist.all_reduce_max(torch.tensor([ms], dtype=torch.float64, device=dev)).item()
+    value = wl["edges"] / (ms * 1e-3)
+
+    # ---- dominant kernel roofline (rank-local, all ranks do the same work) ---------------------
+    summ = rec.summary()
+    top = max((k for k in summ if algorithmic_bytes(k, wl)), key=lambda k: summ[k][1])
+    calls, tot_ms = summ[top]
+    launches_per_set = P
+    sets = calls / launches_per_set
+    achieved = algorithmic_bytes(top, wl) * sets / (tot_ms * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload, {}).get(top)
+    roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "avg_launch_ms": round(tot_ms / calls, 4),
+                "algorithmic_bytes_per_launch": int(algorithmic_bytes(top, wl) / launches_per_set),
+                "kernel_share_of_step": round(tot_ms / sum(step_ms), 4),
+                "kernels_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in sorted(summ.items())}}
+
+    # ---- end-to-end through the public API with HOST buffers -----------------------------------
+    e2e = None if args.no_e2e else run_e2e(args, wl, hp, train, dist, dev, step)
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOADS[args.workload], "nodes": N, "features": F, "meta_paths": P,
+                      "edges": wl["edges"], "heads": K_HEADS, "hid": HID, "mp_att_size": ATT, "classes": C,
+                      "parallelism": f"dst-row shards x{world}" if world > 1 else "single GPU",
+                      "l2_policy": "inputs larger than L2" if flush is None else "L2 flushed between timed steps",
+                      "dropout": 0.0, "projection": "fp32 FFMA"},
+           "roofline": roofline, "e2e": e2e, "gpu_launches": rec.launches, "clocks": clocks,
+           "loss": float(loss)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=20.0)
+    if rank == 0:
+        print(json.dumps(out))
+    if dist:
+        dist.shutdown()
+
+
+def run_e2e(args, wl, hp, train, dist, dev, step):
+    """Same metric through the reference-facing API with HOST inputs: every step copies that step's
+    features and graph structure from pinned host memory, rebuilds the device-side graph handles
+    (dense bias -> CSR for the small configs, CSR + transposed view for the large ones), runs
+    fwd+bwd and reads the loss back."""
+    import han_b200 as hb
+    n_e2e = max(1, min(args.steps, 3))
+    P = wl["P"]
+    if wl["host"] is not None and wl["host"]["bias"] is not None:
+        hX, hB = wl["host"]["X"], wl["host"]["bias"]
+        h2d = hX.numel() * 4 + sum(b.numel() * 4 for b in hB)
+
+        def one():
+            X = hX.to(dev, non_blocking=True).unsqueeze(0)
+            graphs = [hb.MetaPathGraph.from_dense_bias(b.to(dev, non_blocking=True)) for b in hB]
+            return step(X, graphs)
+    else:
+        hX = wl["X"].cpu().pin_memory()
+        hG = [(g.indptr.cpu().pin_memory(), g.indices.cpu().pin_memory()) for g in wl["graphs"]]
+        h2d = hX.numel() * 4 + sum(a.numel() * 8 + b.numel() * 4 for a, b in hG)
+
+        def one():
+            X = hX.to(dev, non_blocking=True).unsqueeze(0)
+            graphs = [hb.MetaPathGraph.from_csr(a, b, n_cols=wl["N"], device=dev, row_offset=wl["lo"]) for a, b in hG]
+            if dist:
+                dist.bind(graphs, wl["N"])
+            return step(X, graphs)
+    one()                                   # warm-up (allocator, pinned staging)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    s.record()
+    for _ in range(n_e2e):
+        loss = one()
+        host_loss = float(loss.detach())    # D2H read of the step's result (synchronises the step)
+    e.record()
+    torch.cuda.synchronize()
+    ms = max(s.elapsed_time(e), (time.perf_counter() - t0) * 1e3) / n_e2e
+    if dist:
+        ms = dist.all_reduce_max(torch.tensor([ms], dtype=torch.float64, device=dev)).item()
+    return {"value": wl["edges"] / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": 4, "ms_per_step": ms, "steps": n_e2e, "loss": host_loss}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py executes oracle/)
+# --------------------------------------------------------------------------------------------------
+def cpu_baseline(workload, budget_s=20.0, steps=None, warmup=1):
+    from han_b200 import synth
+    from oracle import cpu_reference as cr
+    from oracle import han_oracle as O
+    cores = cr.host_threads()
+    if workload in synth.SMALL:
+        cfg = synth.SMALL[workload]()
+        params = O.init_params(np.random.default_rng(1), [cfg.F] * cfg.P, cfg.C, dtype=torch.float32)
+        times = cr.dense_full_step_seconds(cfg, params, steps or 2, warmup)
+        t = statistics.median(times)
+        return {"value": cfg.n_edges() / t, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{len(times)} complete dense fp32 reference steps (fwd+bwd, all {cfg.P * K_HEADS} heads) of the "
+                          f"{workload} config on torch-CPU; median {t:.3f} s/step", "step_s": times}
+    spec = synth.LARGE[workload]
+    R = 16
+    prob = cr.make_rowblock_problem(spec.N, spec.P, K_HEADS, HID, R, min(spec.mean_degree, 64), 7)
+    times, edges = [], 0
+    t_all = time.perf_counter()
+    for it in range((steps or 2) + warmup):
+        dt, edges = cr.dense_rowblock_step_seconds(prob, K_HEADS, HID)
+        if it >= warmup:
+            times.append(dt)
+        if steps is None and time.perf_counter() - t_all > budget_s:
+            break
+    times = times or [dt]
+    t = statistics.median(times)
+    return {"value": edges / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"dense chain (utils/layers.py:26-35,46) fwd+bwd for {R} of {spec.N} destination rows x all "
+                      f"{spec.N} source columns, {spec.P} meta-paths x {K_HEADS} heads, torch-CPU fp32; projection/"
+                      f"semantic excluded (favours CPU); N x N does not fit host memory; median {t:.2f} s per sample",
+            "step_s": times}
+
+
+def run_reference(args):
+    """--impl reference: the reference's dense CPU algorithm (oracle port; TF1 cannot be installed)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_baseline(args.workload, steps=args.steps, warmup=min(args.warmup, 1))
+    step_s = statistics.median(base["step_s"])
+    from han_b200 import synth
+    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+           "steps": len(base["step_s"]), "warmup": min(args.warmup, 1), "ms_per_step": step_s * 1e3,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOADS[args.workload]},
+           "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="syn2m", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
