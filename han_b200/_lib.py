@@ -39,6 +39,10 @@ _SIGNATURES = {
     "han_project_bwd": (c_int, [P, I64, I64, I64, P, I, I, P, P, SZ, I, P]),
     "han_attn_fwd": (c_int, [P, P, I64, P, P, P, I, I, I, P, I64, P, P, P]),
     "han_attn_coefs": (c_int, [P, P, I64, P, P, I, I, P, P]),
+    "han_csr_num_chunks": (c_int64, [I64]),
+    "han_csr_chunk_rows": (c_int, [P, I64, I64, P, P]),
+    "han_attn_fwd_chunked": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P]),
+    "han_attn_bwd_src_chunked": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P]),
     "han_reduce_blocks": (c_int, []),
     "han_attn_bwd_prep": (c_int, [P, I64, P, I64, P, P, I64, I, I, I, P, P]),
     "han_attn_bwd_src": (c_int, [P, P, P, I64, P, P, I, I, P, P, P, P]),
@@ -96,7 +100,8 @@ def stream_ptr():
 KERNELS_PER_CALL = {
     "han_dense_row_counts": 1, "han_scan_counts": 3, "han_dense_fill_indices": 1, "han_csr_transpose": 7,
     "han_csr_sort_rows": 2, "han_project_fwd": None, "han_project_bwd": 2, "han_attn_fwd": 1,
-    "han_attn_coefs": 1, "han_attn_bwd_prep": 1, "han_attn_bwd_src": 1, "han_attn_bwd_dst": 1,
+    "han_attn_coefs": 1, "han_attn_bwd_prep": 1, "han_attn_bwd_src": 1,
+    "han_csr_chunk_rows": 1, "han_attn_fwd_chunked": 1, "han_attn_bwd_src_chunked": 1, "han_attn_bwd_dst": 1,
     "han_attn_bwd_finish": 1, "han_reduce_partials": 1, "han_semantic_fwd": 1, "han_semantic_combine": 1,
     "han_semantic_bwd": 2,
 }

@@ -24,7 +24,7 @@ attn_bwd_prep_kernel(const float* __restrict__ dout, int64_t dout_stride, const 
                      int64_t out_stride, const float* __restrict__ vsave, float* __restrict__ R,
                      int64_t n_dst, int act, float* __restrict__ dbias_partial) {
   constexpr int D = K * H;
-  constexpr int RS = D + 4 * K;
+  constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
   // thread = (row, head); a block covers 256/K consecutive rows; grid-stride over row tiles
   const int head = threadIdx.x % K;
   const int rsub = threadIdx.x / K;
@@ -52,7 +52,7 @@ attn_bwd_prep_kernel(const float* __restrict__ dout, int64_t dout_stride, const 
         *reinterpret_cast<float4*>(R + row * RS + head * H + 4 * q) = g;
         colsum[4 * q] += g.x; colsum[4 * q + 1] += g.y; colsum[4 * q + 2] += g.z; colsum[4 * q + 3] += g.w;
       }
-      R[row * RS + D + 3 * K + head] = delta;
+      R[row * RS + D + 2 * K + head] = delta;
     }
   }
   // block reduce of column sums over the ROWS sub-rows -> dbias_partial[block][D]
@@ -76,7 +76,7 @@ attn_bwd_src_kernel(const int64_t* __restrict__ t_indptr, const int32_t* __restr
                     float* __restrict__ dl_edge) {
   constexpr int D = K * H;
   constexpr int TS = ((D + K + 3) / 4) * 4;
-  constexpr int RS = D + 4 * K;
+  constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
   constexpr int SLOTS = 32 / K;
   constexpr int HV = H / 4;
   const int lane = threadIdx.x & 31;
@@ -103,7 +103,7 @@ attn_bwd_src_kernel(const int64_t* __restrict__ t_indptr, const int32_t* __restr
     const int my_perm = (lane < cnt) ? ldg_stream_i32(perm + base + lane) : 0;
     for (int t = 0; t < cnt; t += SLOTS * UNROLL) {
       float4 g[UNROLL][HV];
-      float f1[UNROLL], mm[UNROLL], ri[UNROLL], de[UNROLL];
+      float f1[UNROLL], mm[UNROLL], de[UNROLL];
       int pe[UNROLL];
       bool ok[UNROLL];
 #pragma unroll
@@ -118,15 +118,14 @@ attn_bwd_src_kernel(const int64_t* __restrict__ t_indptr, const int32_t* __restr
           for (int q = 0; q < HV; ++q) g[u][q] = ldg4(rp + head * H + 4 * q);
           f1[u] = __ldg(rp + D + head);
           mm[u] = __ldg(rp + D + K + head);
-          ri[u] = __ldg(rp + D + 2 * K + head);
-          de[u] = __ldg(rp + D + 3 * K + head);
+          de[u] = __ldg(rp + D + 2 * K + head);
         }
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         if (ok[u]) {
           const float lg = f1[u] + f2;
-          const float a = __expf(leaky(lg) - mm[u]) * ri[u];
+          const float a = __expf(leaky(lg) - mm[u]);
           float da = 0.f;
 #pragma unroll
           for (int q = 0; q < HV; ++q) {

@@ -22,7 +22,7 @@ attn_fwd_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ 
                 float* __restrict__ vsave, const float* __restrict__ colmean) {
   constexpr int D = K * H;
   constexpr int TS = ((D + K + 3) / 4) * 4;
-  constexpr int RS = D + 4 * K;
+  constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
   constexpr int SLOTS = 32 / K;
   constexpr int HV = H / 4;
   const int lane = threadIdx.x & 31;
@@ -105,21 +105,20 @@ attn_fwd_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ 
   }
 
   if (slot == 0) {
-    float rinv;
+    float lse;
     if (end > start) {
-      rinv = 1.f / l;
+      const float rinv = 1.f / l;
+      lse = m + __logf(l);
 #pragma unroll
       for (int h = 0; h < H; ++h) acc[h] *= rinv;
     } else {
       // row without any edge: the dense path degenerates to uniform 1/N over ALL nodes
       // (SURVEY.md section 0.6a); colmean = mean_j S_j when the builder flagged such rows.
-      m = 0.f;
-      rinv = 0.f;
+      lse = 0.f;
 #pragma unroll
       for (int h = 0; h < H; ++h) acc[h] = colmean ? colmean[head * H + h] : 0.f;
     }
-    R[row * RS + D + K + head] = m;
-    R[row * RS + D + 2 * K + head] = rinv;
+    R[row * RS + D + K + head] = lse;
     float* vp = vsave + row * D + head * H;
     float* op = out + row * out_stride + head * H;
 #pragma unroll
@@ -147,7 +146,7 @@ attn_coefs_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
                   float* __restrict__ alpha) {
   constexpr int D = K * H;
   constexpr int TS = ((D + K + 3) / 4) * 4;
-  constexpr int RS = D + 4 * K;
+  constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
   constexpr int SLOTS = 32 / K;
   const int lane = threadIdx.x & 31;
   const int head = lane % K, slot = lane / K;
@@ -155,12 +154,11 @@ attn_coefs_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
   if (row >= n_dst) return;
   const int64_t start = indptr[row], end = indptr[row + 1];
   const float f1v = R[row * RS + D + head];
-  const float m = R[row * RS + D + K + head];
-  const float rinv = R[row * RS + D + 2 * K + head];
+  const float lse = R[row * RS + D + K + head];
   for (int64_t e = start + slot; e < end; e += SLOTS) {
     const int col = indices[e];
     const float f2 = __ldg(T + (int64_t)col * TS + D + head);
-    alpha[e * K + head] = __expf(leaky(f1v + f2) - m) * rinv;
+    alpha[e * K + head] = __expf(leaky(f1v + f2) - lse);
   }
 }
 
@@ -201,7 +199,7 @@ int han_attn_shape_supported(int K, int H) {
 }
 
 int han_table_stride(int K, int H) { return ((K * H + K + 3) / 4) * 4; }
-int han_record_stride(int K, int H) { return K * H + 4 * K; }
+int han_record_stride(int K, int H) { return ((K * H + 3 * K + 3) / 4) * 4; }
 
 int han_attn_fwd(const int64_t* indptr, const int32_t* indices, int64_t n_dst, const float* T,
                  float* R, const float* bias, int K, int H, int act, float* out, int64_t out_stride,

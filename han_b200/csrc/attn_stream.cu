@@ -1,0 +1,476 @@
+// Chunked edge-stream versions of the two gather kernels (K-B forward, K-D by-source backward).
+//
+// Why: the warp-per-row kernels in attn_fwd.cu / attn_bwd.cu hold every gathered row in registers,
+// so registers cap both occupancy and the number of rows in flight (ncu on B200: 35% / 21% warps
+// active, 67% / 35% DRAM utilisation).  Here a warp owns a contiguous CHUNK of the CSR edge stream
+// (whole rows, ~kChunkEdges edges, boundaries precomputed per graph by han_csr_chunk_rows) and
+// pulls the gathered rows through a per-warp shared-memory ring with cp.async (LDGSTS, 16 B per
+// lane, L2-only): STAGES-1 batches of 16 records are always in flight per warp, independent of
+// registers, and work is balanced by edges instead of by rows, so degree skew does not matter.
+// Row boundaries inside the stream are handled by the consumer (segmented online softmax / sums).
+#include "han_common.cuh"
+
+namespace han {
+
+constexpr int kChunkEdges = 2048;   // edges per work item (whole rows; boundaries from chunk_rows)
+constexpr int kBatch = 16;          // records per cp.async group
+constexpr int kStreamWarps = 4;     // warps per CTA
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// chunk_rows[c] = first row whose start offset indptr[r] >= c * kChunkEdges, c in [0, n_chunks);
+// chunk_rows[n_chunks] = n_rows.  n_chunks = nnz / kChunkEdges + 1.
+__global__ void chunk_rows_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, int64_t n_chunks,
+                                  int32_t* __restrict__ chunk_rows) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > n_chunks) return;
+  if (c == n_chunks) {
+    chunk_rows[c] = (int32_t)n_rows;
+    return;
+  }
+  const int64_t target = c * kChunkEdges;
+  int64_t lo = 0, hi = n_rows;  // lower_bound over indptr[0 .. n_rows)
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (indptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  chunk_rows[c] = (int32_t)lo;
+}
+
+// -------------------------------------------------------------------------------------------------
+// forward
+// -------------------------------------------------------------------------------------------------
+template <int K, int H, int STAGES>
+__global__ void __launch_bounds__(kStreamWarps * 32, 4)
+attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                        const int32_t* __restrict__ chunk_rows, int64_t n_chunks,
+                        const float* __restrict__ T, float* __restrict__ R, const float* __restrict__ bias,
+                        int act, float* __restrict__ out, int64_t out_stride, float* __restrict__ vsave,
+                        const float* __restrict__ colmean) {
+  constexpr int D = K * H;
+  constexpr int TS = ((D + K + 3) / 4) * 4;
+  constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
+  constexpr int SLOTS = 32 / K;
+  constexpr int HV = H / 4;
+  constexpr int REC_CHUNKS = TS / 4;
+  constexpr int TOT = kBatch * REC_CHUNKS;
+  constexpr int PER_LANE = (TOT + 31) / 32;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int head = lane % K, slot = lane / K;
+  float* ring = smem + (size_t)w * STAGES * kBatch * TS;
+
+  const int64_t chunk = (int64_t)blockIdx.x * kStreamWarps + w;
+  if (chunk >= n_chunks) return;
+  const int r_lo = chunk_rows[chunk], r_hi = chunk_rows[chunk + 1];
+  if (r_lo >= r_hi) return;
+  const int64_t e_lo = indptr[r_lo], e_hi = indptr[r_hi];
+  const int nb = (int)((e_hi - e_lo + kBatch - 1) / kBatch);
+
+  int q = 0;  // next batch to issue
+  int col_pref = (lane < kBatch && e_lo + lane < e_hi) ? ldg_stream_i32(indices + e_lo + lane) : 0;
+  auto issue = [&]() {
+    if (q < nb) {
+      const int64_t bs = e_lo + (int64_t)q * kBatch;
+      const int cnt = (int)min((int64_t)kBatch, e_hi - bs);
+      float* dst = ring + (size_t)(q % STAGES) * kBatch * TS;
+#pragma unroll
+      for (int i = 0; i < PER_LANE; ++i) {
+        const int c = lane + 32 * i;
+        const int rec = c / REC_CHUNKS, off = c - rec * REC_CHUNKS;
+        const int col = __shfl_sync(0xffffffffu, col_pref, rec & 31);
+        if (c < TOT && rec < cnt) cp_async16(dst + rec * TS + off * 4, T + (int64_t)col * TS + off * 4);
+      }
+      const int64_t nbs = bs + kBatch;
+      col_pref = (lane < kBatch && nbs + lane < e_hi) ? ldg_stream_i32(indices + nbs + lane) : 0;
+    }
+    cp_async_commit();
+    ++q;
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) issue();
+
+  int row = r_lo;
+  int64_t row_start = e_lo;
+  int64_t row_end = indptr[row + 1];
+  float f1v = R[(int64_t)row * RS + D + head];
+  float m = -INFINITY, l = 0.f;
+  float acc[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) acc[h] = 0.f;
+
+  auto finalize_row = [&]() {
+    // merge the SLOTS partial softmax states of each head
+#pragma unroll
+    for (int off = K; off < 32; off <<= 1) {
+      const float mo = __shfl_xor_sync(0xffffffffu, m, off);
+      const float lo = __shfl_xor_sync(0xffffffffu, l, off);
+      const float mn = fmaxf(m, mo);
+      const float s0 = (m == -INFINITY) ? 0.f : __expf(m - mn);
+      const float s1 = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+      l = l * s0 + lo * s1;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float ao = __shfl_xor_sync(0xffffffffu, acc[h], off);
+        acc[h] = acc[h] * s0 + ao * s1;
+      }
+      m = mn;
+    }
+    if (slot == 0) {
+      float lse;
+      if (row_end > row_start) {
+        const float rinv = 1.f / l;
+        lse = m + __logf(l);
+#pragma unroll
+        for (int h = 0; h < H; ++h) acc[h] *= rinv;
+      } else {
+        // row without any edge: dense path = uniform 1/N over ALL nodes
+        lse = 0.f;
+#pragma unroll
+        for (int h = 0; h < H; ++h) acc[h] = colmean ? colmean[head * H + h] : 0.f;
+      }
+      R[(int64_t)row * RS + D + K + head] = lse;
+      float* vp = vsave + (int64_t)row * D + head * H;
+      float* op = out + (int64_t)row * out_stride + head * H;
+#pragma unroll
+      for (int qv = 0; qv < HV; ++qv) {
+        float4 a = make_float4(acc[4 * qv], acc[4 * qv + 1], acc[4 * qv + 2], acc[4 * qv + 3]);
+        *reinterpret_cast<float4*>(vp + 4 * qv) = a;
+        const float4 b = ldg4(bias + head * H + 4 * qv);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        if (act == HAN_ACT_ELU) {
+          a.x = a.x > 0.f ? a.x : expm1f(a.x);
+          a.y = a.y > 0.f ? a.y : expm1f(a.y);
+          a.z = a.z > 0.f ? a.z : expm1f(a.z);
+          a.w = a.w > 0.f ? a.w : expm1f(a.w);
+        }
+        *reinterpret_cast<float4*>(op + 4 * qv) = a;
+      }
+    }
+  };
+  auto next_row = [&]() {
+    ++row;
+    row_start = row_end;
+    if (row < r_hi) {
+      row_end = indptr[row + 1];
+      f1v = R[(int64_t)row * RS + D + head];
+    }
+    m = -INFINITY;
+    l = 0.f;
+#pragma unroll
+    for (int h = 0; h < H; ++h) acc[h] = 0.f;
+  };
+
+  int64_t pos = e_lo;
+  for (int b = 0; b < nb; ++b) {
+    issue();
+    cp_async_wait<STAGES - 1>();
+    __syncwarp();
+    const float* buf = ring + (size_t)(b % STAGES) * kBatch * TS;
+    const int64_t bs = e_lo + (int64_t)b * kBatch;
+    const int64_t be = min(e_hi, bs + kBatch);
+    while (pos < be) {
+      const int64_t seg_end = min(row_end, be);
+      for (int64_t g = pos; g < seg_end; g += SLOTS) {
+        const int64_t ei = g + slot;
+        if (ei < seg_end) {
+          const float* rp = buf + (int)(ei - bs) * TS;
+          const float e = leaky(f1v + rp[D + head]);
+          const float mnew = fmaxf(m, e);
+          const float sc = __expf(m - mnew);   // m = -inf -> 0
+          const float p = __expf(e - mnew);
+          l = fmaf(l, sc, p);
+#pragma unroll
+          for (int qv = 0; qv < HV; ++qv) {
+            const float4 v = *reinterpret_cast<const float4*>(rp + head * H + 4 * qv);
+            acc[4 * qv + 0] = fmaf(acc[4 * qv + 0], sc, p * v.x);
+            acc[4 * qv + 1] = fmaf(acc[4 * qv + 1], sc, p * v.y);
+            acc[4 * qv + 2] = fmaf(acc[4 * qv + 2], sc, p * v.z);
+            acc[4 * qv + 3] = fmaf(acc[4 * qv + 3], sc, p * v.w);
+          }
+          m = mnew;
+        }
+      }
+      pos = seg_end;
+      while (row < r_hi && pos == row_end) {   // row complete (also sweeps up empty rows)
+        finalize_row();
+        next_row();
+      }
+    }
+    __syncwarp();   // all lanes done with this stage before it is refilled
+  }
+  while (row < r_hi) {   // trailing rows without edges
+    finalize_row();
+    next_row();
+  }
+  cp_async_wait<0>();
+}
+
+// -------------------------------------------------------------------------------------------------
+// backward, by source (transposed structure)
+// -------------------------------------------------------------------------------------------------
+template <int K, int H, int STAGES>
+__global__ void __launch_bounds__(kStreamWarps * 32, 3)
+attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t* __restrict__ t_indices,
+                            const int32_t* __restrict__ perm, const int32_t* __restrict__ chunk_rows,
+                            int64_t n_chunks, const float* __restrict__ Tsrc, const float* __restrict__ R,
+                            float* __restrict__ dS_agg, float* __restrict__ df2,
+                            float* __restrict__ dl_edge) {
+  constexpr int D = K * H;
+  constexpr int TS = ((D + K + 3) / 4) * 4;
+  constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
+  constexpr int SLOTS = 32 / K;
+  constexpr int HV = H / 4;
+  constexpr int REC_CHUNKS = RS / 4;
+  constexpr int TOT = kBatch * REC_CHUNKS;
+  constexpr int PER_LANE = (TOT + 31) / 32;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int head = lane % K, slot = lane / K;
+  float* ring = smem + (size_t)w * STAGES * kBatch * RS;
+  int* perm_s = reinterpret_cast<int*>(smem + (size_t)kStreamWarps * STAGES * kBatch * RS) + w * STAGES * kBatch;
+
+  const int64_t chunk = (int64_t)blockIdx.x * kStreamWarps + w;
+  if (chunk >= n_chunks) return;
+  const int r_lo = chunk_rows[chunk], r_hi = chunk_rows[chunk + 1];
+  if (r_lo >= r_hi) return;
+  const int64_t e_lo = t_indptr[r_lo], e_hi = t_indptr[r_hi];
+  const int nb = (int)((e_hi - e_lo + kBatch - 1) / kBatch);
+
+  int q = 0;
+  int row_pref = 0, perm_pref = 0;
+  if (lane < kBatch && e_lo + lane < e_hi) {
+    row_pref = ldg_stream_i32(t_indices + e_lo + lane);
+    perm_pref = ldg_stream_i32(perm + e_lo + lane);
+  }
+  auto issue = [&]() {
+    if (q < nb) {
+      const int64_t bs = e_lo + (int64_t)q * kBatch;
+      const int cnt = (int)min((int64_t)kBatch, e_hi - bs);
+      const int st = q % STAGES;
+      float* dst = ring + (size_t)st * kBatch * RS;
+#pragma unroll
+      for (int i = 0; i < PER_LANE; ++i) {
+        const int c = lane + 32 * i;
+        const int rec = c / REC_CHUNKS, off = c - rec * REC_CHUNKS;
+        const int i_row = __shfl_sync(0xffffffffu, row_pref, rec & 31);
+        if (c < TOT && rec < cnt) cp_async16(dst + rec * RS + off * 4, R + (int64_t)i_row * RS + off * 4);
+      }
+      if (lane < kBatch) perm_s[st * kBatch + lane] = perm_pref;
+      const int64_t nbs = bs + kBatch;
+      if (lane < kBatch && nbs + lane < e_hi) {
+        row_pref = ldg_stream_i32(t_indices + nbs + lane);
+        perm_pref = ldg_stream_i32(perm + nbs + lane);
+      }
+    }
+    cp_async_commit();
+    ++q;
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) issue();
+
+  int row = r_lo;
+  int64_t row_end = t_indptr[row + 1];
+  float sj[H], f2;
+  auto load_src = [&](int r) {
+#pragma unroll
+    for (int qv = 0; qv < HV; ++qv) {
+      const float4 s4 = ldg4(Tsrc + (int64_t)r * TS + head * H + 4 * qv);
+      sj[4 * qv] = s4.x; sj[4 * qv + 1] = s4.y; sj[4 * qv + 2] = s4.z; sj[4 * qv + 3] = s4.w;
+    }
+    f2 = __ldg(Tsrc + (int64_t)r * TS + D + head);
+  };
+  load_src(row);
+  float acc[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) acc[h] = 0.f;
+  float df2acc = 0.f;
+
+  auto finalize_row = [&]() {
+#pragma unroll
+    for (int off = K; off < 32; off <<= 1) {
+      df2acc += __shfl_xor_sync(0xffffffffu, df2acc, off);
+#pragma unroll
+      for (int h = 0; h < H; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], off);
+    }
+    if (slot == 0) {
+      df2[(int64_t)row * K + head] = df2acc;
+#pragma unroll
+      for (int qv = 0; qv < HV; ++qv)
+        *reinterpret_cast<float4*>(dS_agg + (int64_t)row * D + head * H + 4 * qv) =
+            make_float4(acc[4 * qv], acc[4 * qv + 1], acc[4 * qv + 2], acc[4 * qv + 3]);
+    }
+  };
+  auto next_row = [&]() {
+    ++row;
+    if (row < r_hi) {
+      row_end = t_indptr[row + 1];
+      load_src(row);
+    }
+    df2acc = 0.f;
+#pragma unroll
+    for (int h = 0; h < H; ++h) acc[h] = 0.f;
+  };
+
+  int64_t pos = e_lo;
+  for (int b = 0; b < nb; ++b) {
+    issue();
+    cp_async_wait<STAGES - 1>();
+    __syncwarp();
+    const int st = b % STAGES;
+    const float* buf = ring + (size_t)st * kBatch * RS;
+    const int* pbuf = perm_s + st * kBatch;
+    const int64_t bs = e_lo + (int64_t)b * kBatch;
+    const int64_t be = min(e_hi, bs + kBatch);
+    while (pos < be) {
+      const int64_t seg_end = min(row_end, be);
+      for (int64_t g = pos; g < seg_end; g += SLOTS) {
+        const int64_t ei = g + slot;
+        if (ei < seg_end) {
+          const int rec = (int)(ei - bs);
+          const float* rp = buf + rec * RS;
+          const float lg = rp[D + head] + f2;
+          const float a = __expf(leaky(lg) - rp[D + K + head]);
+          float da = 0.f;
+#pragma unroll
+          for (int qv = 0; qv < HV; ++qv) {
+            const float4 g4 = *reinterpret_cast<const float4*>(rp + head * H + 4 * qv);
+            da = fmaf(g4.x, sj[4 * qv], da);
+            da = fmaf(g4.y, sj[4 * qv + 1], da);
+            da = fmaf(g4.z, sj[4 * qv + 2], da);
+            da = fmaf(g4.w, sj[4 * qv + 3], da);
+            acc[4 * qv] = fmaf(a, g4.x, acc[4 * qv]);
+            acc[4 * qv + 1] = fmaf(a, g4.y, acc[4 * qv + 1]);
+            acc[4 * qv + 2] = fmaf(a, g4.z, acc[4 * qv + 2]);
+            acc[4 * qv + 3] = fmaf(a, g4.w, acc[4 * qv + 3]);
+          }
+          const float dl = a * (da - rp[D + 2 * K + head]) * (lg > 0.f ? 1.f : kLeakySlope);
+          df2acc += dl;
+          dl_edge[(int64_t)pbuf[rec] * K + head] = dl;
+        }
+      }
+      pos = seg_end;
+      while (row < r_hi && pos == row_end) {
+        finalize_row();
+        next_row();
+      }
+    }
+    __syncwarp();
+  }
+  while (row < r_hi) {
+    finalize_row();
+    next_row();
+  }
+  cp_async_wait<0>();
+}
+
+template <int K, int H>
+struct StreamCfg {
+  static constexpr int D = K * H;
+  static constexpr int TS = ((D + K + 3) / 4) * 4;
+  static constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
+  // stages chosen so that ~3 CTAs (12 warps) fit in 227 KB and >= 2 batches per warp are in flight
+  static constexpr int FWD_STAGES = 3;
+  static constexpr int BWD_STAGES = 3;
+  static constexpr size_t fwd_smem = (size_t)kStreamWarps * FWD_STAGES * kBatch * TS * 4;
+  static constexpr size_t bwd_smem = (size_t)kStreamWarps * BWD_STAGES * kBatch * (RS * 4 + 4);
+};
+
+template <int K, int H>
+static int launch_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
+                              int64_t n_chunks, const float* T, float* R, const float* bias, int act,
+                              float* out, int64_t out_stride, float* vsave, const float* colmean,
+                              cudaStream_t st) {
+  using C = StreamCfg<K, H>;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(attn_fwd_chunked_kernel<K, H, C::FWD_STAGES>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::fwd_smem);
+    attr = true;
+  }
+  unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
+  attn_fwd_chunked_kernel<K, H, C::FWD_STAGES><<<grid, kStreamWarps * 32, C::fwd_smem, st>>>(
+      indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean);
+  return check_launch("han_attn_fwd_chunked");
+}
+
+template <int K, int H>
+static int launch_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
+                                  const int32_t* chunk_rows, int64_t n_chunks, const float* Tsrc,
+                                  const float* R, float* dS_agg, float* df2, float* dl_edge,
+                                  cudaStream_t st) {
+  using C = StreamCfg<K, H>;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bwd_smem);
+    attr = true;
+  }
+  unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
+  attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES><<<grid, kStreamWarps * 32, C::bwd_smem, st>>>(
+      t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge);
+  return check_launch("han_attn_bwd_src_chunked");
+}
+
+}  // namespace han
+
+using namespace han;
+
+#define HAN_FOR_SHAPES(X) X(8, 8) X(4, 8) X(2, 8) X(1, 8) X(8, 4) X(4, 4) X(1, 4) X(8, 16) X(4, 16) X(1, 16) X(16, 4) X(16, 8)
+
+extern "C" {
+
+int64_t han_csr_num_chunks(int64_t nnz) { return nnz / kChunkEdges + 1; }
+
+int han_csr_chunk_rows(const int64_t* indptr, int64_t n_rows, int64_t nnz, int32_t* chunk_rows,
+                       han_stream_t stream) {
+  HAN_REQUIRE(indptr && chunk_rows, "null pointer");
+  HAN_REQUIRE(n_rows > 0 && nnz >= 0 && n_rows < ((int64_t)1 << 31), "sizes");
+  const int64_t n_chunks = nnz / kChunkEdges + 1;
+  chunk_rows_kernel<<<(unsigned)ceil_div64(n_chunks + 1, 256), 256, 0, as_stream(stream)>>>(indptr, n_rows, n_chunks,
+                                                                                           chunk_rows);
+  return check_launch(__func__);
+}
+
+int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
+                         int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
+                         int K, int H, int act, float* out, int64_t out_stride, float* vsave,
+                         const float* colmean, han_stream_t stream) {
+  HAN_REQUIRE(indptr && chunk_rows && T && R && bias && out && vsave, "null pointer");
+  HAN_REQUIRE(n_dst > 0 && n_chunks > 0, "sizes");
+  HAN_REQUIRE(act == HAN_ACT_ELU || act == HAN_ACT_IDENTITY, "activation");
+  HAN_REQUIRE(out_stride >= (int64_t)K * H && out_stride % 4 == 0, "out_stride");
+  HAN_REQUIRE(((uintptr_t)T % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)vsave % 16 == 0) &&
+              ((uintptr_t)bias % 16 == 0), "16-byte alignment");
+#define X(k, h)         \
+  if (K == k && H == h) \
+    return launch_fwd_chunked<k, h>(indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, as_stream(stream));
+  HAN_FOR_SHAPES(X)
+#undef X
+  return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
+}
+
+int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
+                             const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
+                             const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
+                             float* dl_edge, han_stream_t stream) {
+  HAN_REQUIRE(t_indptr && chunk_rows && Tsrc && R && dS_agg && df2 && dl_edge, "null pointer");
+  HAN_REQUIRE(n_src > 0 && n_chunks > 0, "sizes");
+  HAN_REQUIRE(((uintptr_t)R % 16 == 0) && ((uintptr_t)Tsrc % 16 == 0) && ((uintptr_t)dS_agg % 16 == 0), "16-byte alignment");
+#define X(k, h)         \
+  if (K == k && H == h) \
+    return launch_bwd_src_chunked<k, h>(t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, as_stream(stream));
+  HAN_FOR_SHAPES(X)
+#undef X
+  return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
+}
+
+}  // extern "C"

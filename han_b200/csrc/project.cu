@@ -96,7 +96,7 @@ attn_scores_kernel(float* __restrict__ T, float* __restrict__ R, int64_t n, cons
                    const float* __restrict__ b1, const float* __restrict__ a2, const float* __restrict__ b2) {
   constexpr int D = K * H;
   constexpr int TS = ((D + K + 3) / 4) * 4;
-  constexpr int RS = D + 4 * K;
+  constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t row = idx / K;
   const int head = (int)(idx % K);

@@ -1,0 +1,240 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, destination rows of every meta-path CSR
+partitioned in contiguous equal blocks, NCCL over NVLink for the exchange steps.
+
+The reference is single-process (ex_acm3025.py:163); this layer is new and its contract is "same
+numbers as the single-device run" (SURVEY.md section 8(e)).
+
+Per meta-path and step:
+  forward : all-gather of the projected node table T = [S | f2]   (n_pad x TS per rank)
+  backward: all-gather of the row records R = [dV | f1 | lse | delta] (n_pad x RS per rank), the
+            by-source pass then runs on the edges whose SOURCE is local, and the per-destination
+            sums df1 go back with one reduce-scatter (N x K floats)
+  once    : all-reduce of the parameter gradients and of the loss.
+Collectives run on a side stream and are ordered with events, so the gather of meta-path g+1
+overlaps the aggregation of meta-path g.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as td
+
+from . import _lib
+from ._lib import call, ptr, query, stream_ptr
+from .graph import MetaPathGraph
+
+
+def merge_source_segments(counts: torch.Tensor, segments: Sequence[torch.Tensor]):
+    """Builds the by-source structure of the edges whose source is local from what every rank sent.
+
+    counts   : (W, n_src) int64, counts[r, j] = number of destinations on rank r of local source j
+    segments : W tensors; segments[r] lists, source-major, the GLOBAL destination ids on rank r
+    Returns (indptr int64[n_src+1], indices int32[nnz]): per source, rank 0's destinations, then rank
+    1's, ... -- ascending because destination blocks are ordered by rank.  Pure index arithmetic
+    (device-agnostic), used once per graph.
+    """
+    W, n_src = counts.shape
+    total = counts.sum(0)
+    indptr = torch.zeros(n_src + 1, dtype=torch.int64, device=counts.device)
+    indptr[1:] = torch.cumsum(total, 0)
+    nnz = int(indptr[-1].item())
+    indices = torch.empty(nnz, dtype=torch.int32, device=counts.device)
+    before = torch.cumsum(counts, 0) - counts            # (W, n_src): edges of lower ranks for source j
+    for r in range(W):
+        c = counts[r]
+        n_r = int(c.sum().item())
+        if n_r == 0:
+            continue
+        seg_start = torch.cumsum(c, 0) - c                # offset of source j inside segments[r]
+        src = torch.repeat_interleave(torch.arange(n_src, device=counts.device), c)
+        within = torch.arange(n_r, device=counts.device) - seg_start[src]
+        indices[indptr[:-1][src] + before[r][src] + within] = segments[r].to(torch.int32)
+    return indptr, indices
+
+
+class _BackwardEdges:
+    """Edges (i, j) with j local, in both orders: by source (for the gather pass) and by destination
+    (for the df1 segmented sum)."""
+
+    def __init__(self, by_src: MetaPathGraph, by_dst_indptr: torch.Tensor, pos_in_dst: torch.Tensor):
+        self.by_src = by_src                # rows = local sources, indices = global destination ids
+        self.by_dst_indptr = by_dst_indptr  # int64[N_pad + 1]
+        self.pos_in_dst = pos_in_dst        # int32[nnz]: by-source edge -> slot in by-destination order
+
+
+class RowShard:
+    def __init__(self, rank: int, world: int, device: torch.device, group=None):
+        self.rank, self.world, self.device, self.group = rank, world, device, group
+        self.n_total = None
+        self.n_pad = None
+        self.comm_stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        self._bwd = {}
+
+    # ---- set-up ------------------------------------------------------------------------------
+    @staticmethod
+    def init_process_group() -> "RowShard":
+        rank = int(os.environ["RANK"])
+        world = int(os.environ["WORLD_SIZE"])
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        if torch.cuda.is_available():
+            dev = torch.device("cuda", local)
+            torch.cuda.set_device(dev)
+            td.init_process_group("nccl", device_id=dev)
+        else:
+            dev = torch.device("cpu")
+            td.init_process_group("gloo")
+        return RowShard(rank, world, dev)
+
+    def row_range(self, N: int):
+        """Contiguous equal blocks of ceil(N/W) rows (the last block may be shorter)."""
+        n_pad = -(-N // self.world)
+        lo = min(N, self.rank * n_pad)
+        return lo, min(N, lo + n_pad)
+
+    def bind(self, graphs: Sequence[MetaPathGraph], N: int) -> None:
+        """Once per graph set: exchange the transposed slices so every rank owns the by-source
+        structure of the edges whose source it owns, and build the by-destination order of those
+        same edges (for the df1 sums)."""
+        self.n_total = N
+        self.n_pad = -(-N // self.world)
+        for g in graphs:
+            if id(g) in self._bwd:
+                continue
+            self._bwd[id(g)] = self._exchange(g)
+
+    def _exchange(self, g: MetaPathGraph) -> _BackwardEdges:
+        W, n_pad, N = self.world, self.n_pad, self.n_total
+        dev = g.device
+        lo, hi = self.row_range(N)
+        gt = g.transpose()                                  # rows = ALL sources j, entries = local dest ids
+        deg = (gt.indptr[1:] - gt.indptr[:-1])               # (N,)
+        deg_pad = torch.zeros(W * n_pad, dtype=torch.int64, device=dev)
+        deg_pad[:N] = deg
+        recv_counts = torch.empty(W * n_pad, dtype=torch.int64, device=dev)
+        td.all_to_all_single(recv_counts, deg_pad, group=self.group)     # counts[r, j_local]
+        recv_counts = recv_counts.view(W, n_pad)
+        send_split = deg_pad.view(W, n_pad).sum(1).tolist()
+        recv_split = recv_counts.sum(1).tolist()
+        send = (gt.indices.to(torch.int64) + lo).to(torch.int32)          # global destination ids
+        recv = torch.empty(int(sum(recv_split)), dtype=torch.int32, device=dev)
+        td.all_to_all_single(recv, send, output_split_sizes=[int(x) for x in recv_split],
+                             input_split_sizes=[int(x) for x in send_split], group=self.group)
+        n_loc = hi - lo
+        segs = list(torch.split(recv, [int(x) for x in recv_split]))
+        indptr, indices = merge_source_segments(recv_counts[:, :n_loc].contiguous(), segs)
+        by_src = MetaPathGraph(indptr, indices, n_loc, W * n_pad)
+        by_dst = by_src.transpose()                          # rows = padded global destinations
+        pos = torch.empty_like(by_dst.perm)
+        pos[by_dst.perm.long()] = torch.arange(by_dst.nnz, dtype=torch.int32, device=dev)
+        return _BackwardEdges(by_src, by_dst.indptr, pos)
+
+    # ---- collectives ---------------------------------------------------------------------------
+    def barrier(self):
+        td.barrier(group=self.group)
+
+    def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        td.all_reduce(t, op=td.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_reduce_max(self, t: torch.Tensor) -> torch.Tensor:
+        td.all_reduce(t, op=td.ReduceOp.MAX, group=self.group)
+        return t
+
+    def _pad_rows(self, t: torch.Tensor) -> torch.Tensor:
+        """(.., n_loc, C) -> (.., n_pad, C); only the last rank ever pads."""
+        n_loc = t.shape[-2]
+        if n_loc == self.n_pad:
+            return t
+        out = torch.zeros(*t.shape[:-2], self.n_pad, t.shape[-1], dtype=t.dtype, device=t.device)
+        out[..., :n_loc, :] = t
+        return out
+
+    def all_gather_rows(self, T: torch.Tensor) -> List[torch.Tensor]:
+        """T (G, n_loc, C) -> list of G lazily-completed (W*n_pad, C) tables.  The gathers run on the
+        side stream in meta-path order; ``wait(g)`` makes the current stream wait for table g."""
+        G = T.shape[0]
+        Tp = self._pad_rows(T)
+        full = [torch.empty(self.world * self.n_pad, T.shape[-1], dtype=T.dtype, device=T.device) for _ in range(G)]
+        return _Gathered(self, Tp, full)
+
+    def reduce_scatter_rows(self, partial: torch.Tensor) -> torch.Tensor:
+        """(W*n_pad, C) partial sums -> this rank's (n_pad, C) block of the total."""
+        out = torch.empty(self.n_pad, partial.shape[1], dtype=partial.dtype, device=partial.device)
+        td.reduce_scatter_tensor(out, partial, op=td.ReduceOp.SUM, group=self.group)
+        return out
+
+    # ---- the sharded by-source backward of one meta-path ---------------------------------------
+    def gather_records(self, R: torch.Tensor):
+        """R (G, n_loc, RS) -> gathered handle (see all_gather_rows); issued for all meta-paths at once
+        so that gather g+1 overlaps the by-source pass of g."""
+        return self.all_gather_rows(R)
+
+    def backward_edges(self, plan, g: int, T_local: torch.Tensor, R_full: torch.Tensor, dS: torch.Tensor,
+                       df2: torch.Tensor) -> torch.Tensor:
+        """Runs the by-source gather pass on the edges whose source is local and returns df1 for the
+        local destination rows (after the reduce-scatter of the per-destination partial sums)."""
+        be: _BackwardEdges = self._bwd[id(plan.graphs[g])]
+        K, H = plan.K, plan.H
+        dev = T_local.device
+        n_loc = T_local.shape[0]
+        bs = be.by_src
+        dl = torch.empty(max(bs.nnz, 1), K, dtype=torch.float32, device=dev)
+        cr, n_chunks = bs.chunks()
+        call("han_attn_bwd_src_chunked", ptr(bs.indptr), ptr(bs.indices), ptr(be.pos_in_dst), ptr(cr), n_chunks,
+             n_loc, ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), ptr(dl), stream_ptr())
+        n_all = self.world * self.n_pad
+        df1_part = torch.empty(n_all, K, dtype=torch.float32, device=dev)
+        call("han_attn_bwd_dst", ptr(be.by_dst_indptr), n_all, ptr(dl), K, ptr(df1_part), stream_ptr())
+        df1 = self.reduce_scatter_rows(df1_part)
+        return df1[:n_loc].contiguous()
+
+    # ---- loss / gradients ------------------------------------------------------------------------
+    def masked_loss(self, logits, labels, mask, train_op):
+        """This rank's share of masked CE (models/base_gattn.py:41-48 over the GLOBAL mask) plus
+        1/W of the L2 term, so that the all-reduced gradients equal the single-process ones."""
+        mask = mask.to(logits.dtype)
+        mask_total = self.all_reduce_sum(mask.sum().reshape(1))          # stays on the device: no host sync
+        labels = labels.to(logits.dtype)
+        xent = -(labels * torch.log_softmax(logits, dim=-1)).sum(-1)
+        return ((xent * mask).sum() / mask_total).squeeze(0) + train_op.l2_loss() / self.world
+
+    def all_reduce_grads(self, module: torch.nn.Module) -> None:
+        grads = [p.grad for p in module.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        td.all_reduce(flat, op=td.ReduceOp.SUM, group=self.group)
+        off = 0
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
+
+    def shutdown(self):
+        if td.is_initialized():
+            td.destroy_process_group()
+
+
+class _Gathered:
+    """G all-gathers issued back to back on the side stream; indexing waits for that table only."""
+
+    def __init__(self, shard: RowShard, Tp: torch.Tensor, full: List[torch.Tensor]):
+        self.full = full
+        self.events = []
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(shard.comm_stream):
+            shard.comm_stream.wait_event(ready)
+            for g in range(Tp.shape[0]):
+                td.all_gather_into_tensor(full[g], Tp[g].contiguous(), group=shard.group)
+                ev = torch.cuda.Event()
+                ev.record(shard.comm_stream)
+                self.events.append(ev)
+        for t in full:
+            t.record_stream(shard.comm_stream)
+        Tp.record_stream(shard.comm_stream)
+
+    def __getitem__(self, g: int) -> torch.Tensor:
+        torch.cuda.current_stream().wait_event(self.events[g])
+        return self.full[g]

@@ -170,6 +170,17 @@ class MetaPathGraph:
             self._t = t
         return self._t
 
+    def chunks(self):
+        """(chunk_rows int32[n_chunks+1], n_chunks): whole-row work items of ~2048 edges for the
+        chunked edge-stream kernels.  Built once per graph, cached."""
+        if getattr(self, "_chunks", None) is None:
+            n_chunks = int(query("han_csr_num_chunks", self.nnz))
+            with torch.cuda.device(self.device):
+                cr = torch.empty(n_chunks + 1, dtype=torch.int32, device=self.device)
+                call("han_csr_chunk_rows", ptr(self.indptr), self.n_rows, self.nnz, ptr(cr), stream_ptr())
+            self._chunks = (cr, n_chunks)
+        return self._chunks
+
     def row_slice(self, lo: int, hi: int) -> "MetaPathGraph":
         """Destination-row shard [lo, hi) (column ids stay global)."""
         base = int(self.indptr[lo].item())

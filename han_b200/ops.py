@@ -16,6 +16,11 @@ from .graph import MetaPathGraph
 
 _ACT = {"elu": _lib.ACT_ELU, "identity": _lib.ACT_IDENTITY}
 
+# Gather-kernel flavour: chunked cp.async edge-stream kernels (default) or the warp-per-row
+# register kernels (HAN_ATTN_CHUNKED=0; kept for A/B measurements, identical results).
+import os as _os
+CHUNKED = _os.environ.get("HAN_ATTN_CHUNKED", "1") != "0"
+
 
 def _empty(shape, device, dtype=torch.float32):
     return torch.empty(shape, dtype=dtype, device=device)
@@ -79,9 +84,15 @@ class NodeAttentionFn(torch.autograd.Function):
                 if graph.has_empty_rows():
                     # dense-path semantics of an all -1e9 row: uniform 1/N over all nodes
                     colmean = T_src[g][:, :D].mean(0).contiguous()
-                call("han_attn_fwd", ptr(graph.indptr), ptr(graph.indices), n, ptr(T_src[g]), ptr(R[g]),
-                     ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D, ptr(V[g]), ptr(colmean),
-                     stream_ptr())
+                if CHUNKED:
+                    cr, n_chunks = graph.chunks()
+                    call("han_attn_fwd_chunked", ptr(graph.indptr), ptr(graph.indices), ptr(cr), n_chunks, n,
+                         ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D,
+                         ptr(V[g]), ptr(colmean), stream_ptr())
+                else:
+                    call("han_attn_fwd", ptr(graph.indptr), ptr(graph.indices), n, ptr(T_src[g]), ptr(R[g]),
+                         ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D, ptr(V[g]), ptr(colmean),
+                         stream_ptr())
                 if plan.want_coefs:
                     alpha = _empty((graph.nnz, K), dev)
                     if graph.nnz:
@@ -110,7 +121,7 @@ class NodeAttentionFn(torch.autograd.Function):
             part_par = _empty((NB, 2 * D + 2 * K), dev)
             dbias = _empty((G, D), dev)
             dpar = _empty((G, 2 * D + 2 * K), dev)
-            max_nnz = max([g.nnz for g in plan.graphs] + [1])
+            # 1) row-local prep for every meta-path: dV, delta into the row records; bias gradient
             for g, graph in enumerate(plan.graphs):
                 if graph.has_empty_rows():
                     raise _lib.HanError("backward through rows without any edge is not supported "
@@ -118,16 +129,25 @@ class NodeAttentionFn(torch.autograd.Function):
                 call("han_attn_bwd_prep", ptr(dZ[:, g, :]), G * D, ptr(Z[:, g, :]), G * D, ptr(V[g]),
                      ptr(R[g]), n, K, H, plan.act, ptr(part_bias), stream_ptr())
                 call("han_reduce_partials", ptr(part_bias), NB, D, ptr(dbias[g]), stream_ptr())
+            # sharded: every rank needs the records of ALL destination rows (gathers overlap the passes)
+            R_all = dist.gather_records(R) if dist is not None else None
+            # 2) by-source gather pass, by-destination df1 sums, row-local finish
+            for g, graph in enumerate(plan.graphs):
                 if dist is None:
                     gt = graph.transpose()
                     dl = _empty((max(graph.nnz, 1), K), dev)
                     df1 = _empty((n, K), dev)
-                    call("han_attn_bwd_src", ptr(gt.indptr), ptr(gt.indices), ptr(gt.perm), n, ptr(T[g]),
-                         ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(dl), stream_ptr())
+                    if CHUNKED:
+                        cr, n_chunks = gt.chunks()
+                        call("han_attn_bwd_src_chunked", ptr(gt.indptr), ptr(gt.indices), ptr(gt.perm), ptr(cr),
+                             n_chunks, n, ptr(T[g]), ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(dl), stream_ptr())
+                    else:
+                        call("han_attn_bwd_src", ptr(gt.indptr), ptr(gt.indices), ptr(gt.perm), n, ptr(T[g]),
+                             ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(dl), stream_ptr())
                     call("han_attn_bwd_dst", ptr(graph.indptr), n, ptr(dl), K, ptr(df1), stream_ptr())
                     del dl
                 else:
-                    df1 = dist.backward_edges(plan, g, T[g], R[g], dS[g], df2)
+                    df1 = dist.backward_edges(plan, g, T[g], R_all[g], dS[g], df2)
                 call("han_attn_bwd_finish", ptr(T[g]), n, K, H, ptr(a1[g]), ptr(a2[g]), ptr(df1), ptr(df2),
                      ptr(dS[g]), ptr(part_par), stream_ptr())
                 call("han_reduce_partials", ptr(part_par), NB, 2 * D + 2 * K, ptr(dpar[g]), stream_ptr())

@@ -17,9 +17,10 @@
  *  - Node table T: [n][TS] fp32, TS = han_table_stride(K,H) = roundup(D + K, 4):
  *        T[j][0:D]   = S_j  = X_j W           (utils/layers.py:20)
  *        T[j][D:D+K] = f2_j = S_j a2 + b2     (utils/layers.py:24)
- *  - Row record R: [n][RS] fp32, RS = D + 4K:  [ dV (D) | f1 (K) | m (K) | rinv (K) | delta (K) ]
- *        f1 = S a1 + b1 (utils/layers.py:23), m/rinv = softmax row max / 1/rowsum (:27),
- *        dV, delta are filled by the backward.
+ *  - Row record R: [n][RS] fp32, RS = han_record_stride(K,H) = roundup(D + 3K, 4):
+ *        [ dV (D) | f1 (K) | lse (K) | delta (K) ]
+ *        f1 = S a1 + b1 (utils/layers.py:23); lse = log-sum-exp of the row's logits, so that
+ *        alpha_ij = exp(leaky_relu(f1_i + f2_j) - lse_i) (:27); dV, delta are filled by the backward.
  */
 #ifndef HAN_B200_H
 #define HAN_B200_H
@@ -95,19 +96,35 @@ int han_project_bwd(const float* X, int64_t n, int64_t F, int64_t ldx, const flo
 /* ---- K-B: fused CSR edge-softmax-aggregate. Replaces utils/layers.py:26-35,46 for K heads ---- */
 /* For destination rows [0,n_dst): alpha_ij = softmax_j(leaky_relu_0.2(f1_i + f2_j)), V_i = sum_j
  * alpha_ij S_j, out_i = act(V_i + bias).  T is indexed by the CSR's column ids; f1 is read from
- * R[:, D:D+K]; m and rinv are written to R[:, D+K:D+3K]; V to vsave [n_dst][D]; out to
+ * R[:, D:D+K]; lse is written to R[:, D+K:D+2K]; V to vsave [n_dst][D]; out to
  * out + i*out_stride (so K-B writes straight into Z[n][P][D], models/gat.py:46,58,60).
  * colmean (nullable) [D]: value used for rows with no edge at all (dense-path uniform 1/N row). */
 int han_attn_fwd(const int64_t* indptr, const int32_t* indices, int64_t n_dst, const float* T,
                  float* R, const float* bias, int K, int H, int act, float* out, int64_t out_stride,
                  float* vsave, const float* colmean, han_stream_t stream);
 
-/* Per-edge coefficients alpha [nnz][K] (utils/layers.py:43-44 return_coef), from saved m/rinv. */
+/* Per-edge coefficients alpha [nnz][K] (utils/layers.py:43-44 return_coef), from the saved lse. */
 int han_attn_coefs(const int64_t* indptr, const int32_t* indices, int64_t n_dst, const float* T,
                    const float* R, int K, int H, float* alpha, han_stream_t stream);
 
+/* Chunked edge-stream variants of K-B / the by-source pass of K-D (same results): a warp owns a
+ * contiguous chunk of whole rows (~2048 edges, boundaries precomputed once per graph) and pulls the
+ * gathered rows through a shared-memory cp.async ring, so bytes in flight do not depend on registers
+ * and work is balanced by edges, not rows.  chunk_rows: int32[han_csr_num_chunks(nnz) + 1]. */
+int64_t han_csr_num_chunks(int64_t nnz);
+int han_csr_chunk_rows(const int64_t* indptr, int64_t n_rows, int64_t nnz, int32_t* chunk_rows,
+                       han_stream_t stream);
+int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
+                         int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
+                         int K, int H, int act, float* out, int64_t out_stride, float* vsave,
+                         const float* colmean, han_stream_t stream);
+int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
+                             const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
+                             const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
+                             float* dl_edge, han_stream_t stream);
+
 /* ---- K-D: backward of K-B ----------------------------------------------------------------- */
-/* prep (row-local): dV = dout * act'(.), delta = <dV, V> per head -> R[:, 0:D], R[:, D+3K:D+4K];
+/* prep (row-local): dV = dout * act'(.), delta = <dV, V> per head -> R[:, 0:D], R[:, D+2K:D+3K];
  * dbias_partial [han_reduce_blocks()][D] per-block column sums of dV. */
 int han_reduce_blocks(void);
 int han_attn_bwd_prep(const float* dout, int64_t dout_stride, const float* out, int64_t out_stride,

@@ -55,8 +55,58 @@ def _product_node_attention(cfg, par, K, H, act_name, upstream, want_coefs=False
 SHAPES = [(8, 8), (4, 8), (1, 8), (8, 4), (2, 8), (8, 16), (16, 4), (1, 4), (4, 16)]
 
 
+@pytest.fixture(params=[True, False], ids=["chunked", "warp_per_row"])
+def flavour(request, monkeypatch):
+    """Both gather-kernel flavours (cp.async edge-stream chunks / warp-per-row registers)."""
+    from han_b200 import ops
+    monkeypatch.setattr(ops, "CHUNKED", request.param)
+    return request.param
+
+
+def test_chunk_boundaries_on_a_larger_graph(flavour):
+    """~75 chunks of 2048 edges: rows straddling batch and chunk boundaries, a row longer than a
+    whole chunk, runs of empty transposed rows; checked against the fp64 edge-list twin (forward)
+    and its autograd (backward)."""
+    import han_b200 as hb
+    from han_b200 import ops
+    rng = np.random.default_rng(77)
+    n, F, K, H = 5000, 24, 8, 8
+    deg = rng.integers(1, 60, size=n)
+    deg[1234] = 2400                                 # longer than one 2048-edge chunk
+    rows = []
+    for i in range(n):
+        c = rng.choice(n // 2, size=deg[i], replace=False)   # sources only in the first half: the
+        c[0] = min(i, n // 2 - 1) if i < n // 2 else c[0]     # transposed graph has 2500 empty rows
+        rows.append(np.unique(c).astype(np.int32))
+    indptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    indices = np.concatenate(rows)
+    X = rng.normal(size=(n, F)).astype(np.float32)
+    par = _rand_params(rng, F, 1, K, H)
+    up = torch.from_numpy(rng.normal(size=(n, 1, K * H)))
+    # oracle: edge-list twin per head
+    p64 = {k: v.clone().double().requires_grad_(True) for k, v in par.items()}
+    heads = []
+    for k in range(K):
+        hp = {"W": p64["W"][:, k * H:(k + 1) * H], "a1": p64["a1"][0, k], "b1": p64["b1"][0, k],
+              "a2": p64["a2"][0, k], "b2": p64["b2"][0, k], "bias": p64["bias"][0, k * H:(k + 1) * H]}
+        heads.append(O.attn_head_edges(torch.from_numpy(X).double(), indptr, indices, hp))
+    Zo = torch.cat(heads, -1).unsqueeze(1)
+    (Zo * up).sum().backward()
+    dev = torch.device("cuda")
+    p32 = {k: v.float().to(dev).requires_grad_(True) for k, v in par.items()}
+    g = hb.MetaPathGraph.from_csr(indptr, indices, n_cols=n)
+    plan = ops.NodeAttentionPlan(graphs=[g], K=K, H=H)
+    Z = ops.node_attention(plan, torch.from_numpy(X).to(dev), p32["W"], p32["a1"], p32["b1"], p32["a2"], p32["b2"],
+                           p32["bias"])
+    (Z * up.float().to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert_close(Z, Zo.detach(), "Z")
+    for k in p64:
+        assert_close(p32[k].grad, p64[k].grad, "d" + k)
+
+
 @pytest.mark.parametrize("K,H", SHAPES)
-def test_node_attention_fwd_bwd_parity(K, H):
+def test_node_attention_fwd_bwd_parity(K, H, flavour):
     cfg = synth.tiny(seed=K * 31 + H, n=131, f=37, p=2, deg=7.0)   # N, F not multiples of 32/4
     rng = np.random.default_rng(K * 100 + H)
     par = _rand_params(rng, cfg.F, cfg.P, K, H)
@@ -80,7 +130,7 @@ def test_identity_activation_and_three_metapaths():
         assert_close(gp[k], go[k], "d" + k)
 
 
-def test_degenerate_rows_and_long_rows():
+def test_degenerate_rows_and_long_rows(flavour):
     """single-neighbour rows (alpha == 1 exactly), a full row, a source every node attends to (long
     transposed row), rows longer than one 32-edge chunk, no-self-loop rows."""
     cfg = synth.tiny(seed=9, n=200, f=24, p=2, deg=3.0)
