@@ -31,6 +31,8 @@ import torch
 METRIC = "han_fwd_bwd_metapath_edges_per_s"
 UNIT = "edges/s"
 K_HEADS, HID, ATT = 8, 8, 128
+PROJ_NAMES = {0: "fp32 FFMA", 1: "tcgen05 3xTF32 (fp32-grade)", 2: "tcgen05 2xTF32 (0/1 features exact; fp32-grade)",
+              3: "tcgen05 TF32"}
 
 WORKLOADS = {
     "syn2m": "synthetic 2M-node heterograph, 4 meta-paths, avg degree 50, 256-d feats",
@@ -195,11 +197,14 @@ def run_ours(args):
         for g in wl["graphs"]:
             g.transpose()          # built once per graph (like adj_to_bias, outside the step)
     X1 = wl["X"].unsqueeze(0)
+    from han_b200 import synth as _synth
+    pmode = {"fp32": 0, "tf32x3": 1, "tf32x2": 2, "tf32": 3,
+             "auto": 2 if args.workload in _synth.SMALL else 1}[args.projection]   # SMALL configs: 0/1 features
 
     def step(Xin, graphs):
         hp.zero_grad(set_to_none=True)
         logits, _, _ = hb.HeteGAT_multi.inference([Xin] * P, C, N, True, 0.0, 0.0, graphs, [HID], [K_HEADS, 1],
-                                                  params=hp, dist=dist)
+                                                  params=hp, dist=dist, project_mode=pmode)
         if dist is None:
             ce = hb.BaseGAttN.masked_softmax_cross_entropy(logits.reshape(-1, C), wl["labels"], wl["mask"])
             total = ce + train.l2_loss()
@@ -288,7 +293,7 @@ def run_ours(args):
                       "edges": wl["edges"], "heads": K_HEADS, "hid": HID, "mp_att_size": ATT, "classes": C,
                       "parallelism": f"dst-row shards x{world}" if world > 1 else "single GPU",
                       "l2_policy": "inputs larger than L2" if flush is None else "L2 flushed between timed steps",
-                      "dropout": 0.0, "projection": "fp32 FFMA"},
+                      "dropout": 0.0, "projection": PROJ_NAMES[pmode]},
            "roofline": roofline, "e2e": e2e, "gpu_launches": rec.launches, "clocks": clocks,
            "loss": float(loss)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -409,6 +414,8 @@ def main():
     ap.add_argument("--workload", default="syn2m", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--projection", default="auto", choices=["auto", "fp32", "tf32x3", "tf32x2", "tf32"],
+                    help="K-A arithmetic: auto = tcgen05 3xTF32 (real-valued X) / 2xTF32 (0/1 features), both FP32-grade")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

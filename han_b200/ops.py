@@ -71,8 +71,23 @@ class NodeAttentionFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             T = _empty((G, n, TS), dev)
             R = _empty((G, n, RS), dev)
-            call("han_project_fwd", ptr(X), n, F, X.stride(0), ptr(W), G, K, H, ptr(a1), ptr(b1), ptr(a2),
-                 ptr(b2), ptr(T), ptr(R), plan.project_mode, stream_ptr())
+            if plan.project_mode == 0:
+                call("han_project_fwd", ptr(X), n, F, X.stride(0), ptr(W), G, K, H, ptr(a1), ptr(b1), ptr(a2),
+                     ptr(b2), ptr(T), ptr(R), 0, stream_ptr())
+            else:
+                # tcgen05 path: TMA needs 16-byte aligned rows; at most 4 meta-paths (256 TMEM columns) per launch
+                Xa = X
+                if X.stride(0) % 4 != 0 or X.data_ptr() % 16 != 0:
+                    Xa = torch.zeros(n, (F + 3) // 4 * 4, dtype=X.dtype, device=dev)
+                    Xa[:, :F] = X
+                for g0 in range(0, G, 4):
+                    g1 = min(G, g0 + 4)
+                    Wg = W[:, g0 * D:g1 * D].contiguous() if (g0, g1) != (0, G) else W
+                    ws_bytes = query("han_project_tc_workspace_bytes", F, g1 - g0, K, H)
+                    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                    call("han_project_fwd_tc", ptr(Xa), n, F, Xa.stride(0), ptr(Wg), g1 - g0, K, H, ptr(a1[g0]),
+                         ptr(b1[g0]), ptr(a2[g0]), ptr(b2[g0]), ptr(T[g0]), ptr(R[g0]), plan.project_mode, ptr(ws),
+                         ws_bytes, stream_ptr(), kernels=2)
             # sources of every local destination row: all-gather the node tables when sharded
             T_src = dist.all_gather_rows(T) if dist is not None else T
             Z = _empty((n, G, D), dev)
@@ -155,7 +170,7 @@ class NodeAttentionFn(torch.autograd.Function):
             ws_bytes = query("han_project_bwd_workspace_bytes", n, F, G, D)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             call("han_project_bwd", ptr(X), n, F, X.stride(0), ptr(dS), G, D, ptr(dW), ptr(ws), ws_bytes,
-                 plan.project_mode, stream_ptr())
+                 0, stream_ptr())   # dW stays on the exact-FP32 FFMA kernel for now
         da1 = dpar[:, :D].reshape(G, K, H)
         da2 = dpar[:, D:2 * D].reshape(G, K, H)
         db1 = dpar[:, 2 * D:2 * D + K]

@@ -87,6 +87,16 @@ int han_project_fwd(const float* X, int64_t n, int64_t F, int64_t ldx, const flo
                     int H, const float* a1, const float* b1, const float* a2, const float* b2,
                     float* T, float* R, int mode, han_stream_t stream);
 
+/* The same projection on the tcgen05 tensor cores (TMA-staged operands, TMEM accumulators, f1/f2
+ * fused into the epilogue).  K = H = 8, 1 <= G <= 4 (<= 256 accumulator columns), X 16-byte aligned
+ * with ldx % 4 == 0.  mode 1 = 3xTF32 (X and W split hi+lo: FP32-grade), 2 = 2xTF32 (X exactly
+ * representable in tf32, e.g. 0/1 features; only W split), 3 = plain TF32.
+ * ws: han_project_tc_workspace_bytes (transposed hi/lo copies of W). */
+size_t han_project_tc_workspace_bytes(int64_t F, int G, int K, int H);
+int han_project_fwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const float* W, int G, int K,
+                       int H, const float* a1, const float* b1, const float* a2, const float* b2,
+                       float* T, float* R, int mode, void* ws, size_t ws_bytes, han_stream_t stream);
+
 /* dW [F][G*D] = X^T dS  (split over rows + deterministic reduce).  dS [G][n][D].
  * ws: han_project_bwd_workspace_bytes. */
 size_t han_project_bwd_workspace_bytes(int64_t n, int64_t F, int G, int D);

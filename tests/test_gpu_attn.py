@@ -118,6 +118,30 @@ def test_node_attention_fwd_bwd_parity(K, H, flavour):
         assert_close(gp[k], go[k], "d" + k)
 
 
+@pytest.mark.parametrize("mode,binary,rel", [(1, False, 1e-5), (2, True, 1e-5), (3, False, 1e-2)])
+@pytest.mark.parametrize("n,F,P", [(300, 37, 2), (515, 256, 4), (130, 96, 5), (128, 32, 1)])
+def test_tensor_core_projection(mode, binary, rel, n, F, P):
+    """K-A on tcgen05 (TMA + TMEM): 3xTF32 must meet the FP32 bound, 2xTF32 too when X is exactly
+    representable in tf32 (0/1 features), plain TF32 the looser stated bound."""
+    import han_b200 as hb
+    from han_b200 import ops
+    cfg = synth.tiny(seed=n + F + P, n=n, f=F, p=P, deg=6.0, binary=binary)
+    rng = np.random.default_rng(n * 7 + F)
+    par = _rand_params(rng, F, P, 8, 8)
+    up = torch.from_numpy(rng.normal(size=(n, P, 64)))
+    Zo, go, _ = _oracle_node_attention(cfg, par, 8, 8, O.elu, up)
+    dev = torch.device("cuda")
+    p = {k: v.float().to(dev).requires_grad_(True) for k, v in par.items()}
+    graphs = [hb.process.adj_to_bias(a, [cfg.N]) for a in cfg.adjs()]
+    plan = ops.NodeAttentionPlan(graphs=graphs, K=8, H=8, project_mode=mode)
+    Z = ops.node_attention(plan, torch.from_numpy(cfg.X).to(dev), p["W"], p["a1"], p["b1"], p["a2"], p["b2"], p["bias"])
+    (Z * up.float().to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert_close(Z, Zo, "Z", rel=rel, rtol=max(1e-4, 30 * rel))
+    for k in go:
+        assert_close(p[k].grad, go[k], "d" + k, rel=rel, rtol=max(1e-4, 30 * rel))
+
+
 def test_identity_activation_and_three_metapaths():
     cfg = synth.tiny(seed=5, n=64, f=16, p=3, deg=4.0)
     rng = np.random.default_rng(55)
