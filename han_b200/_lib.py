@@ -41,6 +41,7 @@ _SIGNATURES = {
     "han_project_bwd": (c_int, [P, I64, I64, I64, P, I, I, P, P, SZ, I, P]),
     "han_attn_fwd": (c_int, [P, P, I64, P, P, P, I, I, I, P, I64, P, P, P]),
     "han_attn_coefs": (c_int, [P, P, I64, P, P, I, I, P, P]),
+    "han_csr_chunk_edges": (c_int64, [I64]),
     "han_csr_num_chunks": (c_int64, [I64]),
     "han_csr_chunk_rows": (c_int, [P, I64, I64, P, P]),
     "han_attn_fwd_chunked": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P]),

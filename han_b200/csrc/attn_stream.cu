@@ -3,7 +3,7 @@
 // Why: the warp-per-row kernels in attn_fwd.cu / attn_bwd.cu hold every gathered row in registers,
 // so registers cap both occupancy and the number of rows in flight (ncu on B200: 35% / 21% warps
 // active, 67% / 35% DRAM utilisation).  Here a warp owns a contiguous CHUNK of the CSR edge stream
-// (whole rows, ~kChunkEdges edges, boundaries precomputed per graph by han_csr_chunk_rows) and
+// (whole rows, ~chunk_edges edges, boundaries precomputed per graph by han_csr_chunk_rows) and
 // pulls the gathered rows through a per-warp shared-memory ring with cp.async (LDGSTS, 16 B per
 // lane, L2-only): STAGES-1 batches of 16 records are always in flight per warp, independent of
 // registers, and work is balanced by edges instead of by rows, so degree skew does not matter.
@@ -12,7 +12,8 @@
 
 namespace han {
 
-constexpr int kChunkEdges = 2048;   // edges per work item (whole rows; boundaries from chunk_rows)
+constexpr int kMaxChunkEdges = 2048;   // edges per work item (whole rows; boundaries from chunk_rows)
+constexpr int kMinChunkEdges = 128;
 constexpr int kBatch = 16;          // records per cp.async group
 constexpr int kStreamWarps = 4;     // warps per CTA
 
@@ -26,17 +27,17 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// chunk_rows[c] = first row whose start offset indptr[r] >= c * kChunkEdges, c in [0, n_chunks);
-// chunk_rows[n_chunks] = n_rows.  n_chunks = nnz / kChunkEdges + 1.
+// chunk_rows[c] = first row whose start offset indptr[r] >= c * chunk_edges, c in [0, n_chunks);
+// chunk_rows[n_chunks] = n_rows.  n_chunks = nnz / chunk_edges + 1.
 __global__ void chunk_rows_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, int64_t n_chunks,
-                                  int32_t* __restrict__ chunk_rows) {
+                                  int64_t chunk_edges, int32_t* __restrict__ chunk_rows) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c > n_chunks) return;
   if (c == n_chunks) {
     chunk_rows[c] = (int32_t)n_rows;
     return;
   }
-  const int64_t target = c * kChunkEdges;
+  const int64_t target = c * chunk_edges;
   int64_t lo = 0, hi = n_rows;  // lower_bound over indptr[0 .. n_rows)
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
@@ -428,14 +429,24 @@ using namespace han;
 
 extern "C" {
 
-int64_t han_csr_num_chunks(int64_t nnz) { return nnz / kChunkEdges + 1; }
+// Work-item size: ~2048 edges on large graphs (amortises the pipeline fill), smaller on small graphs so
+// that there are at least ~32 work items per SM.
+int64_t han_csr_chunk_edges(int64_t nnz) {
+  int64_t c = nnz / ((int64_t)kNumSMs * 32);
+  if (c > kMaxChunkEdges) c = kMaxChunkEdges;
+  if (c < kMinChunkEdges) c = kMinChunkEdges;
+  return c;
+}
+
+int64_t han_csr_num_chunks(int64_t nnz) { return nnz / han_csr_chunk_edges(nnz) + 1; }
 
 int han_csr_chunk_rows(const int64_t* indptr, int64_t n_rows, int64_t nnz, int32_t* chunk_rows,
                        han_stream_t stream) {
   HAN_REQUIRE(indptr && chunk_rows, "null pointer");
   HAN_REQUIRE(n_rows > 0 && nnz >= 0 && n_rows < ((int64_t)1 << 31), "sizes");
-  const int64_t n_chunks = nnz / kChunkEdges + 1;
-  chunk_rows_kernel<<<(unsigned)ceil_div64(n_chunks + 1, 256), 256, 0, as_stream(stream)>>>(indptr, n_rows, n_chunks,
+  const int64_t ce = han_csr_chunk_edges(nnz);
+  const int64_t n_chunks = nnz / ce + 1;
+  chunk_rows_kernel<<<(unsigned)ceil_div64(n_chunks + 1, 256), 256, 0, as_stream(stream)>>>(indptr, n_rows, n_chunks, ce,
                                                                                            chunk_rows);
   return check_launch(__func__);
 }

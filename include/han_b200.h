@@ -82,7 +82,8 @@ int han_csr_sort_rows(int64_t n_rows, const int64_t* indptr, int32_t* indices, i
 /* ---- K-A: projection. Replaces utils/layers.py:20,23,24 for G groups of K heads at once ----- */
 /* X [n][ldx] (F columns used), W [F][G*D] (meta-path g, head k in columns g*D + k*H ...),
  * a1,a2 [G][K][H], b1,b2 [G][K].  Writes T [G][n][TS] and f1 into R[g][:, D:D+K] (R [G][n][RS]).
- * mode: 0 = fp32 CUDA-core FFMA; 1 = tcgen05 3xTF32 (fp32-grade); 2 = tcgen05 1xTF32. */
+ * mode must be 0: exact-FP32 CUDA-core FFMA, any supported (K,H), any alignment; the tensor-core
+ * variants are han_project_fwd_tc below. */
 int han_project_fwd(const float* X, int64_t n, int64_t F, int64_t ldx, const float* W, int G, int K,
                     int H, const float* a1, const float* b1, const float* a2, const float* b2,
                     float* T, float* R, int mode, han_stream_t stream);
@@ -118,9 +119,10 @@ int han_attn_coefs(const int64_t* indptr, const int32_t* indices, int64_t n_dst,
                    const float* R, int K, int H, float* alpha, han_stream_t stream);
 
 /* Chunked edge-stream variants of K-B / the by-source pass of K-D (same results): a warp owns a
- * contiguous chunk of whole rows (~2048 edges, boundaries precomputed once per graph) and pulls the
+ * contiguous chunk of whole rows (~han_csr_chunk_edges(nnz) edges, boundaries precomputed once per graph) and pulls the
  * gathered rows through a shared-memory cp.async ring, so bytes in flight do not depend on registers
  * and work is balanced by edges, not rows.  chunk_rows: int32[han_csr_num_chunks(nnz) + 1]. */
+int64_t han_csr_chunk_edges(int64_t nnz);   /* ~nnz/(148*32) clamped to [128, 2048] */
 int64_t han_csr_num_chunks(int64_t nnz);
 int han_csr_chunk_rows(const int64_t* indptr, int64_t n_rows, int64_t nnz, int32_t* chunk_rows,
                        han_stream_t stream);

@@ -41,7 +41,8 @@ def test_host_queries(lib):
     assert lib.han_attn_shape_supported(3, 5) == 0
     assert lib.han_table_stride(8, 8) == 72 and lib.han_record_stride(8, 8) == 88
     assert lib.han_table_stride(1, 8) == 12 and lib.han_record_stride(1, 8) == 12
-    assert lib.han_csr_num_chunks(0) == 1 and lib.han_csr_num_chunks(5000) == 3
+    assert lib.han_csr_num_chunks(0) == 1 and lib.han_csr_num_chunks(5000) == 5000 // 128 + 1
+    assert lib.han_csr_chunk_edges(100_000_000) == 2048 and lib.han_csr_chunk_edges(2_000_000) == 422
     assert lib.han_semantic_shape_supported(64, 128) == 1
     assert lib.han_reduce_blocks() > 0
     assert lib.han_scan_workspace_bytes(2_000_000) >= 8 * (2_000_000 // 2048)
