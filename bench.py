@@ -171,6 +171,8 @@ def algorithmic_bytes(name, wl):
 # our arm
 # --------------------------------------------------------------------------------------------------
 def run_ours(args):
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line only)
     import han_b200 as hb
     from han_b200 import _lib
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,8 +239,18 @@ def run_ours(args):
         torch.cuda.synchronize()
     barrier()
 
-    rec = _lib.CallRecorder(time_events=True)
-    _lib.set_recorder(rec)
+    # launch count of one step (eager, counted by the ctypes layer), then optional whole-step graph capture
+    counter = _lib.CallRecorder(time_events=False)
+    _lib.set_recorder(counter)
+    step(X1, wl["graphs"])
+    _lib.set_recorder(None)
+    launches_per_step = counter.launches
+    run_step = lambda: step(X1, wl["graphs"])
+    if args.cuda_graph:
+        from han_b200.graphs import GraphedStep
+        run_step = GraphedStep(run_step, warmup=1)
+    barrier()
+
     mark_lo = sampler.mark()
     torch.cuda.nvtx.range_push("han_timed")
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -247,14 +259,27 @@ def run_ours(args):
         if flush is not None:
             flush.zero_()
         s.record()
-        loss = step(X1, wl["graphs"])
+        loss = run_step()
         e.record()
     barrier()
     torch.cuda.nvtx.range_pop()
-    _lib.set_recorder(None)
     if rank == 0:
         time.sleep(0.25)     # let the sampler flush the samples taken during the region
     clocks = sampler.stop(max(0, mark_lo - 1), None) if rank == 0 else None
+    # per-kernel CUDA events: the same K steps again, eagerly, with an event pair around every C-ABI call
+    # (graph replays cannot carry timing events; kernel durations do not depend on how they are launched)
+    rec = _lib.CallRecorder(time_events=True)
+    _lib.set_recorder(rec)
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for s, e in ev2:
+        if flush is not None:
+            flush.zero_()
+        s.record()
+        step(X1, wl["graphs"])
+        e.record()
+    barrier()
+    _lib.set_recorder(None)
+    eager_ms = sum(s.elapsed_time(e) for s, e in ev2) / len(ev2)
     step_ms = [s.elapsed_time(e) for s, e in ev]
     ms = sum(step_ms) / len(step_ms)
     loss = loss.detach().clone().reshape(1)
@@ -280,7 +305,9 @@ def run_ours(args):
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": round(tot_ms / calls, 4),
                 "algorithmic_bytes_per_launch": int(algorithmic_bytes(top, wl) / launches_per_set),
-                "kernel_share_of_step": round(tot_ms / sum(step_ms), 4),
+                "kernel_share_of_step": round(tot_ms / (eager_ms * args.steps), 4),
+                "timing": "per-launch CUDA events over K eager steps run right after the timed region",
+                "eager_ms_per_step": round(eager_ms, 3),
                 "kernels_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in sorted(summ.items())}}
 
     # ---- end-to-end through the public API with HOST buffers -----------------------------------
@@ -294,7 +321,8 @@ def run_ours(args):
                       "parallelism": f"dst-row shards x{world}" if world > 1 else "single GPU",
                       "l2_policy": "inputs larger than L2" if flush is None else "L2 flushed between timed steps",
                       "dropout": 0.0, "projection": PROJ_NAMES[pmode]},
-           "roofline": roofline, "e2e": e2e, "gpu_launches": rec.launches, "clocks": clocks,
+           "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+           "cuda_graph": bool(args.cuda_graph),
            "loss": float(loss)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=20.0)
@@ -414,6 +442,8 @@ def main():
     ap.add_argument("--workload", default="syn2m", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
+                    help="launch every kernel from Python instead of replaying the captured step")
     ap.add_argument("--projection", default="auto", choices=["auto", "fp32", "tf32x3", "tf32x2", "tf32"],
                     help="K-A arithmetic: auto = tcgen05 3xTF32 (real-valued X) / 2xTF32 (0/1 features), both FP32-grade")
     args = ap.parse_args()

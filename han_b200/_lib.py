@@ -49,7 +49,7 @@ _SIGNATURES = {
     "han_reduce_blocks": (c_int, []),
     "han_attn_bwd_prep": (c_int, [P, I64, P, I64, P, P, I64, I, I, I, P, P]),
     "han_attn_bwd_src": (c_int, [P, P, P, I64, P, P, I, I, P, P, P, P]),
-    "han_attn_bwd_dst": (c_int, [P, I64, P, I, P, P]),
+    "han_attn_bwd_dst": (c_int, [P, I64, I64, P, I, P, P]),
     "han_attn_bwd_finish": (c_int, [P, I64, I, I, P, P, P, P, P, P, P]),
     "han_reduce_partials": (c_int, [P, I, I64, P, P]),
     "han_semantic_shape_supported": (c_int, [I, I]),

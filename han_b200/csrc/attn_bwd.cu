@@ -184,6 +184,27 @@ attn_bwd_dst_kernel(const int64_t* __restrict__ indptr, int64_t n_dst, const flo
   if (slot == 0) df1[row * K + head] = s;
 }
 
+// short-row variant (sharded runs: ~degree/world edges per row): a K-lane group owns a row, 32/K rows per warp
+template <int K>
+__global__ void __launch_bounds__(256)
+attn_bwd_dst_short_kernel(const int64_t* __restrict__ indptr, int64_t n_dst, const float* __restrict__ dl_edge,
+                          float* __restrict__ df1) {
+  constexpr int SLOTS = 32 / K;
+  const int lane = threadIdx.x & 31;
+  const int head = lane % K, slot = lane / K;
+  const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * SLOTS + slot;
+  if (row >= n_dst) return;
+  const int64_t start = indptr[row], end = indptr[row + 1];
+  float s0 = 0.f, s1 = 0.f;
+  int64_t e = start;
+  for (; e + 1 < end; e += 2) {
+    s0 += __ldg(dl_edge + e * K + head);
+    s1 += __ldg(dl_edge + (e + 1) * K + head);
+  }
+  if (e < end) s0 += __ldg(dl_edge + e * K + head);
+  df1[row * K + head] = s0 + s1;
+}
+
 // ---- finish: row-local; dS_tot = dS_agg + df1 a1^T + df2 a2^T and parameter-gradient partials ----
 template <int K, int H>
 __global__ void __launch_bounds__(256)
@@ -303,20 +324,24 @@ int han_attn_bwd_src(const int64_t* t_indptr, const int32_t* t_indices, const in
   return fail_arg(__func__, "unsupported (K,H)");
 }
 
-int han_attn_bwd_dst(const int64_t* indptr, int64_t n_dst, const float* dl_edge, int K, float* df1,
+int han_attn_bwd_dst(const int64_t* indptr, int64_t n_dst, int64_t nnz, const float* dl_edge, int K, float* df1,
                      han_stream_t stream) {
   HAN_REQUIRE(indptr && dl_edge && df1, "null pointer");
-  HAN_REQUIRE(n_dst > 0, "n_dst > 0 required");
-  unsigned grid = (unsigned)ceil_div64(n_dst, 8);
+  HAN_REQUIRE(n_dst > 0 && nnz >= 0, "n_dst > 0 required");
   cudaStream_t st = as_stream(stream);
+  const bool short_rows = nnz < 16 * n_dst;   // mean degree < 16: one K-lane group per row
+#define HAN_DST(k)                                                                                       \
+  case k:                                                                                                \
+    if (short_rows)                                                                                      \
+      attn_bwd_dst_short_kernel<k><<<(unsigned)ceil_div64(n_dst, 8 * (32 / k)), 256, 0, st>>>(indptr, n_dst, dl_edge, df1); \
+    else                                                                                                 \
+      attn_bwd_dst_kernel<k><<<(unsigned)ceil_div64(n_dst, 8), 256, 0, st>>>(indptr, n_dst, dl_edge, df1); \
+    break;
   switch (K) {
-    case 1: attn_bwd_dst_kernel<1><<<grid, 256, 0, st>>>(indptr, n_dst, dl_edge, df1); break;
-    case 2: attn_bwd_dst_kernel<2><<<grid, 256, 0, st>>>(indptr, n_dst, dl_edge, df1); break;
-    case 4: attn_bwd_dst_kernel<4><<<grid, 256, 0, st>>>(indptr, n_dst, dl_edge, df1); break;
-    case 8: attn_bwd_dst_kernel<8><<<grid, 256, 0, st>>>(indptr, n_dst, dl_edge, df1); break;
-    case 16: attn_bwd_dst_kernel<16><<<grid, 256, 0, st>>>(indptr, n_dst, dl_edge, df1); break;
+    HAN_DST(1) HAN_DST(2) HAN_DST(4) HAN_DST(8) HAN_DST(16)
     default: return fail_arg(__func__, "unsupported K");
   }
+#undef HAN_DST
   return check_launch(__func__);
 }
 

@@ -186,7 +186,7 @@ class RowShard:
              n_loc, ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), ptr(dl), stream_ptr())
         n_all = self.world * self.n_pad
         df1_part = torch.empty(n_all, K, dtype=torch.float32, device=dev)
-        call("han_attn_bwd_dst", ptr(be.by_dst_indptr), n_all, ptr(dl), K, ptr(df1_part), stream_ptr())
+        call("han_attn_bwd_dst", ptr(be.by_dst_indptr), n_all, bs.nnz, ptr(dl), K, ptr(df1_part), stream_ptr())
         df1 = self.reduce_scatter_rows(df1_part)
         return df1[:n_loc].contiguous()
 

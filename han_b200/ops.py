@@ -159,7 +159,7 @@ class NodeAttentionFn(torch.autograd.Function):
                     else:
                         call("han_attn_bwd_src", ptr(gt.indptr), ptr(gt.indices), ptr(gt.perm), n, ptr(T[g]),
                              ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(dl), stream_ptr())
-                    call("han_attn_bwd_dst", ptr(graph.indptr), n, ptr(dl), K, ptr(df1), stream_ptr())
+                    call("han_attn_bwd_dst", ptr(graph.indptr), n, graph.nnz, ptr(dl), K, ptr(df1), stream_ptr())
                     del dl
                 else:
                     df1 = dist.backward_edges(plan, g, T[g], R_all[g], dS[g], df2)

