@@ -327,9 +327,15 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=20.0)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if dist:
-        dist.shutdown()
+        # Leave without tearing NCCL down: destroying a communicator whose collectives were captured in a
+        # CUDA graph can block at interpreter exit; all results are out, all ranks are past the last barrier.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_e2e(args, wl, hp, train, dist, dev, step):

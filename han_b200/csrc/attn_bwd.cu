@@ -17,12 +17,29 @@
 
 namespace han {
 
+// multimem.st: one store to a multicast address lands in the same offset of every rank's buffer (NVLS)
+__device__ __forceinline__ void mc_store4(float* p, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void mc_store1(float* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// local rows -> multicast rows (for producers without a fused multicast epilogue)
+__global__ void multicast_copy_kernel(const float4* __restrict__ src, float* __restrict__ dst_mc, int64_t n_vec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x)
+    mc_store4(dst_mc + 4 * i, src[i]);
+}
+
 // ---- prep: row-local ---------------------------------------------------------------------------
 template <int K, int H>
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const float* __restrict__ dout, int64_t dout_stride, const float* __restrict__ out,
                      int64_t out_stride, const float* __restrict__ vsave, float* __restrict__ R,
-                     int64_t n_dst, int act, float* __restrict__ dbias_partial) {
+                     int64_t n_dst, int act, float* __restrict__ dbias_partial, float* __restrict__ Rmc,
+                     int64_t r_row0) {
   constexpr int D = K * H;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
   // thread = (row, head); a block covers 256/K consecutive rows; grid-stride over row tiles
@@ -49,10 +66,20 @@ attn_bwd_prep_kernel(const float* __restrict__ dout, int64_t dout_stride, const 
         }
         const float4 v = ldg4_stream(vsave + row * D + head * H + 4 * q);
         delta += g.x * v.x + g.y * v.y + g.z * v.z + g.w * v.w;
-        *reinterpret_cast<float4*>(R + row * RS + head * H + 4 * q) = g;
+        if (Rmc != nullptr)   // sharded: the record goes to every rank's copy with one multicast store
+          mc_store4(Rmc + (r_row0 + row) * RS + head * H + 4 * q, g);
+        else
+          *reinterpret_cast<float4*>(R + row * RS + head * H + 4 * q) = g;
         colsum[4 * q] += g.x; colsum[4 * q + 1] += g.y; colsum[4 * q + 2] += g.z; colsum[4 * q + 3] += g.w;
       }
-      R[row * RS + D + 2 * K + head] = delta;
+      if (Rmc != nullptr) {
+        float* rp = Rmc + (r_row0 + row) * RS + D + head;
+        mc_store1(rp, R[row * RS + D + head]);              // f1  (written by the projection, local)
+        mc_store1(rp + K, R[row * RS + D + K + head]);      // lse (written by the forward, local)
+        mc_store1(rp + 2 * K, delta);
+      } else {
+        R[row * RS + D + 2 * K + head] = delta;
+      }
     }
   }
   // block reduce of column sums over the ROWS sub-rows -> dbias_partial[block][D]
@@ -289,16 +316,27 @@ extern "C" {
 
 int han_reduce_blocks(void) { return kReduceBlocks; }
 
+int han_multicast_copy(const float* src, float* dst_mc, int64_t n_floats, han_stream_t stream) {
+  HAN_REQUIRE(src && dst_mc, "null pointer");
+  HAN_REQUIRE(n_floats > 0 && n_floats % 4 == 0, "n_floats must be a positive multiple of 4");
+  HAN_REQUIRE(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst_mc % 16 == 0), "16-byte alignment");
+  // a small grid is enough to saturate NVLink egress and leaves the SMs to the compute kernels
+  multicast_copy_kernel<<<kNumSMs / 4, 512, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(src), dst_mc,
+                                                                   n_floats / 4);
+  return check_launch(__func__);
+}
+
 int han_attn_bwd_prep(const float* dout, int64_t dout_stride, const float* out, int64_t out_stride,
                       const float* vsave, float* R, int64_t n_dst, int K, int H, int act,
-                      float* dbias_partial, han_stream_t stream) {
+                      float* dbias_partial, float* R_mc, int64_t r_row0, han_stream_t stream) {
   HAN_REQUIRE(dout && out && vsave && R && dbias_partial, "null pointer");
-  HAN_REQUIRE(n_dst > 0, "n_dst > 0 required");
+  HAN_REQUIRE(n_dst > 0 && r_row0 >= 0, "n_dst > 0 required");
   HAN_REQUIRE(dout_stride % 4 == 0 && out_stride % 4 == 0, "strides must be multiples of 4 floats");
+  HAN_REQUIRE((uintptr_t)R_mc % 16 == 0, "multicast records must be 16-byte aligned");
 #define X(k, h)                                                                                        \
   if (K == k && H == h) {                                                                              \
     attn_bwd_prep_kernel<k, h><<<kReduceBlocks, 256, 0, as_stream(stream)>>>(                          \
-        dout, dout_stride, out, out_stride, vsave, R, n_dst, act, dbias_partial);                      \
+        dout, dout_stride, out, out_stride, vsave, R, n_dst, act, dbias_partial, R_mc, r_row0);        \
     return check_launch(__func__);                                                                     \
   }
   HAN_FOR_SHAPES(X)

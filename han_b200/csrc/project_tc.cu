@@ -89,6 +89,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 16-byte row store: plain, or multimem.st to a multicast address (one store, every rank's copy)
+__device__ __forceinline__ void store_row16(float* p, bool multicast, float a, float b, float c, float d) {
+  if (multicast)
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
+                 "f"(d)
+                 : "memory");
+  else
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -118,7 +128,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                   const __grid_constant__ CUtensorMap tmBlo, int64_t n_rows, int nkb, int G,
                   const float* __restrict__ a1, const float* __restrict__ b1, const float* __restrict__ a2,
-                  const float* __restrict__ b2, float* __restrict__ T, float* __restrict__ R) {
+                  const float* __restrict__ b2, float* __restrict__ T, float* __restrict__ R,
+                  float* __restrict__ Tmc, int64_t t_rows, int64_t t_row0) {
   constexpr int D = 64, K = 8, H = 8, TS = 72, RS = 88;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -256,17 +267,21 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           f1[k] = s1;
           f2[k] = s2;
         }
-        float4* tp = reinterpret_cast<float4*>(T + ((int64_t)g * n_rows + row) * TS);
+        // node-table row: local store, or ONE multicast store per 16 B that NVSwitch replicates into the
+        // same offset of every rank's table (GEMM epilogue fused with the all-gather)
+        float* tbase = (Tmc != nullptr) ? Tmc + ((int64_t)g * t_rows + t_row0 + row) * TS
+                                        : T + ((int64_t)g * n_rows + row) * TS;
+        const bool mc = Tmc != nullptr;
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          tp[c] = make_float4(__uint_as_float(v0[4 * c]), __uint_as_float(v0[4 * c + 1]), __uint_as_float(v0[4 * c + 2]),
-                              __uint_as_float(v0[4 * c + 3]));
+          store_row16(tbase + 4 * c, mc, __uint_as_float(v0[4 * c]), __uint_as_float(v0[4 * c + 1]),
+                      __uint_as_float(v0[4 * c + 2]), __uint_as_float(v0[4 * c + 3]));
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          tp[8 + c] = make_float4(__uint_as_float(v1[4 * c]), __uint_as_float(v1[4 * c + 1]),
-                                  __uint_as_float(v1[4 * c + 2]), __uint_as_float(v1[4 * c + 3]));
-        tp[16] = make_float4(f2[0], f2[1], f2[2], f2[3]);
-        tp[17] = make_float4(f2[4], f2[5], f2[6], f2[7]);
+          store_row16(tbase + 32 + 4 * c, mc, __uint_as_float(v1[4 * c]), __uint_as_float(v1[4 * c + 1]),
+                      __uint_as_float(v1[4 * c + 2]), __uint_as_float(v1[4 * c + 3]));
+        store_row16(tbase + 64, mc, f2[0], f2[1], f2[2], f2[3]);
+        store_row16(tbase + 68, mc, f2[4], f2[5], f2[6], f2[7]);
         float4* rp = reinterpret_cast<float4*>(R + ((int64_t)g * n_rows + row) * RS + D);
         rp[0] = make_float4(f1[0], f1[1], f1[2], f1[3]);
         rp[1] = make_float4(f1[4], f1[5], f1[6], f1[7]);
@@ -331,8 +346,11 @@ size_t han_project_tc_workspace_bytes(int64_t F, int G, int K, int H) {
 
 int han_project_fwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const float* W, int G, int K, int H,
                        const float* a1, const float* b1, const float* a2, const float* b2, float* T, float* R,
-                       int mode, void* ws, size_t ws_bytes, han_stream_t stream) {
-  HAN_REQUIRE(X && W && a1 && b1 && a2 && b2 && T && R && ws, "null pointer");
+                       float* T_mc, int64_t t_rows, int64_t t_row0, int mode, void* ws, size_t ws_bytes,
+                       han_stream_t stream) {
+  HAN_REQUIRE(X && W && a1 && b1 && a2 && b2 && (T || T_mc) && R && ws, "null pointer");
+  HAN_REQUIRE(T_mc == nullptr || (t_rows >= t_row0 + n && t_row0 >= 0 && (uintptr_t)T_mc % 16 == 0),
+              "multicast table: t_row0 + n <= t_rows, 16-byte aligned");
   HAN_REQUIRE(K == 8 && H == 8, "the tensor-core projection is built for K = H = 8");
   HAN_REQUIRE(G >= 1 && G <= 4, "1 <= G <= 4 meta-paths per launch (256 accumulator columns)");
   HAN_REQUIRE(mode >= 1 && mode <= 3, "mode 1 (3xTF32), 2 (2xTF32, tf32-exact X) or 3 (TF32)");
@@ -363,11 +381,14 @@ int han_project_fwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const 
     attr = true;
   }
   if (mode == 1)
-    project_tc_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, a2, b2, T, R);
+    project_tc_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, a2, b2, T, R,
+                                                                  T_mc, t_rows, t_row0);
   else if (mode == 2)
-    project_tc_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, a2, b2, T, R);
+    project_tc_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, a2, b2, T, R,
+                                                                  T_mc, t_rows, t_row0);
   else
-    project_tc_kernel<3><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, a2, b2, T, R);
+    project_tc_kernel<3><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, a2, b2, T, R,
+                                                                  T_mc, t_rows, t_row0);
   return check_launch(__func__);
 }
 

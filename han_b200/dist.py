@@ -64,12 +64,55 @@ class _BackwardEdges:
         self.pos_in_dst = pos_in_dst        # int32[nnz]: by-source edge -> slot in by-destination order
 
 
+class SymmetricTables:
+    """Full-size node table T [G][W*n_pad][TS] and record table R [G][W*n_pad][RS] in symmetric memory
+    (torch.distributed._symmetric_memory): every rank holds a copy at the same offsets and one NVLS
+    MULTICAST address maps all copies, so a producer kernel's ``multimem.st`` lands in every rank's
+    table (NVSwitch replicates it) -- the exchange is fused into the producers (projection epilogue,
+    backward prep) instead of being a separate collective.  ``fence_*`` is the cross-rank barrier that
+    says "everyone's rows have landed" / "nobody reads the old contents any more"."""
+
+    def __init__(self, shard: "RowShard", G: int, TS: int, RS: int):
+        import torch.distributed._symmetric_memory as symm
+        dev = shard.device
+        n_all = shard.world * shard.n_pad
+        self.G, self.TS, self.RS, self.n_all = G, TS, RS, n_all
+        self.T = symm.empty(G * n_all * TS, dtype=torch.float32, device=dev)
+        self.hT = symm.rendezvous(self.T, td.group.WORLD)
+        self.R = symm.empty(G * n_all * RS, dtype=torch.float32, device=dev)
+        self.hR = symm.rendezvous(self.R, td.group.WORLD)
+        self.T_mc = int(self.hT.multicast_ptr)
+        self.R_mc = int(self.hR.multicast_ptr)
+        if not self.T_mc or not self.R_mc:
+            raise RuntimeError("symmetric memory has no multicast (NVLS) mapping on this system")
+        self.T.zero_()
+        self.R.zero_()
+        self.Tv = self.T.view(G, n_all, TS)
+        self.Rv = self.R.view(G, n_all, RS)
+
+    def T_mc_row(self, g: int, row: int):
+        import ctypes
+        return ctypes.c_void_p(self.T_mc + ((g * self.n_all + row) * self.TS) * 4)
+
+    def R_mc_row(self, g: int, row: int):
+        import ctypes
+        return ctypes.c_void_p(self.R_mc + ((g * self.n_all + row) * self.RS) * 4)
+
+    def fence_T(self, channel: int):
+        self.hT.barrier(channel=channel)
+
+    def fence_R(self, channel: int):
+        self.hR.barrier(channel=channel)
+
+
 class RowShard:
     def __init__(self, rank: int, world: int, device: torch.device, group=None):
         self.rank, self.world, self.device, self.group = rank, world, device, group
         self.n_total = None
         self.n_pad = None
-        self.comm_stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        self._tables = {}
+        self.use_multicast = os.environ.get("HAN_DIST_COMM", "multicast") != "nccl"
+        self.comm_stream = torch.cuda.Stream(device=device, priority=-1) if device.type == "cuda" else None
         self._bwd = {}
 
     # ---- set-up ------------------------------------------------------------------------------
@@ -81,7 +124,12 @@ class RowShard:
         if torch.cuda.is_available():
             dev = torch.device("cuda", local)
             torch.cuda.set_device(dev)
-            td.init_process_group("nccl", device_id=dev)
+            # High-priority NCCL stream: the gather kernels fill every SM (3-4 CTAs each holding ~55-68 KB
+            # of shared memory), so a default-priority collective launched next to them only starts when
+            # the whole compute grid has drained -- i.e. no overlap at all.  With priority its CTAs are
+            # placed as soon as compute CTAs retire (every ~100 us).
+            opts = td.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            td.init_process_group("nccl", device_id=dev, pg_options=opts)
         else:
             dev = torch.device("cpu")
             td.init_process_group("gloo")
@@ -129,6 +177,25 @@ class RowShard:
         pos = torch.empty_like(by_dst.perm)
         pos[by_dst.perm.long()] = torch.arange(by_dst.nnz, dtype=torch.int32, device=dev)
         return _BackwardEdges(by_src, by_dst.indptr, pos)
+
+    def symmetric_tables(self, G: int, K: int, H: int) -> Optional[SymmetricTables]:
+        """The multicast-mapped tables for this plan shape (allocated and rendezvoused once; a
+        collective call, so every rank must ask for the same shapes in the same order), or None when
+        NVLS multicast is unavailable / HAN_DIST_COMM=nccl (then NCCL all-gathers are used)."""
+        if not self.use_multicast or self.device.type != "cuda":
+            return None
+        key = (G, K, H, self.n_pad)
+        if key not in self._tables:
+            TS, RS = query("han_table_stride", K, H), query("han_record_stride", K, H)
+            try:
+                self._tables[key] = SymmetricTables(self, G, TS, RS)
+            except Exception as ex:  # noqa: BLE001  (API or fabric without multicast)
+                import warnings
+                warnings.warn(f"han_b200.dist: NVLS multicast path unavailable ({type(ex).__name__}: {ex}); "
+                              "using NCCL all-gathers")
+                self.use_multicast = False
+                return None
+        return self._tables[key]
 
     # ---- collectives ---------------------------------------------------------------------------
     def barrier(self):

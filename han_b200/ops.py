@@ -68,14 +68,44 @@ class NodeAttentionFn(torch.autograd.Function):
         dev = X.device
         TS, RS = query("han_table_stride", K, H), query("han_record_stride", K, H)
         dist = plan.dist
+        tabs = dist.symmetric_tables(G, K, H) if dist is not None else None
         with torch.cuda.device(dev):
-            T = _empty((G, n, TS), dev)
             R = _empty((G, n, RS), dev)
-            if plan.project_mode == 0:
+            if tabs is not None:
+                # Sharded, NVLS path: every producer writes its rows straight into ALL ranks' tables through
+                # the multicast address (GEMM epilogue fused with the all-gather), then one cross-rank fence.
+                lo = dist.row_range(dist.n_total)[0]
+                n_all = dist.world * dist.n_pad
+                tabs.fence_T(1)                      # nobody is still reading the previous step's tables
+                if plan.project_mode == 0 or (K, H) != (8, 8):
+                    Tl = _empty((G, n, TS), dev)
+                    call("han_project_fwd", ptr(X), n, F, X.stride(0), ptr(W), G, K, H, ptr(a1), ptr(b1), ptr(a2),
+                         ptr(b2), ptr(Tl), ptr(R), 0, stream_ptr())
+                    for g in range(G):
+                        call("han_multicast_copy", ptr(Tl[g]), tabs.T_mc_row(g, lo), n * TS, stream_ptr(), kernels=1)
+                else:
+                    Xa = X
+                    if X.stride(0) % 4 != 0 or X.data_ptr() % 16 != 0:
+                        Xa = torch.zeros(n, (F + 3) // 4 * 4, dtype=X.dtype, device=dev)
+                        Xa[:, :F] = X
+                    for g0 in range(0, G, 4):
+                        g1 = min(G, g0 + 4)
+                        Wg = W[:, g0 * D:g1 * D].contiguous() if (g0, g1) != (0, G) else W
+                        ws_bytes = query("han_project_tc_workspace_bytes", F, g1 - g0, K, H)
+                        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                        call("han_project_fwd_tc", ptr(Xa), n, F, Xa.stride(0), ptr(Wg), g1 - g0, K, H, ptr(a1[g0]),
+                             ptr(b1[g0]), ptr(a2[g0]), ptr(b2[g0]), None, ptr(R[g0]), tabs.T_mc_row(g0, 0), n_all, lo,
+                             plan.project_mode, ptr(ws), ws_bytes, stream_ptr(), kernels=2)
+                tabs.fence_T(0)                      # all ranks' rows have landed everywhere
+                T = tabs.Tv[:, lo:lo + n]            # local rows (views into the symmetric table)
+                T_src = tabs.Tv
+            elif plan.project_mode == 0:
+                T = _empty((G, n, TS), dev)
                 call("han_project_fwd", ptr(X), n, F, X.stride(0), ptr(W), G, K, H, ptr(a1), ptr(b1), ptr(a2),
                      ptr(b2), ptr(T), ptr(R), 0, stream_ptr())
             else:
                 # tcgen05 path: TMA needs 16-byte aligned rows; at most 4 meta-paths (256 TMEM columns) per launch
+                T = _empty((G, n, TS), dev)
                 Xa = X
                 if X.stride(0) % 4 != 0 or X.data_ptr() % 16 != 0:
                     Xa = torch.zeros(n, (F + 3) // 4 * 4, dtype=X.dtype, device=dev)
@@ -86,10 +116,11 @@ class NodeAttentionFn(torch.autograd.Function):
                     ws_bytes = query("han_project_tc_workspace_bytes", F, g1 - g0, K, H)
                     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                     call("han_project_fwd_tc", ptr(Xa), n, F, Xa.stride(0), ptr(Wg), g1 - g0, K, H, ptr(a1[g0]),
-                         ptr(b1[g0]), ptr(a2[g0]), ptr(b2[g0]), ptr(T[g0]), ptr(R[g0]), plan.project_mode, ptr(ws),
-                         ws_bytes, stream_ptr(), kernels=2)
-            # sources of every local destination row: all-gather the node tables when sharded
-            T_src = dist.all_gather_rows(T) if dist is not None else T
+                         ptr(b1[g0]), ptr(a2[g0]), ptr(b2[g0]), ptr(T[g0]), ptr(R[g0]), None, 0, 0,
+                         plan.project_mode, ptr(ws), ws_bytes, stream_ptr(), kernels=2)
+            if tabs is None:
+                # sharded without NVLS: NCCL all-gather of the node tables on the side stream
+                T_src = dist.all_gather_rows(T) if dist is not None else T
             Z = _empty((n, G, D), dev)
             V = _empty((G, n, D), dev)
             plan.coefs = []
@@ -136,16 +167,25 @@ class NodeAttentionFn(torch.autograd.Function):
             part_par = _empty((NB, 2 * D + 2 * K), dev)
             dbias = _empty((G, D), dev)
             dpar = _empty((G, 2 * D + 2 * K), dev)
+            tabs = dist.symmetric_tables(G, K, H) if dist is not None else None
+            lo_row = dist.row_range(dist.n_total)[0] if tabs is not None else 0
             # 1) row-local prep for every meta-path: dV, delta into the row records; bias gradient
             for g, graph in enumerate(plan.graphs):
                 if graph.has_empty_rows():
                     raise _lib.HanError("backward through rows without any edge is not supported "
                                         "(adj_to_bias always inserts self-loops)")
+                # sharded + NVLS: the prep kernel writes the complete record of its rows into every
+                # rank's record table through the multicast address (prep fused with the all-gather)
                 call("han_attn_bwd_prep", ptr(dZ[:, g, :]), G * D, ptr(Z[:, g, :]), G * D, ptr(V[g]),
-                     ptr(R[g]), n, K, H, plan.act, ptr(part_bias), stream_ptr())
+                     ptr(R[g]), n, K, H, plan.act, ptr(part_bias),
+                     tabs.R_mc_row(g, 0) if tabs is not None else None, lo_row, stream_ptr())
                 call("han_reduce_partials", ptr(part_bias), NB, D, ptr(dbias[g]), stream_ptr())
-            # sharded: every rank needs the records of ALL destination rows (gathers overlap the passes)
-            R_all = dist.gather_records(R) if dist is not None else None
+            # sharded: every rank needs the records of ALL destination rows
+            if tabs is not None:
+                tabs.fence_R(0)
+                R_all = tabs.Rv
+            else:
+                R_all = dist.gather_records(R) if dist is not None else None   # NCCL, overlaps the passes
             # 2) by-source gather pass, by-destination df1 sums, row-local finish
             for g, graph in enumerate(plan.graphs):
                 if dist is None:

@@ -96,7 +96,15 @@ int han_project_fwd(const float* X, int64_t n, int64_t F, int64_t ldx, const flo
 size_t han_project_tc_workspace_bytes(int64_t F, int G, int K, int H);
 int han_project_fwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const float* W, int G, int K,
                        int H, const float* a1, const float* b1, const float* a2, const float* b2,
-                       float* T, float* R, int mode, void* ws, size_t ws_bytes, han_stream_t stream);
+                       float* T, float* R, float* T_mc, int64_t t_rows, int64_t t_row0, int mode, void* ws,
+                       size_t ws_bytes, han_stream_t stream);
+/* T_mc (nullable): NVLS MULTICAST address of a symmetric node table [G][t_rows][TS] shared by all
+ * ranks.  When given, the epilogue writes its rows at row offset t_row0 with multimem.st, so the
+ * GEMM and the all-gather of its output are one kernel: NVSwitch replicates every 16-byte store into
+ * all ranks' tables while the next tile is being multiplied.  T is then unused (may be NULL). */
+
+/* Copies local floats to a multicast address (for producers without a fused multicast epilogue). */
+int han_multicast_copy(const float* src, float* dst_mc, int64_t n_floats, han_stream_t stream);
 
 /* dW [F][G*D] = X^T dS  (split over rows + deterministic reduce).  dS [G][n][D].
  * ws: han_project_bwd_workspace_bytes. */
@@ -141,7 +149,10 @@ int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, 
 int han_reduce_blocks(void);
 int han_attn_bwd_prep(const float* dout, int64_t dout_stride, const float* out, int64_t out_stride,
                       const float* vsave, float* R, int64_t n_dst, int K, int H, int act,
-                      float* dbias_partial, han_stream_t stream);
+                      float* dbias_partial, float* R_mc, int64_t r_row0, han_stream_t stream);
+/* R_mc (nullable): multicast address of a symmetric record table [rows][RS]; when given, the complete
+ * record (dV | f1 | lse | delta) of local row i is written to row r_row0 + i of every rank's copy
+ * (prep fused with the all-gather of the records); f1 and lse are read from the local R. */
 
 /* by-source pass over the transposed structure: for source rows [0,n_src):
  *   dS_agg_j = sum_i alpha_ij dV_i ; df2_j = sum_i dl_ij ; dl_edge[perm[t]][K] = dl_ij

@@ -62,9 +62,12 @@ def main():
         params = O.init_params(np.random.default_rng(seed + 1), [cfg.F] * cfg.P, cfg.C)
         run_case(shard, cfg, params, mode)
     shard.barrier()
+    torch.cuda.synchronize()
     if shard.rank == 0:
-        print("DIST_CHECK_OK world=%d" % shard.world)
-    shard.shutdown()
+        mode = "multicast" if (shard.use_multicast and shard._tables) else "nccl"
+        print("DIST_CHECK_OK world=%d comm=%s" % (shard.world, mode), flush=True)
+    sys.stdout.flush()
+    os._exit(0)     # skip communicator / symmetric-memory teardown (can block at interpreter exit)
 
 
 if __name__ == "__main__":
