@@ -36,7 +36,7 @@ _SIGNATURES = {
     "han_csr_sort_rows": (c_int, [I64, P, P, P, P, P, P]),
     "han_project_fwd": (c_int, [P, I64, I64, I64, P, I, I, I, P, P, P, P, P, P, I, P]),
     "han_project_tc_workspace_bytes": (SZ, [I64, I, I, I]),
-    "han_project_fwd_tc": (c_int, [P, I64, I64, I64, P, I, I, I, P, P, P, P, P, P, P, I64, I64, I, P, SZ, P]),
+    "han_project_fwd_tc": (c_int, [P, I64, I64, I64, P, I, I, I, P, P, P, P, P, P, P, I64, I64, I64, I, P, SZ, P]),
     "han_multicast_copy": (c_int, [P, P, I64, P]),
     "han_project_bwd_workspace_bytes": (SZ, [I64, I64, I, I]),
     "han_project_bwd": (c_int, [P, I64, I64, I64, P, I, I, P, P, SZ, I, P]),

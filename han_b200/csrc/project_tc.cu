@@ -129,7 +129,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const __grid_constant__ CUtensorMap tmBlo, int64_t n_rows, int nkb, int G,
                   const float* __restrict__ a1, const float* __restrict__ b1, const float* __restrict__ a2,
                   const float* __restrict__ b2, float* __restrict__ T, float* __restrict__ R,
-                  float* __restrict__ Tmc, int64_t t_rows, int64_t t_row0) {
+                  float* __restrict__ Tmc, int64_t t_rows, int64_t t_row0, int64_t r_rows) {
   constexpr int D = 64, K = 8, H = 8, TS = 72, RS = 88;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -269,8 +269,10 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         // node-table row: local store, or ONE multicast store per 16 B that NVSwitch replicates into the
         // same offset of every rank's table (GEMM epilogue fused with the all-gather)
+        // (t_rows / r_rows: rows per meta-path of the destination tables; they exceed n_rows when the
+        //  destination is this rank's slice of a full-size table shared with the other ranks)
         float* tbase = (Tmc != nullptr) ? Tmc + ((int64_t)g * t_rows + t_row0 + row) * TS
-                                        : T + ((int64_t)g * n_rows + row) * TS;
+                                        : T + ((int64_t)g * t_rows + t_row0 + row) * TS;
         const bool mc = Tmc != nullptr;
 #pragma unroll
         for (int c = 0; c < 8; ++c)
@@ -282,7 +284,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                       __uint_as_float(v1[4 * c + 2]), __uint_as_float(v1[4 * c + 3]));
         store_row16(tbase + 64, mc, f2[0], f2[1], f2[2], f2[3]);
         store_row16(tbase + 68, mc, f2[4], f2[5], f2[6], f2[7]);
-        float4* rp = reinterpret_cast<float4*>(R + ((int64_t)g * n_rows + row) * RS + D);
+        float4* rp = reinterpret_cast<float4*>(R + ((int64_t)g * r_rows + row) * RS + D);
         rp[0] = make_float4(f1[0], f1[1], f1[2], f1[3]);
         rp[1] = make_float4(f1[4], f1[5], f1[6], f1[7]);
       }
@@ -346,11 +348,13 @@ size_t han_project_tc_workspace_bytes(int64_t F, int G, int K, int H) {
 
 int han_project_fwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const float* W, int G, int K, int H,
                        const float* a1, const float* b1, const float* a2, const float* b2, float* T, float* R,
-                       float* T_mc, int64_t t_rows, int64_t t_row0, int mode, void* ws, size_t ws_bytes,
-                       han_stream_t stream) {
+                       float* T_mc, int64_t t_rows, int64_t t_row0, int64_t r_rows, int mode, void* ws,
+                       size_t ws_bytes, han_stream_t stream) {
   HAN_REQUIRE(X && W && a1 && b1 && a2 && b2 && (T || T_mc) && R && ws, "null pointer");
-  HAN_REQUIRE(T_mc == nullptr || (t_rows >= t_row0 + n && t_row0 >= 0 && (uintptr_t)T_mc % 16 == 0),
-              "multicast table: t_row0 + n <= t_rows, 16-byte aligned");
+  if (t_rows == 0) t_rows = n;   // destination tables are exactly [G][n][.]
+  if (r_rows == 0) r_rows = n;
+  HAN_REQUIRE(t_rows >= t_row0 + n && t_row0 >= 0 && r_rows >= n, "t_row0 + n <= t_rows and n <= r_rows required");
+  HAN_REQUIRE(((uintptr_t)T_mc % 16 == 0) && ((uintptr_t)T % 16 == 0) && ((uintptr_t)R % 16 == 0), "16-byte alignment");
   HAN_REQUIRE(K == 8 && H == 8, "the tensor-core projection is built for K = H = 8");
   HAN_REQUIRE(G >= 1 && G <= 4, "1 <= G <= 4 meta-paths per launch (256 accumulator columns)");
   HAN_REQUIRE(mode >= 1 && mode <= 3, "mode 1 (3xTF32), 2 (2xTF32, tf32-exact X) or 3 (TF32)");
@@ -382,13 +386,13 @@ int han_project_fwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const 
   }
   if (mode == 1)
     project_tc_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, a2, b2, T, R,
-                                                                  T_mc, t_rows, t_row0);
+                                                                  T_mc, t_rows, t_row0, r_rows);
   else if (mode == 2)
     project_tc_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, a2, b2, T, R,
-                                                                  T_mc, t_rows, t_row0);
+                                                                  T_mc, t_rows, t_row0, r_rows);
   else
     project_tc_kernel<3><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, a2, b2, T, R,
-                                                                  T_mc, t_rows, t_row0);
+                                                                  T_mc, t_rows, t_row0, r_rows);
   return check_launch(__func__);
 }
 

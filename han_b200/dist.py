@@ -83,12 +83,18 @@ class SymmetricTables:
         self.hR = symm.rendezvous(self.R, td.group.WORLD)
         self.T_mc = int(self.hT.multicast_ptr)
         self.R_mc = int(self.hR.multicast_ptr)
-        if not self.T_mc or not self.R_mc:
+        if shard.comm == "multicast" and (not self.T_mc or not self.R_mc):
             raise RuntimeError("symmetric memory has no multicast (NVLS) mapping on this system")
         self.T.zero_()
         self.R.zero_()
         self.Tv = self.T.view(G, n_all, TS)
         self.Rv = self.R.view(G, n_all, RS)
+        self.shard = shard
+        W = shard.world
+        # peer-mapped views of every rank's tables (for copy-engine pulls) and one side stream per peer
+        self.peers_T = [self.hT.get_buffer(r, (G, n_all, TS), torch.float32) for r in range(W)]
+        self.peers_R = [self.hR.get_buffer(r, (G, n_all, RS), torch.float32) for r in range(W)]
+        self.pull_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(W - 1)]
 
     def T_mc_row(self, g: int, row: int):
         import ctypes
@@ -104,6 +110,53 @@ class SymmetricTables:
     def fence_R(self, channel: int):
         self.hR.barrier(channel=channel)
 
+    def _pull(self, hdl, view, peers):
+        """After the cross-rank fence (every rank's block is complete), fetch the W-1 remote row blocks
+        with peer-to-peer cudaMemcpyAsync: copy engines only, no SMs, so the transfers run fully
+        concurrently with the aggregation kernels.  One side stream per peer, meta-paths in order;
+        indexing the result with g waits only for table g."""
+        sh = self.shard
+        W, n_pad = sh.world, sh.n_pad
+        cur = torch.cuda.current_stream()
+        hdl.barrier(channel=0)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        events = [[] for _ in range(self.G)]
+        for k in range(1, W):
+            r = (sh.rank + k) % W
+            st = self.pull_streams[k - 1]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                for g in range(self.G):
+                    view[g, r * n_pad:(r + 1) * n_pad].copy_(peers[r][g, r * n_pad:(r + 1) * n_pad], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    events[g].append(ev)
+        return _Pulled(view, events)
+
+    def exchange_T(self, fused_multicast: bool):
+        if fused_multicast:
+            self.fence_T(0)           # producers already wrote every rank's copy (multimem.st)
+            return self.Tv
+        return self._pull(self.hT, self.Tv, self.peers_T)
+
+    def exchange_R(self, fused_multicast: bool):
+        if fused_multicast:
+            self.fence_R(0)
+            return self.Rv
+        return self._pull(self.hR, self.Rv, self.peers_R)
+
+
+class _Pulled:
+    def __init__(self, view, events):
+        self.view, self.events = view, events
+
+    def __getitem__(self, g: int) -> torch.Tensor:
+        cur = torch.cuda.current_stream()
+        for ev in self.events[g]:
+            cur.wait_event(ev)
+        return self.view[g]
+
 
 class RowShard:
     def __init__(self, rank: int, world: int, device: torch.device, group=None):
@@ -111,7 +164,12 @@ class RowShard:
         self.n_total = None
         self.n_pad = None
         self._tables = {}
-        self.use_multicast = os.environ.get("HAN_DIST_COMM", "multicast") != "nccl"
+        # exchange of the node tables / row records between ranks:
+        #   "pull"      (default) symmetric memory + copy-engine peer copies, overlapped with the kernels
+        #   "multicast" producers write every rank's copy through the NVLS multicast address (multimem.st)
+        #   "nccl"      plain NCCL all-gathers on a high-priority side stream
+        self.comm = os.environ.get("HAN_DIST_COMM", "pull")
+        self.use_multicast = self.comm != "nccl"
         self.comm_stream = torch.cuda.Stream(device=device, priority=-1) if device.type == "cuda" else None
         self._bwd = {}
 
@@ -191,9 +249,10 @@ class RowShard:
                 self._tables[key] = SymmetricTables(self, G, TS, RS)
             except Exception as ex:  # noqa: BLE001  (API or fabric without multicast)
                 import warnings
-                warnings.warn(f"han_b200.dist: NVLS multicast path unavailable ({type(ex).__name__}: {ex}); "
+                warnings.warn(f"han_b200.dist: symmetric-memory exchange unavailable ({type(ex).__name__}: {ex}); "
                               "using NCCL all-gathers")
                 self.use_multicast = False
+                self.comm = "nccl"
                 return None
         return self._tables[key]
 

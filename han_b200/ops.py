@@ -70,42 +70,35 @@ class NodeAttentionFn(torch.autograd.Function):
         dist = plan.dist
         tabs = dist.symmetric_tables(G, K, H) if dist is not None else None
         with torch.cuda.device(dev):
-            R = _empty((G, n, RS), dev)
+            fused_mc = False
+            t_rows = r_rows = 0
             if tabs is not None:
-                # Sharded, NVLS path: every producer writes its rows straight into ALL ranks' tables through
-                # the multicast address (GEMM epilogue fused with the all-gather), then one cross-rank fence.
+                # Sharded over GPUs: T and R live in full-size tables in symmetric (peer-mapped) memory; this
+                # rank produces its own row block in place and the exchange brings in the other blocks.
                 lo = dist.row_range(dist.n_total)[0]
-                n_all = dist.world * dist.n_pad
-                tabs.fence_T(1)                      # nobody is still reading the previous step's tables
-                if plan.project_mode == 0 or (K, H) != (8, 8):
-                    Tl = _empty((G, n, TS), dev)
-                    call("han_project_fwd", ptr(X), n, F, X.stride(0), ptr(W), G, K, H, ptr(a1), ptr(b1), ptr(a2),
-                         ptr(b2), ptr(Tl), ptr(R), 0, stream_ptr())
-                    for g in range(G):
-                        call("han_multicast_copy", ptr(Tl[g]), tabs.T_mc_row(g, lo), n * TS, stream_ptr(), kernels=1)
-                else:
-                    Xa = X
-                    if X.stride(0) % 4 != 0 or X.data_ptr() % 16 != 0:
-                        Xa = torch.zeros(n, (F + 3) // 4 * 4, dtype=X.dtype, device=dev)
-                        Xa[:, :F] = X
-                    for g0 in range(0, G, 4):
-                        g1 = min(G, g0 + 4)
-                        Wg = W[:, g0 * D:g1 * D].contiguous() if (g0, g1) != (0, G) else W
-                        ws_bytes = query("han_project_tc_workspace_bytes", F, g1 - g0, K, H)
-                        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                        call("han_project_fwd_tc", ptr(Xa), n, F, Xa.stride(0), ptr(Wg), g1 - g0, K, H, ptr(a1[g0]),
-                             ptr(b1[g0]), ptr(a2[g0]), ptr(b2[g0]), None, ptr(R[g0]), tabs.T_mc_row(g0, 0), n_all, lo,
-                             plan.project_mode, ptr(ws), ws_bytes, stream_ptr(), kernels=2)
-                tabs.fence_T(0)                      # all ranks' rows have landed everywhere
-                T = tabs.Tv[:, lo:lo + n]            # local rows (views into the symmetric table)
-                T_src = tabs.Tv
-            elif plan.project_mode == 0:
+                tabs.fence_T(1)                       # nobody still reads / pulls the previous step's tables
+                T = tabs.Tv[:, lo:lo + n]
+                R = tabs.Rv[:, lo:lo + n]
+                t_rows = r_rows = tabs.n_all
+                fused_mc = dist.comm == "multicast"   # producers write through the NVLS multicast address
+            else:
                 T = _empty((G, n, TS), dev)
+                R = _empty((G, n, RS), dev)
+            if plan.project_mode == 0 or (K, H) != (8, 8):
+                # exact-FP32 FFMA projection (any shape); contiguous outputs, placed into the tables afterwards
+                Tl = T if tabs is None else _empty((G, n, TS), dev)
+                Rl = R if tabs is None else _empty((G, n, RS), dev)
                 call("han_project_fwd", ptr(X), n, F, X.stride(0), ptr(W), G, K, H, ptr(a1), ptr(b1), ptr(a2),
-                     ptr(b2), ptr(T), ptr(R), 0, stream_ptr())
+                     ptr(b2), ptr(Tl), ptr(Rl), 0, stream_ptr())
+                if tabs is not None:
+                    R[:, :, D:D + K] = Rl[:, :, D:D + K]
+                    if fused_mc:
+                        for g in range(G):
+                            call("han_multicast_copy", ptr(Tl[g]), tabs.T_mc_row(g, lo), n * TS, stream_ptr())
+                    else:
+                        T.copy_(Tl)
             else:
                 # tcgen05 path: TMA needs 16-byte aligned rows; at most 4 meta-paths (256 TMEM columns) per launch
-                T = _empty((G, n, TS), dev)
                 Xa = X
                 if X.stride(0) % 4 != 0 or X.data_ptr() % 16 != 0:
                     Xa = torch.zeros(n, (F + 3) // 4 * 4, dtype=X.dtype, device=dev)
@@ -116,11 +109,14 @@ class NodeAttentionFn(torch.autograd.Function):
                     ws_bytes = query("han_project_tc_workspace_bytes", F, g1 - g0, K, H)
                     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                     call("han_project_fwd_tc", ptr(Xa), n, F, Xa.stride(0), ptr(Wg), g1 - g0, K, H, ptr(a1[g0]),
-                         ptr(b1[g0]), ptr(a2[g0]), ptr(b2[g0]), ptr(T[g0]), ptr(R[g0]), None, 0, 0,
+                         ptr(b1[g0]), ptr(a2[g0]), ptr(b2[g0]), None if fused_mc else ptr(T[g0]), ptr(R[g0]),
+                         tabs.T_mc_row(g0, 0) if fused_mc else None, t_rows, lo if fused_mc else 0, r_rows,
                          plan.project_mode, ptr(ws), ws_bytes, stream_ptr(), kernels=2)
-            if tabs is None:
-                # sharded without NVLS: NCCL all-gather of the node tables on the side stream
-                T_src = dist.all_gather_rows(T) if dist is not None else T
+            # sources of every local destination row
+            if tabs is not None:
+                T_src = tabs.exchange_T(fused_mc)     # cross-rank fence (+ copy-engine pulls of the peers' blocks)
+            else:
+                T_src = dist.all_gather_rows(T) if dist is not None else T    # NCCL all-gather on a side stream
             Z = _empty((n, G, D), dev)
             V = _empty((G, n, D), dev)
             plan.coefs = []
@@ -169,6 +165,7 @@ class NodeAttentionFn(torch.autograd.Function):
             dpar = _empty((G, 2 * D + 2 * K), dev)
             tabs = dist.symmetric_tables(G, K, H) if dist is not None else None
             lo_row = dist.row_range(dist.n_total)[0] if tabs is not None else 0
+            fused_mc = tabs is not None and dist.comm == "multicast"
             # 1) row-local prep for every meta-path: dV, delta into the row records; bias gradient
             for g, graph in enumerate(plan.graphs):
                 if graph.has_empty_rows():
@@ -178,12 +175,11 @@ class NodeAttentionFn(torch.autograd.Function):
                 # rank's record table through the multicast address (prep fused with the all-gather)
                 call("han_attn_bwd_prep", ptr(dZ[:, g, :]), G * D, ptr(Z[:, g, :]), G * D, ptr(V[g]),
                      ptr(R[g]), n, K, H, plan.act, ptr(part_bias),
-                     tabs.R_mc_row(g, 0) if tabs is not None else None, lo_row, stream_ptr())
+                     tabs.R_mc_row(g, 0) if fused_mc else None, lo_row, stream_ptr())
                 call("han_reduce_partials", ptr(part_bias), NB, D, ptr(dbias[g]), stream_ptr())
             # sharded: every rank needs the records of ALL destination rows
             if tabs is not None:
-                tabs.fence_R(0)
-                R_all = tabs.Rv
+                R_all = tabs.exchange_R(fused_mc)
             else:
                 R_all = dist.gather_records(R) if dist is not None else None   # NCCL, overlaps the passes
             # 2) by-source gather pass, by-destination df1 sums, row-local finish

@@ -96,12 +96,14 @@ int han_project_fwd(const float* X, int64_t n, int64_t F, int64_t ldx, const flo
 size_t han_project_tc_workspace_bytes(int64_t F, int G, int K, int H);
 int han_project_fwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const float* W, int G, int K,
                        int H, const float* a1, const float* b1, const float* a2, const float* b2,
-                       float* T, float* R, float* T_mc, int64_t t_rows, int64_t t_row0, int mode, void* ws,
-                       size_t ws_bytes, han_stream_t stream);
-/* T_mc (nullable): NVLS MULTICAST address of a symmetric node table [G][t_rows][TS] shared by all
- * ranks.  When given, the epilogue writes its rows at row offset t_row0 with multimem.st, so the
- * GEMM and the all-gather of its output are one kernel: NVSwitch replicates every 16-byte store into
- * all ranks' tables while the next tile is being multiplied.  T is then unused (may be NULL). */
+                       float* T, float* R, float* T_mc, int64_t t_rows, int64_t t_row0, int64_t r_rows,
+                       int mode, void* ws, size_t ws_bytes, han_stream_t stream);
+/* Destination addressing: meta-path g, local row i goes to T + ((g*t_rows + t_row0 + i)*TS) and
+ * R + ((g*r_rows + i)*RS); t_rows / r_rows = 0 mean n (tables are exactly [G][n][.]); larger values
+ * let the kernel write this rank's slice of full-size tables shared with other ranks.
+ * T_mc (nullable): NVLS MULTICAST address of a symmetric node table [G][t_rows][TS].  When given, the
+ * epilogue writes its rows with multimem.st instead, so the GEMM and the all-gather of its output are
+ * one kernel: NVSwitch replicates every store into all ranks' tables.  T is then unused. */
 
 /* Copies local floats to a multicast address (for producers without a fused multicast epilogue). */
 int han_multicast_copy(const float* src, float* dst_mc, int64_t n_floats, han_stream_t stream);

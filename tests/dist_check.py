@@ -64,7 +64,7 @@ def main():
     shard.barrier()
     torch.cuda.synchronize()
     if shard.rank == 0:
-        mode = "multicast" if (shard.use_multicast and shard._tables) else "nccl"
+        mode = shard.comm if (shard.use_multicast and shard._tables) else "nccl"
         print("DIST_CHECK_OK world=%d comm=%s" % (shard.world, mode), flush=True)
     sys.stdout.flush()
     os._exit(0)     # skip communicator / symmetric-memory teardown (can block at interpreter exit)

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("comm", ["multicast", "nccl"])
+@pytest.mark.parametrize("comm", ["pull", "multicast", "nccl"])
 def test_sharded_step_matches_oracle(comm):
     n = torch.cuda.device_count()
     if n < 2:
@@ -21,7 +21,7 @@ def test_sharded_step_matches_oracle(comm):
     n = 2 if n < 4 else 4
     env = dict(os.environ, HAN_DIST_COMM=comm)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
-           "--master-addr", "127.0.0.1", "--master-port", "29533" if comm == "nccl" else "29534",
+           "--master-addr", "127.0.0.1", "--master-port", str(29533 + ["pull", "multicast", "nccl"].index(comm)),
            os.path.join(ROOT, "tests", "dist_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
