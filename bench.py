@@ -252,7 +252,7 @@ def run_ours(args):
     barrier()
 
     mark_lo = sampler.mark()
-    torch.cuda.nvtx.range_push("han_timed")
+    nvtx_id = torch.cuda.nvtx.range_start("han_timed")   # start/end ranges span all threads (autograd runs backward in its own)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for s, e in ev:
@@ -262,7 +262,7 @@ def run_ours(args):
         loss = run_step()
         e.record()
     barrier()
-    torch.cuda.nvtx.range_pop()
+    torch.cuda.nvtx.range_end(nvtx_id)
     if rank == 0:
         time.sleep(0.25)     # let the sampler flush the samples taken during the region
     clocks = sampler.stop(max(0, mark_lo - 1), None) if rank == 0 else None
@@ -280,6 +280,24 @@ def run_ours(args):
     barrier()
     _lib.set_recorder(None)
     eager_ms = sum(s.elapsed_time(e) for s, e in ev2) / len(ev2)
+    if os.environ.get("HAN_TRACE") and rank == 0:
+        # debugging aid: timeline of one eager step (all streams) -> gpurun_out/trace_*.txt
+        _lib.TRACE = []
+        _lib.trace_mark("step >")
+        step(X1, wl["graphs"])
+        _lib.trace_mark("step <")
+        torch.cuda.synchronize()
+        t0 = _lib.TRACE[0][1]
+        rows = sorted((t0.elapsed_time(ev), lab) for lab, ev in _lib.TRACE)
+        _lib.TRACE = None
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        tag = os.environ.get("HAN_DIST_COMM", "pull") if world > 1 else "single"
+        with open(os.path.join(ROOT, "gpurun_out", f"trace_{tag}_g{world}.txt"), "w") as f:
+            for t, lab in rows:
+                f.write(f"{t:9.3f}  {lab}\n")
+    elif os.environ.get("HAN_TRACE"):
+        step(X1, wl["graphs"])      # keep the other ranks in lock-step with rank 0's traced step
+    barrier()
     step_ms = [s.elapsed_time(e) for s, e in ev]
     ms = sum(step_ms) / len(step_ms)
     loss = loss.detach().clone().reshape(1)

@@ -40,6 +40,8 @@ _SIGNATURES = {
     "han_multicast_copy": (c_int, [P, P, I64, P]),
     "han_project_bwd_workspace_bytes": (SZ, [I64, I64, I, I]),
     "han_project_bwd": (c_int, [P, I64, I64, I64, P, I, I, P, P, SZ, I, P]),
+    "han_project_bwd_tc_workspace_bytes": (SZ, [I64, I64, I]),
+    "han_project_bwd_tc": (c_int, [P, I64, I64, I64, P, I, P, P, SZ, I, P]),
     "han_attn_fwd": (c_int, [P, P, I64, P, P, P, I, I, I, P, I64, P, P, P]),
     "han_attn_coefs": (c_int, [P, P, I64, P, P, I, I, P, P]),
     "han_csr_chunk_edges": (c_int64, [I64]),
@@ -127,6 +129,17 @@ class CallRecorder:
 
 _recorder = None
 
+# Optional timeline (debugging aid, HAN_TRACE=1 in bench.py): (label, event) pairs recorded on whatever
+# stream is current; elapsed times against the first event give a per-step timeline across streams.
+TRACE = None
+
+
+def trace_mark(label: str):
+    if TRACE is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        TRACE.append((label, ev))
+
 
 def set_recorder(rec):
     global _recorder
@@ -143,7 +156,11 @@ def call(name: str, *args, kernels: int = None):
         if rec.time_events:
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
+    if TRACE is not None:
+        trace_mark(name + " >")
     rc = getattr(lib, name)(*args)
+    if TRACE is not None:
+        trace_mark(name + " <")
     if rec is not None and rec.time_events:
         e.record()
         rec.events.setdefault(name, []).append((s, e))

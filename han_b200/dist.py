@@ -119,19 +119,27 @@ class SymmetricTables:
         W, n_pad = sh.world, sh.n_pad
         cur = torch.cuda.current_stream()
         hdl.barrier(channel=0)
+        _lib.trace_mark("fence done")
         ready = torch.cuda.Event()
         ready.record(cur)
         events = [[] for _ in range(self.G)]
-        for k in range(1, W):
-            r = (sh.rank + k) % W
-            st = self.pull_streams[k - 1]
-            st.wait_event(ready)
-            with torch.cuda.stream(st):
-                for g in range(self.G):
+        # table by table: the W-1 copies of table g run concurrently (one per peer), and table g+1 starts
+        # only when table g is complete, so the consumer of table g is never starved by later tables
+        for g in range(self.G):
+            for k in range(1, W):
+                r = (sh.rank + k) % W
+                st = self.pull_streams[k - 1]
+                if g == 0:
+                    st.wait_event(ready)
+                else:
+                    for ev in events[g - 1]:
+                        st.wait_event(ev)
+                with torch.cuda.stream(st):
                     view[g, r * n_pad:(r + 1) * n_pad].copy_(peers[r][g, r * n_pad:(r + 1) * n_pad], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(st)
                     events[g].append(ev)
+                    _lib.trace_mark(f"pull g{g} peer{r} done")
         return _Pulled(view, events)
 
     def exchange_T(self, fused_multicast: bool):
@@ -155,6 +163,7 @@ class _Pulled:
         cur = torch.cuda.current_stream()
         for ev in self.events[g]:
             cur.wait_event(ev)
+        _lib.trace_mark(f"table {g} ready")
         return self.view[g]
 
 
@@ -288,7 +297,9 @@ class RowShard:
     def reduce_scatter_rows(self, partial: torch.Tensor) -> torch.Tensor:
         """(W*n_pad, C) partial sums -> this rank's (n_pad, C) block of the total."""
         out = torch.empty(self.n_pad, partial.shape[1], dtype=partial.dtype, device=partial.device)
+        _lib.trace_mark("reduce_scatter >")
         td.reduce_scatter_tensor(out, partial, op=td.ReduceOp.SUM, group=self.group)
+        _lib.trace_mark("reduce_scatter <")
         return out
 
     # ---- the sharded by-source backward of one meta-path ---------------------------------------
@@ -313,8 +324,22 @@ class RowShard:
         n_all = self.world * self.n_pad
         df1_part = torch.empty(n_all, K, dtype=torch.float32, device=dev)
         call("han_attn_bwd_dst", ptr(be.by_dst_indptr), n_all, bs.nnz, ptr(dl), K, ptr(df1_part), stream_ptr())
-        df1 = self.reduce_scatter_rows(df1_part)
-        return df1[:n_loc].contiguous()
+        # reduce-scatter on the side stream: it overlaps the next meta-path's gather pass; the caller
+        # waits on the returned event before the row-local finish
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        out = torch.empty(self.n_pad, K, dtype=torch.float32, device=dev)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ready)
+            _lib.trace_mark("reduce_scatter >")
+            td.reduce_scatter_tensor(out, df1_part, op=td.ReduceOp.SUM, group=self.group)
+            _lib.trace_mark("reduce_scatter <")
+            done = torch.cuda.Event()
+            done.record(self.comm_stream)
+        df1_part.record_stream(self.comm_stream)
+        out.record_stream(self.comm_stream)
+        return out, done
 
     # ---- loss / gradients ------------------------------------------------------------------------
     def masked_loss(self, logits, labels, mask, train_op):
@@ -329,7 +354,9 @@ class RowShard:
     def all_reduce_grads(self, module: torch.nn.Module) -> None:
         grads = [p.grad for p in module.parameters() if p.grad is not None]
         flat = torch.cat([g.reshape(-1) for g in grads])
+        _lib.trace_mark("all_reduce grads >")
         td.all_reduce(flat, op=td.ReduceOp.SUM, group=self.group)
+        _lib.trace_mark("all_reduce grads <")
         off = 0
         for g in grads:
             n = g.numel()
@@ -357,10 +384,12 @@ class _Gathered:
                 ev = torch.cuda.Event()
                 ev.record(shard.comm_stream)
                 self.events.append(ev)
+                _lib.trace_mark(f"nccl gather {g} done")
         for t in full:
             t.record_stream(shard.comm_stream)
         Tp.record_stream(shard.comm_stream)
 
     def __getitem__(self, g: int) -> torch.Tensor:
         torch.cuda.current_stream().wait_event(self.events[g])
+        _lib.trace_mark(f"table {g} ready")
         return self.full[g]

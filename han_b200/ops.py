@@ -183,6 +183,7 @@ class NodeAttentionFn(torch.autograd.Function):
             else:
                 R_all = dist.gather_records(R) if dist is not None else None   # NCCL, overlaps the passes
             # 2) by-source gather pass, by-destination df1 sums, row-local finish
+            pending = []
             for g, graph in enumerate(plan.graphs):
                 if dist is None:
                     gt = graph.transpose()
@@ -198,15 +199,37 @@ class NodeAttentionFn(torch.autograd.Function):
                     call("han_attn_bwd_dst", ptr(graph.indptr), n, graph.nnz, ptr(dl), K, ptr(df1), stream_ptr())
                     del dl
                 else:
-                    df1 = dist.backward_edges(plan, g, T[g], R_all[g], dS[g], df2)
+                    # sharded: df1 comes back from a reduce-scatter that runs on the side stream while the
+                    # next meta-path's gather pass is already going; the finish is deferred (loop 3)
+                    df2_g = _empty((n, K), dev)
+                    pending.append((g, df2_g) + dist.backward_edges(plan, g, T[g], R_all[g], dS[g], df2_g))
+                    continue
                 call("han_attn_bwd_finish", ptr(T[g]), n, K, H, ptr(a1[g]), ptr(a2[g]), ptr(df1), ptr(df2),
                      ptr(dS[g]), ptr(part_par), stream_ptr())
                 call("han_reduce_partials", ptr(part_par), NB, 2 * D + 2 * K, ptr(dpar[g]), stream_ptr())
+            # 3) sharded only: row-local finish once each meta-path's df1 has arrived
+            for g, df2_g, df1_g, done in pending:
+                torch.cuda.current_stream().wait_event(done)
+                call("han_attn_bwd_finish", ptr(T[g]), n, K, H, ptr(a1[g]), ptr(a2[g]), ptr(df1_g), ptr(df2_g),
+                     ptr(dS[g]), ptr(part_par), stream_ptr())
+                call("han_reduce_partials", ptr(part_par), NB, 2 * D + 2 * K, ptr(dpar[g]), stream_ptr())
             dW = _empty((F, G * D), dev)
-            ws_bytes = query("han_project_bwd_workspace_bytes", n, F, G, D)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            call("han_project_bwd", ptr(X), n, F, X.stride(0), ptr(dS), G, D, ptr(dW), ptr(ws), ws_bytes,
-                 0, stream_ptr())   # dW stays on the exact-FP32 FFMA kernel for now
+            if plan.project_mode != 0 and (K, H) == (8, 8):
+                # tcgen05 split-K GEMM over the node index (3xTF32 / 2xTF32: fp32-grade)
+                for g0 in range(0, G, 4):
+                    g1 = min(G, g0 + 4)
+                    out = dW if (g0, g1) == (0, G) else _empty((F, (g1 - g0) * D), dev)
+                    ws_bytes = query("han_project_bwd_tc_workspace_bytes", n, F, g1 - g0)
+                    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                    call("han_project_bwd_tc", ptr(X), n, F, X.stride(0), ptr(dS[g0]), g1 - g0, ptr(out), ptr(ws),
+                         ws_bytes, plan.project_mode, stream_ptr(), kernels=2)
+                    if out is not dW:
+                        dW[:, g0 * D:g1 * D] = out
+            else:
+                ws_bytes = query("han_project_bwd_workspace_bytes", n, F, G, D)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                call("han_project_bwd", ptr(X), n, F, X.stride(0), ptr(dS), G, D, ptr(dW), ptr(ws), ws_bytes,
+                     0, stream_ptr())
         da1 = dpar[:, :D].reshape(G, K, H)
         da2 = dpar[:, D:2 * D].reshape(G, K, H)
         db1 = dpar[:, 2 * D:2 * D + K]

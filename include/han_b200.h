@@ -114,6 +114,13 @@ size_t han_project_bwd_workspace_bytes(int64_t n, int64_t F, int G, int D);
 int han_project_bwd(const float* X, int64_t n, int64_t F, int64_t ldx, const float* dS, int G, int D,
                     float* dW, void* ws, size_t ws_bytes, int mode, han_stream_t stream);
 
+/* The same dW on the tcgen05 tensor cores (K = H = 8, 1 <= G <= 4): split-K over the node index,
+ * producer warps transpose + hi/lo-split the operands into the swizzled K-major layout, accumulators
+ * in TMEM, deterministic second-stage reduce.  mode as in han_project_fwd_tc. */
+size_t han_project_bwd_tc_workspace_bytes(int64_t n, int64_t F, int G);
+int han_project_bwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const float* dS, int G,
+                       float* dW, void* ws, size_t ws_bytes, int mode, han_stream_t stream);
+
 /* ---- K-B: fused CSR edge-softmax-aggregate. Replaces utils/layers.py:26-35,46 for K heads ---- */
 /* For destination rows [0,n_dst): alpha_ij = softmax_j(leaky_relu_0.2(f1_i + f2_j)), V_i = sum_j
  * alpha_ij S_j, out_i = act(V_i + bias).  T is indexed by the CSR's column ids; f1 is read from

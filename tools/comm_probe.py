@@ -73,9 +73,44 @@ def main():
         if rank == 0:
             print(f"[probe] copy-engine pull from {world - 1} peers: {ms:.3f} ms -> {recv_mb / ms:.1f} GB/s "
                   f"received per rank (data ok={ok})", flush=True)
+        # SM-based pull: an elementwise kernel that loads straight from the peer mapping (LDG over NVLink)
+        def sm_pull():
+            hdl.barrier(channel=0)
+            for k in range(1, world):
+                r = (rank + k) % world
+                torch.mul(peers[r], 1.0, out=full[r * n_pad:(r + 1) * n_pad])
+            hdl.barrier(channel=1)
+
+        ms = timed(sm_pull)
+        if rank == 0:
+            print(f"[probe] SM pull (LDG from peers): {ms:.3f} ms -> {recv_mb / ms:.1f} GB/s received per rank", flush=True)
+
+        # multicast push: every rank writes its shard once to the NVLS multicast address of a full table
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import ctypes
+        from han_b200 import _lib
+        fullsym = symm.empty(world * n_pad, COLS, dtype=torch.float32, device=dev)
+        hf = symm.rendezvous(fullsym, td.group.WORLD)
+        mcp = int(hf.multicast_ptr)
+        if mcp:
+            def mc_push():
+                hf.barrier(channel=0)
+                _lib.call("han_multicast_copy", _lib.ptr(shard), ctypes.c_void_p(mcp + rank * n_pad * COLS * 4),
+                          n_pad * COLS, _lib.stream_ptr())
+                hf.barrier(channel=1)
+
+            ms = timed(mc_push)
+            nxt = (rank + 1) % world
+            td.all_gather_into_tensor(full, shard)
+            torch.cuda.synchronize()
+            ok = torch.equal(fullsym, full)
+            if rank == 0:
+                print(f"[probe] multicast push (multimem.st, coalesced, 37 CTAs): {ms:.3f} ms -> {recv_mb / ms:.1f} GB/s "
+                      f"received per rank (data ok={ok})", flush=True)
     except Exception as ex:  # noqa: BLE001
         if rank == 0:
-            print(f"[probe] symmetric memory unavailable: {type(ex).__name__}: {ex}", flush=True)
+            import traceback
+            print(f"[probe] symmetric memory unavailable: {type(ex).__name__}: {ex}\n{traceback.format_exc()}", flush=True)
     td.barrier()
     torch.cuda.synchronize()
     sys.stdout.flush()
