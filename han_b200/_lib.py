@@ -19,6 +19,7 @@ P = c_void_p
 I64 = c_int64
 I = c_int
 SZ = c_size_t
+FL = ctypes.c_float
 
 # name -> (restype, argtypes); mirrors include/han_b200.h one to one
 _SIGNATURES = {
@@ -47,13 +48,16 @@ _SIGNATURES = {
     "han_csr_chunk_edges": (c_int64, [I64]),
     "han_csr_num_chunks": (c_int64, [I64]),
     "han_csr_chunk_rows": (c_int, [P, I64, I64, P, P]),
-    "han_attn_fwd_chunked": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P]),
-    "han_attn_bwd_src_chunked": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P]),
+    "han_attn_fwd_chunked": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, FL, I, I64, P]),
+    "han_attn_bwd_src_chunked": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P, FL, I, I64, P]),
+    "han_project_fwd_drop": (c_int, [P, I64, I64, I64, P, I64, I, I, I, P, P, P, P, P, P, P, P, FL, I, I64, P]),
+    "han_project_bwd_drop_workspace_bytes": (SZ, [I64, I64, I]),
+    "han_project_bwd_drop": (c_int, [P, I64, I64, I64, P, I, I, I, P, I64, P, SZ, P, FL, I, I64, P]),
     "han_reduce_blocks": (c_int, []),
     "han_attn_bwd_prep": (c_int, [P, I64, P, I64, P, P, I64, I, I, I, P, P, I64, P]),
     "han_attn_bwd_src": (c_int, [P, P, P, I64, P, P, I, I, P, P, P, P]),
     "han_attn_bwd_dst": (c_int, [P, I64, I64, P, I, P, P]),
-    "han_attn_bwd_finish": (c_int, [P, I64, I, I, P, P, P, P, P, P, P]),
+    "han_attn_bwd_finish": (c_int, [P, I64, I, I, P, P, P, P, P, P, P, P, FL, I, I64, P]),
     "han_reduce_partials": (c_int, [P, I, I64, P, P]),
     "han_semantic_shape_supported": (c_int, [I, I]),
     "han_semantic_fwd": (c_int, [P, I64, I, I, I, P, P, P, I, P, P, P, P, P]),

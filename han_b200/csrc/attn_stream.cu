@@ -9,6 +9,7 @@
 // registers, and work is balanced by edges instead of by rows, so degree skew does not matter.
 // Row boundaries inside the stream are handled by the consumer (segmented online softmax / sums).
 #include "han_common.cuh"
+#include "han_rng.cuh"
 
 namespace han {
 
@@ -16,6 +17,15 @@ constexpr int kMaxChunkEdges = 2048;   // edges per work item (whole rows; bound
 constexpr int kMinChunkEdges = 128;
 constexpr int kBatch = 16;          // records per cp.async group
 constexpr int kStreamWarps = 4;     // warps per CTA
+
+// attention-coefficient dropout arguments (thr == 0: disabled)
+struct DropCoef {
+  const uint32_t* seed_ptr;   // device word holding the step seed (a captured CUDA graph can bump it per replay)
+  uint32_t thr;               // keep probability * 2^24
+  float inv_keep;
+  uint32_t metapath;          // stream id
+  int64_t row0;               // global id of local row 0 (destination rows forward, source rows backward)
+};
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -55,7 +65,7 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
                         const int32_t* __restrict__ chunk_rows, int64_t n_chunks,
                         const float* __restrict__ T, float* __restrict__ R, const float* __restrict__ bias,
                         int act, float* __restrict__ out, int64_t out_stride, float* __restrict__ vsave,
-                        const float* __restrict__ colmean) {
+                        const float* __restrict__ colmean, DropCoef dc) {
   constexpr int D = K * H;
   constexpr int TS = ((D + K + 3) / 4) * 4;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
@@ -68,6 +78,9 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int head = lane % K, slot = lane / K;
   float* ring = smem + (size_t)w * STAGES * kBatch * TS;
+  int* col_s = reinterpret_cast<int*>(smem + (size_t)kStreamWarps * STAGES * kBatch * TS) + w * STAGES * kBatch;
+  // attention-coefficient dropout (utils/layers.py:29-30): mask bit from (seed, dst, src, head)
+  const uint32_t cseed = dc.thr ? stream_seed(*dc.seed_ptr, 3u, dc.metapath, (uint32_t)head) : 0u;
 
   const int64_t chunk = (int64_t)blockIdx.x * kStreamWarps + w;
   if (chunk >= n_chunks) return;
@@ -90,6 +103,7 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
         const int col = __shfl_sync(0xffffffffu, col_pref, rec & 31);
         if (c < TOT && rec < cnt) cp_async16(dst + rec * TS + off * 4, T + (int64_t)col * TS + off * 4);
       }
+      if (lane < kBatch) col_s[(q % STAGES) * kBatch + lane] = col_pref;
       const int64_t nbs = bs + kBatch;
       col_pref = (lane < kBatch && nbs + lane < e_hi) ? ldg_stream_i32(indices + nbs + lane) : 0;
     }
@@ -176,6 +190,7 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
     cp_async_wait<STAGES - 1>();
     __syncwarp();
     const float* buf = ring + (size_t)(b % STAGES) * kBatch * TS;
+    const int* cbuf = col_s + (b % STAGES) * kBatch;
     const int64_t bs = e_lo + (int64_t)b * kBatch;
     const int64_t be = min(e_hi, bs + kBatch);
     while (pos < be) {
@@ -188,14 +203,19 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
           const float mnew = fmaxf(m, e);
           const float sc = __expf(m - mnew);   // m = -inf -> 0
           const float p = __expf(e - mnew);
-          l = fmaf(l, sc, p);
+          l = fmaf(l, sc, p);        // the softmax normaliser always sees every neighbour
+          float pk = p;              // ... the aggregate only the kept ones, scaled 1/keep (no re-normalisation)
+          if (dc.thr) {
+            const uint32_t src = (uint32_t)cbuf[(int)(ei - bs)];
+            pk = keep24(cseed, (uint32_t)(row + dc.row0), src, dc.thr) ? p * dc.inv_keep : 0.f;
+          }
 #pragma unroll
           for (int qv = 0; qv < HV; ++qv) {
             const float4 v = *reinterpret_cast<const float4*>(rp + head * H + 4 * qv);
-            acc[4 * qv + 0] = fmaf(acc[4 * qv + 0], sc, p * v.x);
-            acc[4 * qv + 1] = fmaf(acc[4 * qv + 1], sc, p * v.y);
-            acc[4 * qv + 2] = fmaf(acc[4 * qv + 2], sc, p * v.z);
-            acc[4 * qv + 3] = fmaf(acc[4 * qv + 3], sc, p * v.w);
+            acc[4 * qv + 0] = fmaf(acc[4 * qv + 0], sc, pk * v.x);
+            acc[4 * qv + 1] = fmaf(acc[4 * qv + 1], sc, pk * v.y);
+            acc[4 * qv + 2] = fmaf(acc[4 * qv + 2], sc, pk * v.z);
+            acc[4 * qv + 3] = fmaf(acc[4 * qv + 3], sc, pk * v.w);
           }
           m = mnew;
         }
@@ -224,7 +244,7 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
                             const int32_t* __restrict__ perm, const int32_t* __restrict__ chunk_rows,
                             int64_t n_chunks, const float* __restrict__ Tsrc, const float* __restrict__ R,
                             float* __restrict__ dS_agg, float* __restrict__ df2,
-                            float* __restrict__ dl_edge) {
+                            float* __restrict__ dl_edge, DropCoef dc) {
   constexpr int D = K * H;
   constexpr int TS = ((D + K + 3) / 4) * 4;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
@@ -238,6 +258,8 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
   const int head = lane % K, slot = lane / K;
   float* ring = smem + (size_t)w * STAGES * kBatch * RS;
   int* perm_s = reinterpret_cast<int*>(smem + (size_t)kStreamWarps * STAGES * kBatch * RS) + w * STAGES * kBatch;
+  int* row_s = perm_s + kStreamWarps * STAGES * kBatch;
+  const uint32_t cseed = dc.thr ? stream_seed(*dc.seed_ptr, 3u, dc.metapath, (uint32_t)head) : 0u;
 
   const int64_t chunk = (int64_t)blockIdx.x * kStreamWarps + w;
   if (chunk >= n_chunks) return;
@@ -265,7 +287,10 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
         const int i_row = __shfl_sync(0xffffffffu, row_pref, rec & 31);
         if (c < TOT && rec < cnt) cp_async16(dst + rec * RS + off * 4, R + (int64_t)i_row * RS + off * 4);
       }
-      if (lane < kBatch) perm_s[st * kBatch + lane] = perm_pref;
+      if (lane < kBatch) {
+        perm_s[st * kBatch + lane] = perm_pref;
+        row_s[st * kBatch + lane] = row_pref;
+      }
       const int64_t nbs = bs + kBatch;
       if (lane < kBatch && nbs + lane < e_hi) {
         row_pref = ldg_stream_i32(t_indices + nbs + lane);
@@ -329,6 +354,7 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
     const int st = b % STAGES;
     const float* buf = ring + (size_t)st * kBatch * RS;
     const int* pbuf = perm_s + st * kBatch;
+    const int* rbuf = row_s + st * kBatch;
     const int64_t bs = e_lo + (int64_t)b * kBatch;
     const int64_t be = min(e_hi, bs + kBatch);
     while (pos < be) {
@@ -340,6 +366,11 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
           const float* rp = buf + rec * RS;
           const float lg = rp[D + head] + f2;
           const float a = __expf(leaky(lg) - rp[D + K + head]);
+          // coefficient dropout: alpha~ = alpha * m / keep feeds the aggregate; d alpha = d alpha~ * m / keep
+          float mk = 1.f;
+          if (dc.thr)
+            mk = keep24(cseed, (uint32_t)rbuf[rec], (uint32_t)(row + dc.row0), dc.thr) ? dc.inv_keep : 0.f;
+          const float am = a * mk;
           float da = 0.f;
 #pragma unroll
           for (int qv = 0; qv < HV; ++qv) {
@@ -348,12 +379,12 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
             da = fmaf(g4.y, sj[4 * qv + 1], da);
             da = fmaf(g4.z, sj[4 * qv + 2], da);
             da = fmaf(g4.w, sj[4 * qv + 3], da);
-            acc[4 * qv] = fmaf(a, g4.x, acc[4 * qv]);
-            acc[4 * qv + 1] = fmaf(a, g4.y, acc[4 * qv + 1]);
-            acc[4 * qv + 2] = fmaf(a, g4.z, acc[4 * qv + 2]);
-            acc[4 * qv + 3] = fmaf(a, g4.w, acc[4 * qv + 3]);
+            acc[4 * qv] = fmaf(am, g4.x, acc[4 * qv]);
+            acc[4 * qv + 1] = fmaf(am, g4.y, acc[4 * qv + 1]);
+            acc[4 * qv + 2] = fmaf(am, g4.z, acc[4 * qv + 2]);
+            acc[4 * qv + 3] = fmaf(am, g4.w, acc[4 * qv + 3]);
           }
-          const float dl = a * (da - rp[D + 2 * K + head]) * (lg > 0.f ? 1.f : kLeakySlope);
+          const float dl = a * (da * mk - rp[D + 2 * K + head]) * (lg > 0.f ? 1.f : kLeakySlope);
           df2acc += dl;
           dl_edge[(int64_t)pbuf[rec] * K + head] = dl;
         }
@@ -373,6 +404,16 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
   cp_async_wait<0>();
 }
 
+static DropCoef make_drop(const uint32_t* seed_ptr, float keep, int metapath, int64_t row0) {
+  DropCoef dc;
+  dc.seed_ptr = seed_ptr;
+  dc.thr = (keep < 1.f) ? (uint32_t)(keep * 16777216.f + 0.5f) : 0u;
+  dc.inv_keep = (keep < 1.f) ? 1.f / ((float)dc.thr / 16777216.f) : 1.f;   // unbiased for the quantised keep
+  dc.metapath = (uint32_t)metapath;
+  dc.row0 = row0;
+  return dc;
+}
+
 template <int K, int H>
 struct StreamCfg {
   static constexpr int D = K * H;
@@ -381,15 +422,15 @@ struct StreamCfg {
   // stages chosen so that ~3 CTAs (12 warps) fit in 227 KB and >= 2 batches per warp are in flight
   static constexpr int FWD_STAGES = 3;
   static constexpr int BWD_STAGES = 3;
-  static constexpr size_t fwd_smem = (size_t)kStreamWarps * FWD_STAGES * kBatch * TS * 4;
-  static constexpr size_t bwd_smem = (size_t)kStreamWarps * BWD_STAGES * kBatch * (RS * 4 + 4);
+  static constexpr size_t fwd_smem = (size_t)kStreamWarps * FWD_STAGES * kBatch * (TS * 4 + 4);
+  static constexpr size_t bwd_smem = (size_t)kStreamWarps * BWD_STAGES * kBatch * (RS * 4 + 8);
 };
 
 template <int K, int H>
 static int launch_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
                               int64_t n_chunks, const float* T, float* R, const float* bias, int act,
                               float* out, int64_t out_stride, float* vsave, const float* colmean,
-                              cudaStream_t st) {
+                              DropCoef dc, cudaStream_t st) {
   using C = StreamCfg<K, H>;
   static bool attr = false;
   if (!attr) {
@@ -399,14 +440,14 @@ static int launch_fwd_chunked(const int64_t* indptr, const int32_t* indices, con
   }
   unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
   attn_fwd_chunked_kernel<K, H, C::FWD_STAGES><<<grid, kStreamWarps * 32, C::fwd_smem, st>>>(
-      indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean);
+      indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, dc);
   return check_launch("han_attn_fwd_chunked");
 }
 
 template <int K, int H>
 static int launch_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
                                   const int32_t* chunk_rows, int64_t n_chunks, const float* Tsrc,
-                                  const float* R, float* dS_agg, float* df2, float* dl_edge,
+                                  const float* R, float* dS_agg, float* df2, float* dl_edge, DropCoef dc,
                                   cudaStream_t st) {
   using C = StreamCfg<K, H>;
   static bool attr = false;
@@ -417,7 +458,7 @@ static int launch_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indi
   }
   unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
   attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES><<<grid, kStreamWarps * 32, C::bwd_smem, st>>>(
-      t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge);
+      t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, dc);
   return check_launch("han_attn_bwd_src_chunked");
 }
 
@@ -454,8 +495,11 @@ int han_csr_chunk_rows(const int64_t* indptr, int64_t n_rows, int64_t nnz, int32
 int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
                          int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                          int K, int H, int act, float* out, int64_t out_stride, float* vsave,
-                         const float* colmean, han_stream_t stream) {
+                         const float* colmean, const uint32_t* seed_ptr, float coef_keep, int metapath,
+                         int64_t row0, han_stream_t stream) {
   HAN_REQUIRE(indptr && chunk_rows && T && R && bias && out && vsave, "null pointer");
+  HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
+  const DropCoef dc = make_drop(seed_ptr, coef_keep, metapath, row0);
   HAN_REQUIRE(n_dst > 0 && n_chunks > 0, "sizes");
   HAN_REQUIRE(act == HAN_ACT_ELU || act == HAN_ACT_IDENTITY, "activation");
   HAN_REQUIRE(out_stride >= (int64_t)K * H && out_stride % 4 == 0, "out_stride");
@@ -463,7 +507,7 @@ int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const in
               ((uintptr_t)bias % 16 == 0), "16-byte alignment");
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_fwd_chunked<k, h>(indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, as_stream(stream));
+    return launch_fwd_chunked<k, h>(indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, dc, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
@@ -472,13 +516,16 @@ int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const in
 int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
                              const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                              const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                             float* dl_edge, han_stream_t stream) {
+                             float* dl_edge, const uint32_t* seed_ptr, float coef_keep, int metapath,
+                             int64_t row0, han_stream_t stream) {
   HAN_REQUIRE(t_indptr && chunk_rows && Tsrc && R && dS_agg && df2 && dl_edge, "null pointer");
+  HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
+  const DropCoef dc = make_drop(seed_ptr, coef_keep, metapath, row0);
   HAN_REQUIRE(n_src > 0 && n_chunks > 0, "sizes");
   HAN_REQUIRE(((uintptr_t)R % 16 == 0) && ((uintptr_t)Tsrc % 16 == 0) && ((uintptr_t)dS_agg % 16 == 0), "16-byte alignment");
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_bwd_src_chunked<k, h>(t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, as_stream(stream));
+    return launch_bwd_src_chunked<k, h>(t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, dc, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");

@@ -320,7 +320,8 @@ class RowShard:
         dl = torch.empty(max(bs.nnz, 1), K, dtype=torch.float32, device=dev)
         cr, n_chunks = bs.chunks()
         call("han_attn_bwd_src_chunked", ptr(bs.indptr), ptr(bs.indices), ptr(be.pos_in_dst), ptr(cr), n_chunks,
-             n_loc, ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), ptr(dl), stream_ptr())
+             n_loc, ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), ptr(dl), ptr(plan.seed),
+             1.0 - plan.coef_drop, plan.metapath_id(g), self.row_range(self.n_total)[0], stream_ptr())
         n_all = self.world * self.n_pad
         df1_part = torch.empty(n_all, K, dtype=torch.float32, device=dev)
         call("han_attn_bwd_dst", ptr(be.by_dst_indptr), n_all, bs.nnz, ptr(dl), K, ptr(df1_part), stream_ptr())

@@ -42,8 +42,9 @@ class HeteGAT_multi(BaseGAttN):
         graph), ``semantic_mode`` ("reference" per-node beta | "paper" node-mean beta), ``dist``
         (row-shard context for multi-GPU), ``project_mode``, ``return_coef``.
         """
-        if attn_drop != 0.0 or ffd_drop != 0.0:
-            raise NotImplementedError("dropout (layers.py:18-19,29-32) is not built yet; feed 0.0")
+        attn_drop, ffd_drop = float(attn_drop), float(ffd_drop)
+        if not (0.0 <= attn_drop < 1.0 and 0.0 <= ffd_drop < 1.0):
+            raise ValueError("attn_drop and ffd_drop are probabilities of dropping, in [0, 1)")
         if residual:
             raise NotImplementedError("residual=True is dead code for hid_units=[8] (gat.py:45) and not built")
         if len(hid_units) != 1:
@@ -62,13 +63,20 @@ class HeteGAT_multi(BaseGAttN):
                                              mp_att_size, device=dev)
                 variables.set_default_store(params)
         act = ops.activation_code(activation)
+        seed = None
+        if attn_drop or ffd_drop:
+            # training-mode dropout (ex_acm3025.py:185-186 feeds 0.6 / 0.6; 0.0 at evaluation): a fresh mask
+            # set per call; the seed word lives on the device so a captured CUDA graph advances it too
+            seed = params.drop_seed
+            seed.add_(1)
 
         coef_out = [None] * P
         groups = _group_by_input(xs)
         z_parts = []
         for grp in groups:
             plan = ops.NodeAttentionPlan(graphs=[graphs[p] for p in grp], K=K, H=H, act=act,
-                                         project_mode=project_mode, dist=dist, want_coefs=return_coef)
+                                         project_mode=project_mode, dist=dist, want_coefs=return_coef,
+                                         in_drop=ffd_drop, coef_drop=attn_drop, seed=seed, metapath_ids=list(grp))
             if len(grp) == 1:
                 p = grp[0]
                 W, a1, b1 = params.W[p], params.a1[p].unsqueeze(0), params.b1[p].unsqueeze(0)

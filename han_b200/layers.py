@@ -60,6 +60,17 @@ def _squeeze_batch(seq: torch.Tensor) -> torch.Tensor:
     return seq
 
 
+_DROP_SEEDS = {}
+
+
+def _drop_seed(device) -> torch.Tensor:
+    """Device-resident dropout seed word for stand-alone attn_head calls (one per device)."""
+    key = str(device)
+    if key not in _DROP_SEEDS:
+        _DROP_SEEDS[key] = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32).to(device)
+    return _DROP_SEEDS[key]
+
+
 def new_head_params(F: int, H: int, device, generator=None) -> Dict[str, torch.nn.Parameter]:
     """The variables one ``attn_head`` call creates (layers.py:20,23,24,35) with TF's default
     initialisers: glorot-uniform kernels, zero biases."""
@@ -81,9 +92,6 @@ def attn_head(seq, out_sz, bias_mat, activation, in_drop=0.0, coef_drop=0.0, res
     ``params``: dict W (F,H), a1 (H,), b1 (), a2 (H,), b2 (), bias (H,); created with the
     reference initialisers when omitted and returned as ``attn_head.last_params``.
     """
-    if in_drop != 0.0 or coef_drop != 0.0:
-        raise NotImplementedError("dropout inside attn_head (layers.py:18-19,29-32) is not built yet; "
-                                  "run with in_drop = coef_drop = 0.0")
     if residual:
         raise NotImplementedError("residual=True (layers.py:38-42) needs the input-gradient path; not built yet")
     x = _squeeze_batch(seq)
@@ -93,8 +101,13 @@ def attn_head(seq, out_sz, bias_mat, activation, in_drop=0.0, coef_drop=0.0, res
     if params is None:
         params = new_head_params(x.shape[1], H, x.device)
     attn_head.last_params = params
+    seed = None
+    if in_drop or coef_drop:
+        seed = _drop_seed(x.device)
+        seed.add_(1)
     plan = ops.NodeAttentionPlan(graphs=[graph], K=1, H=H, act=ops.activation_code(activation),
-                                 want_coefs=bool(return_coef))
+                                 want_coefs=bool(return_coef), in_drop=float(in_drop), coef_drop=float(coef_drop),
+                                 seed=seed)
     Z = ops.node_attention(plan, x, params["W"], params["a1"].reshape(1, 1, H), params["b1"].reshape(1, 1),
                            params["a2"].reshape(1, 1, H), params["b2"].reshape(1, 1),
                            params["bias"].reshape(1, H))

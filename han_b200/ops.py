@@ -37,6 +37,15 @@ class NodeAttentionPlan:
     dist: Optional[object] = None          # han_b200.dist.RowShard when sharded over GPUs
     want_coefs: bool = False
     coefs: List[torch.Tensor] = field(default_factory=list)   # filled by forward when want_coefs
+    # training-mode dropout (utils/layers.py:18-19,29-32): probabilities of DROPPING, as the reference
+    # feeds them (ex_acm3025.py:185-186); masks are functions of (seed, meta-path, head, coordinates)
+    in_drop: float = 0.0                   # ffd_drop: input features per head + projected features
+    coef_drop: float = 0.0                 # attn_drop: attention coefficients
+    seed: Optional[torch.Tensor] = None    # int32[1] on the device (a captured graph can advance it)
+    metapath_ids: Optional[Sequence[int]] = None   # stream ids of the G meta-paths (default 0..G-1)
+
+    def metapath_id(self, g: int) -> int:
+        return int(self.metapath_ids[g]) if self.metapath_ids is not None else g
 
     @property
     def G(self):
@@ -84,12 +93,24 @@ class NodeAttentionFn(torch.autograd.Function):
             else:
                 T = _empty((G, n, TS), dev)
                 R = _empty((G, n, RS), dev)
-            if plan.project_mode == 0 or (K, H) != (8, 8):
+            row0 = dist.row_range(dist.n_total)[0] if dist is not None else 0
+            S_keep = None
+            if (plan.in_drop or plan.coef_drop) and plan.seed is None:
+                raise _lib.HanError("dropout needs plan.seed (an int32[1] CUDA tensor)")
+            if plan.in_drop or plan.project_mode == 0 or (K, H) != (8, 8):
                 # exact-FP32 FFMA projection (any shape); contiguous outputs, placed into the tables afterwards
                 Tl = T if tabs is None else _empty((G, n, TS), dev)
                 Rl = R if tabs is None else _empty((G, n, RS), dev)
-                call("han_project_fwd", ptr(X), n, F, X.stride(0), ptr(W), G, K, H, ptr(a1), ptr(b1), ptr(a2),
-                     ptr(b2), ptr(Tl), ptr(Rl), 0, stream_ptr())
+                if plan.in_drop:
+                    # training mode: per-head input masks + dropped projected features (layers.py:18-19,31-32)
+                    S_keep = _empty((G, n, D), dev)
+                    for g in range(G):    # one launch per meta-path: each has its own mask stream id
+                        call("han_project_fwd_drop", ptr(X), n, F, X.stride(0), ptr(W[:, g * D:]), G * D, 1, K, H,
+                             ptr(a1[g]), ptr(b1[g]), ptr(a2[g]), ptr(b2[g]), ptr(Tl[g]), ptr(Rl[g]), ptr(S_keep[g]),
+                             ptr(plan.seed), 1.0 - plan.in_drop, plan.metapath_id(g), row0, stream_ptr(), kernels=2)
+                else:
+                    call("han_project_fwd", ptr(X), n, F, X.stride(0), ptr(W), G, K, H, ptr(a1), ptr(b1), ptr(a2),
+                         ptr(b2), ptr(Tl), ptr(Rl), 0, stream_ptr())
                 if tabs is not None:
                     R[:, :, D:D + K] = Rl[:, :, D:D + K]
                     if fused_mc:
@@ -130,8 +151,11 @@ class NodeAttentionFn(torch.autograd.Function):
                     cr, n_chunks = graph.chunks()
                     call("han_attn_fwd_chunked", ptr(graph.indptr), ptr(graph.indices), ptr(cr), n_chunks, n,
                          ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D,
-                         ptr(V[g]), ptr(colmean), stream_ptr())
+                         ptr(V[g]), ptr(colmean), ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), row0,
+                         stream_ptr())
                 else:
+                    if plan.coef_drop:
+                        raise _lib.HanError("attention dropout needs the chunked kernels (HAN_ATTN_CHUNKED=1)")
                     call("han_attn_fwd", ptr(graph.indptr), ptr(graph.indices), n, ptr(T_src[g]), ptr(R[g]),
                          ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D, ptr(V[g]), ptr(colmean),
                          stream_ptr())
@@ -142,6 +166,7 @@ class NodeAttentionFn(torch.autograd.Function):
                              ptr(R[g]), K, H, ptr(alpha), stream_ptr())
                     plan.coefs.append(alpha)
         ctx.plan = plan
+        ctx.S_keep = S_keep
         ctx.save_for_backward(X, a1, a2, T, R, V, Z)
         ctx.mark_non_differentiable()
         return Z
@@ -150,6 +175,7 @@ class NodeAttentionFn(torch.autograd.Function):
     def backward(ctx, dZ):
         plan: NodeAttentionPlan = ctx.plan
         X, a1, a2, T, R, V, Z = ctx.saved_tensors
+        S_keep = ctx.S_keep
         G, K, H, D = plan.G, plan.K, plan.H, plan.D
         n, F = X.shape
         dev = X.device
@@ -164,7 +190,7 @@ class NodeAttentionFn(torch.autograd.Function):
             dbias = _empty((G, D), dev)
             dpar = _empty((G, 2 * D + 2 * K), dev)
             tabs = dist.symmetric_tables(G, K, H) if dist is not None else None
-            lo_row = dist.row_range(dist.n_total)[0] if tabs is not None else 0
+            lo_row = dist.row_range(dist.n_total)[0] if dist is not None else 0
             fused_mc = tabs is not None and dist.comm == "multicast"
             # 1) row-local prep for every meta-path: dV, delta into the row records; bias gradient
             for g, graph in enumerate(plan.graphs):
@@ -192,7 +218,8 @@ class NodeAttentionFn(torch.autograd.Function):
                     if CHUNKED:
                         cr, n_chunks = gt.chunks()
                         call("han_attn_bwd_src_chunked", ptr(gt.indptr), ptr(gt.indices), ptr(gt.perm), ptr(cr),
-                             n_chunks, n, ptr(T[g]), ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(dl), stream_ptr())
+                             n_chunks, n, ptr(T[g]), ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(dl),
+                             ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), 0, stream_ptr())
                     else:
                         call("han_attn_bwd_src", ptr(gt.indptr), ptr(gt.indices), ptr(gt.perm), n, ptr(T[g]),
                              ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(dl), stream_ptr())
@@ -205,16 +232,26 @@ class NodeAttentionFn(torch.autograd.Function):
                     pending.append((g, df2_g) + dist.backward_edges(plan, g, T[g], R_all[g], dS[g], df2_g))
                     continue
                 call("han_attn_bwd_finish", ptr(T[g]), n, K, H, ptr(a1[g]), ptr(a2[g]), ptr(df1), ptr(df2),
-                     ptr(dS[g]), ptr(part_par), stream_ptr())
+                     ptr(dS[g]), ptr(part_par), ptr(S_keep[g]) if S_keep is not None else None, ptr(plan.seed),
+                     1.0 - plan.in_drop, plan.metapath_id(g), lo_row, stream_ptr())
                 call("han_reduce_partials", ptr(part_par), NB, 2 * D + 2 * K, ptr(dpar[g]), stream_ptr())
             # 3) sharded only: row-local finish once each meta-path's df1 has arrived
             for g, df2_g, df1_g, done in pending:
                 torch.cuda.current_stream().wait_event(done)
                 call("han_attn_bwd_finish", ptr(T[g]), n, K, H, ptr(a1[g]), ptr(a2[g]), ptr(df1_g), ptr(df2_g),
-                     ptr(dS[g]), ptr(part_par), stream_ptr())
+                     ptr(dS[g]), ptr(part_par), ptr(S_keep[g]) if S_keep is not None else None, ptr(plan.seed),
+                     1.0 - plan.in_drop, plan.metapath_id(g), lo_row, stream_ptr())
                 call("han_reduce_partials", ptr(part_par), NB, 2 * D + 2 * K, ptr(dpar[g]), stream_ptr())
             dW = _empty((F, G * D), dev)
-            if plan.project_mode != 0 and (K, H) == (8, 8):
+            if plan.in_drop:
+                # training mode: dW_k = (X * m_k / keep)^T dS_k with the forward's masks regenerated
+                ws_bytes = query("han_project_bwd_drop_workspace_bytes", n, F, D)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                for g in range(G):
+                    call("han_project_bwd_drop", ptr(X), n, F, X.stride(0), ptr(dS[g]), 1, K, H, ptr(dW[:, g * D:]),
+                         G * D, ptr(ws), ws_bytes, ptr(plan.seed), 1.0 - plan.in_drop, plan.metapath_id(g), lo_row,
+                         stream_ptr(), kernels=2)
+            elif plan.project_mode != 0 and (K, H) == (8, 8):
                 # tcgen05 split-K GEMM over the node index (3xTF32 / 2xTF32: fp32-grade)
                 for g0 in range(0, G, 4):
                     g1 = min(G, g0 + 4)

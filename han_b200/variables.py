@@ -66,6 +66,10 @@ class HANParams(nn.Module):
         self.Wc = nn.ParameterList([P_(_glorot_(torch.empty(D, self.C, **kw), D, self.C, g))
                                     for _ in range(self.out_heads)])
         self.bc = nn.ParameterList([P_(torch.zeros(self.C, **kw)) for _ in range(self.out_heads)])
+        # dropout seed word (device-resident int32; bumped once per training forward)
+        s0 = int(torch.randint(0, 2 ** 31 - 1, (1,), generator=g).item())
+        seed = torch.tensor([s0], dtype=torch.int32)
+        self.register_buffer("drop_seed", seed.to(device) if device is not None else seed)
 
     # ---- exchange with the oracle's dict layout (tests) -----------------------------------------
     def load_dict(self, params: Dict) -> "HANParams":

@@ -146,11 +146,18 @@ int han_csr_chunk_rows(const int64_t* indptr, int64_t n_rows, int64_t nnz, int32
 int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
                          int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                          int K, int H, int act, float* out, int64_t out_stride, float* vsave,
-                         const float* colmean, han_stream_t stream);
+                         const float* colmean, const uint32_t* seed_ptr, float coef_keep, int metapath,
+                         int64_t row0, han_stream_t stream);
 int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
                              const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                              const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                             float* dl_edge, han_stream_t stream);
+                             float* dl_edge, const uint32_t* seed_ptr, float coef_keep, int metapath,
+                             int64_t row0, han_stream_t stream);
+/* Training-mode dropout of the attention coefficients (utils/layers.py:29-30: coefs scaled 1/keep where
+ * kept, zeroed elsewhere, NOT re-normalised): coef_keep = 1 - coef_drop in (0,1]; 1 disables it.  The
+ * mask bit of edge (dst i, src j), head k of meta-path `metapath` is a pure function of (*seed_ptr, i, j,
+ * k, metapath) (han_rng.cuh), recomputed identically by the forward, the backward and every rank; row0
+ * is the global id of local row 0.  seed_ptr is a DEVICE word so a captured CUDA graph can advance it. */
 
 /* ---- K-D: backward of K-B ----------------------------------------------------------------- */
 /* prep (row-local): dV = dout * act'(.), delta = <dV, V> per head -> R[:, 0:D], R[:, D+2K:D+3K];
@@ -177,8 +184,25 @@ int han_attn_bwd_dst(const int64_t* indptr, int64_t n_dst, int64_t nnz, const fl
 /* finish (row-local): dS_tot = dS_agg + df1 a1^T + df2 a2^T (in place into dS_agg);
  * partial sums for da1,da2 [K][H], db1,db2 [K]: part [han_reduce_blocks()][2*D + 2*K]. */
 int han_attn_bwd_finish(const float* T, int64_t n, int K, int H, const float* a1, const float* a2,
-                        const float* df1, const float* df2, float* dS, float* part,
+                        const float* df1, const float* df2, float* dS, float* part, const float* S_keep,
+                        const uint32_t* seed_ptr, float in_keep, int metapath, int64_t row0,
                         han_stream_t stream);
+/* in_keep < 1 (training-mode dropout of the projected features, utils/layers.py:31-32): dS_agg is the
+ * gradient w.r.t. the dropped S and is passed through the same mask; S_keep [n][D] is the un-dropped S. */
+
+/* ---- training-mode projection with feed-forward dropout (utils/layers.py:18-19,31-32) ------------- */
+/* Every head of every meta-path draws its own mask over the input features (one tf.nn.dropout per
+ * attn_head call), so S_k = (X * m_k / keep) W_k; f1/f2 come from the un-dropped S, which is kept in
+ * S_keep [G][n][D] for the backward, and T receives S dropped once more for the aggregation.  FP32 FFMA
+ * with the mask bits generated while X is staged; K <= 8.  in_keep = 1 - ffd_drop in (0,1). */
+int han_project_fwd_drop(const float* X, int64_t n, int64_t F, int64_t ldx, const float* W, int64_t ldw,
+                         int G, int K, int H, const float* a1, const float* b1, const float* a2, const float* b2,
+                         float* T, float* R, float* S_keep, const uint32_t* seed_ptr, float in_keep,
+                         int metapath0, int64_t row0, han_stream_t stream);
+size_t han_project_bwd_drop_workspace_bytes(int64_t n, int64_t F, int D);
+int han_project_bwd_drop(const float* X, int64_t n, int64_t F, int64_t ldx, const float* dS, int G, int K,
+                         int H, float* dW, int64_t ldw, void* ws, size_t ws_bytes, const uint32_t* seed_ptr,
+                         float in_keep, int metapath0, int64_t row0, han_stream_t stream);
 
 /* Deterministic column sums of partial buffers: outv[c] = sum_b part[b][c]. */
 int han_reduce_partials(const float* part, int nblocks, int64_t cols, float* outv, han_stream_t stream);

@@ -127,7 +127,7 @@ def identity(x: torch.Tensor) -> torch.Tensor:
 def attn_head(seq: torch.Tensor, out_sz: int, bias_mat: torch.Tensor, activation: Callable,
               hp: Dict[str, torch.Tensor], in_drop: float = 0.0, coef_drop: float = 0.0,
               residual: bool = False, return_coef: bool = False,
-              gen: Optional[torch.Generator] = None):
+              gen: Optional[torch.Generator] = None, masks: Optional[Dict[str, torch.Tensor]] = None):
     """Restates ``attn_head`` (utils/layers.py:7-46).
 
     ``seq`` (1,N,F); ``bias_mat`` (1,N,N); ``hp`` holds the variables the reference
@@ -135,6 +135,19 @@ def attn_head(seq: torch.Tensor, out_sz: int, bias_mat: torch.Tensor, activation
     ``a1`` (H,), ``b1`` () [:23], ``a2`` (H,), ``b2`` () [:24], ``bias`` (H,) [:35].
     """
     assert hp["W"].shape[1] == out_sz
+    if masks is not None:
+        # test hook: the three tf.nn.dropout calls with GIVEN 0/1 keep masks (x: (N,F), coef: (N,N),
+        # s: (N,H)) instead of fresh random ones, so a CUDA run with the same masks can be compared exactly
+        seq = seq * masks["x"].to(seq.dtype) / (1.0 - in_drop)             # :18-19
+        seq_fts = _conv1d_k1(seq, hp["W"], None)                           # :20
+        f_1 = _conv1d_k1(seq_fts, hp["a1"].reshape(-1, 1), hp["b1"])       # :23
+        f_2 = _conv1d_k1(seq_fts, hp["a2"].reshape(-1, 1), hp["b2"])       # :24
+        logits = f_1 + f_2.transpose(1, 2)                                 # :26
+        coefs = torch.softmax(F.leaky_relu(logits, LEAKY_SLOPE) + bias_mat, dim=-1)  # :27
+        coefs = coefs * masks["coef"].to(seq.dtype) / (1.0 - coef_drop)    # :29-30
+        seq_fts = seq_fts * masks["s"].to(seq.dtype) / (1.0 - in_drop)     # :31-32
+        ret = torch.matmul(coefs, seq_fts) + hp["bias"]                    # :34-35
+        return (activation(ret), coefs) if return_coef else activation(ret)
     if in_drop != 0.0:                                                     # :18-19
         seq = _dropout(seq, 1.0 - in_drop, gen)
     seq_fts = _conv1d_k1(seq, hp["W"], None)                               # :20  (1,N,H)

@@ -238,5 +238,6 @@ def test_attn_head_reference_signature():
     assert_close(out, ref, "attn_head")
     assert_close(ec.to_dense(), coefs, "coefs")
     assert (ec.to_dense()[0].cpu()[torch.from_numpy(bias[0]) < 0] == 0).all()    # masked coefficients exactly 0
-    with pytest.raises(NotImplementedError):
-        hb.layers.attn_head(seq, H, bias, hb.layers.elu, 0.6, 0.6, params=hp)
+    # the reference's training-time call shape (in_drop = coef_drop = 0.6) runs and differs from eval
+    dropped = hb.layers.attn_head(seq, H, torch.from_numpy(bias.astype(np.float32)), hb.layers.elu, 0.6, 0.6, params=hp)
+    assert dropped.shape == out.shape and torch.isfinite(dropped).all() and not torch.equal(dropped, out)
