@@ -54,8 +54,61 @@ def run_case(shard, cfg, params, mode):
             assert_close(gp[k], v, f"d{k}")
 
 
+def run_dropout_case(shard):
+    """Sharded node attention with training-mode dropout: masks are keyed by GLOBAL node ids, so the
+    sharded run must equal the whole-graph oracle fed the same masks (numpy replica of han_rng.cuh)."""
+    import torch.distributed as td
+    from han_b200 import ops
+    from tests.test_gpu_dropout import coef_mask, s_mask, x_mask
+    K, H, D, in_drop, coef_drop = 8, 8, 64, 0.5, 0.4
+    cfg = synth.tiny(seed=91, n=150, f=20, p=2, deg=6.0)
+    rng = np.random.default_rng(92)
+    t = lambda *s: torch.from_numpy(rng.normal(size=s) * 0.3)
+    G, F, n = cfg.P, cfg.F, cfg.N
+    par = {"W": t(F, G * D), "a1": t(G, K, H), "b1": t(G, K), "a2": t(G, K, H), "b2": t(G, K), "bias": t(G, D)}
+    up = torch.from_numpy(rng.normal(size=(n, G, D)))
+    dev = shard.device
+    lo, hi = shard.row_range(n)
+    seed = torch.tensor([424242], dtype=torch.int32, device=dev)
+    p = {k: v.float().to(dev).requires_grad_(True) for k, v in par.items()}
+    full = [hb.process.adj_to_bias(a, [n]) for a in cfg.adjs()]
+    graphs = [g.row_slice(lo, hi) for g in full]
+    shard._bwd = {}
+    shard.bind(graphs, n)
+    plan = ops.NodeAttentionPlan(graphs=graphs, K=K, H=H, in_drop=in_drop, coef_drop=coef_drop, seed=seed,
+                                 metapath_ids=[0, 1], dist=shard)
+    Z = ops.node_attention(plan, torch.from_numpy(cfg.X[lo:hi]).to(dev), p["W"], p["a1"], p["b1"], p["a2"], p["b2"],
+                           p["bias"])
+    (Z * up[lo:hi].float().to(dev)).sum().backward()
+    for v in p.values():
+        td.all_reduce(v.grad)
+    torch.cuda.synchronize()
+    sv = 424242
+    p64 = {k: v.clone().double().requires_grad_(True) for k, v in par.items()}
+    X = torch.from_numpy(cfg.X).double()[None]
+    biases = [torch.from_numpy(O.adj_to_bias(a, [n], 1)) for a in cfg.adjs()]
+    cols = []
+    for g in range(G):
+        sm = s_mask(sv, g, n, D, 1.0 - in_drop)
+        heads = []
+        for k in range(K):
+            hp = {"W": p64["W"][:, g * D + k * H:g * D + (k + 1) * H], "a1": p64["a1"][g, k], "b1": p64["b1"][g, k],
+                  "a2": p64["a2"][g, k], "b2": p64["b2"][g, k], "bias": p64["bias"][g, k * H:(k + 1) * H]}
+            masks = {"x": torch.from_numpy(x_mask(sv, g, k, n, F, 1.0 - in_drop)),
+                     "coef": torch.from_numpy(coef_mask(sv, g, k, n, n, 1.0 - coef_drop)),
+                     "s": torch.from_numpy(sm[:, k * H:(k + 1) * H])}
+            heads.append(O.attn_head(X, H, biases[g], O.elu, hp, in_drop=in_drop, coef_drop=coef_drop, masks=masks)[0])
+        cols.append(torch.cat(heads, -1))
+    Zo = torch.stack(cols, 1)
+    (Zo * up).sum().backward()
+    assert_close(Z, Zo.detach()[lo:hi], "Z shard (dropout)")
+    for k in p64:
+        assert_close(p[k].grad, p64[k].grad, "d" + k + " (dropout)")
+
+
 def main():
     shard = hd.RowShard.init_process_group()
+    run_dropout_case(shard)
     for seed, n, mode in ((61, 257, "reference"), (62, 400, "paper"), (63, 96, "reference")):
         cfg = synth.tiny(seed=seed, n=n, f=36, p=3, deg=6.0)
         cfg.masks[1][:, 5] = True                  # one source every node attends to (crosses shards)
