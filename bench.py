@@ -205,7 +205,7 @@ def run_ours(args):
 
     def step(Xin, graphs):
         hp.zero_grad(set_to_none=True)
-        logits, _, _ = hb.HeteGAT_multi.inference([Xin] * P, C, N, True, 0.0, 0.0, graphs, [HID], [K_HEADS, 1],
+        logits, _, _ = hb.HeteGAT_multi.inference([Xin] * P, C, N, True, args.dropout, args.dropout, graphs, [HID], [K_HEADS, 1],
                                                   params=hp, dist=dist, project_mode=pmode)
         if dist is None:
             ce = hb.BaseGAttN.masked_softmax_cross_entropy(logits.reshape(-1, C), wl["labels"], wl["mask"])
@@ -338,7 +338,7 @@ def run_ours(args):
                       "edges": wl["edges"], "heads": K_HEADS, "hid": HID, "mp_att_size": ATT, "classes": C,
                       "parallelism": f"dst-row shards x{world}" if world > 1 else "single GPU",
                       "l2_policy": "inputs larger than L2" if flush is None else "L2 flushed between timed steps",
-                      "dropout": 0.0, "projection": PROJ_NAMES[pmode]},
+                      "dropout": args.dropout, "projection": PROJ_NAMES[pmode] if not args.dropout else "fp32 FFMA with per-head input masks"},
            "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
            "cuda_graph": bool(args.cuda_graph),
            "loss": float(loss)}
@@ -466,6 +466,8 @@ def main():
     ap.add_argument("--workload", default="syn2m", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--dropout", type=float, default=0.0,
+                    help="attn_drop = ffd_drop (the reference trains with 0.6); 0 = parity / headline setting")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
                     help="launch every kernel from Python instead of replaying the captured step")
     ap.add_argument("--projection", default="auto", choices=["auto", "fp32", "tf32x3", "tf32x2", "tf32"],
