@@ -25,6 +25,28 @@ def _group_by_input(xs: Sequence[torch.Tensor]) -> List[List[int]]:
     return groups
 
 
+class HeteGAT(BaseGAttN):
+    """models/gat.py:132-203: one shared feature tensor for every meta-path and, with
+    ``return_coef=True``, the head-averaged attention coefficients of every meta-path
+    (``tf.concat(head_coef_list, 0)`` -> ``reduce_mean(axis=0)``, :165-167) -- the interpretability
+    output of the paper.  The coefficients come back restricted to edges (``layers.EdgeCoefs`` with
+    one column; ``.to_dense()`` gives the reference's (1,N,N) matrix)."""
+
+    @staticmethod
+    def inference(inputs, nb_classes, nb_nodes, training, attn_drop, ffd_drop,
+                  bias_mat_list, hid_units, n_heads, activation=None, residual=False,
+                  mp_att_size=128, return_coef=False, **kw):
+        out = HeteGAT_multi.inference([inputs] * len(bias_mat_list), nb_classes, nb_nodes, training, attn_drop,
+                                      ffd_drop, bias_mat_list, hid_units, n_heads,
+                                      activation=elu if activation is None else activation, residual=residual,
+                                      mp_att_size=mp_att_size, return_coef=return_coef, **kw)
+        if not return_coef:
+            return out                                                  # :202-203
+        logits, final_embed, att_val, coefs = out
+        coef_list = [layers.EdgeCoefs(c.graph, c.alpha.mean(dim=1, keepdim=True)) for c in coefs]   # :165-167
+        return logits, final_embed, att_val, coef_list                 # :200-201
+
+
 class HeteGAT_multi(BaseGAttN):
     @staticmethod
     def inference(inputs_list, nb_classes, nb_nodes, training, attn_drop, ffd_drop,

@@ -176,3 +176,67 @@ def test_training_step_reduces_loss_and_matches_oracle_adam():
             big = g0.abs() > 1e-4 * g0.abs().max()
             assert torch.allclose(hp.W[0].detach().double().cpu()[big], ref[big], atol=2e-5)
     assert losses[-1] < losses[0] and 0.0 <= float(acc) <= 1.0
+
+
+def test_hetegat_shared_inputs_and_head_averaged_coefficients():
+    """HeteGAT.inference(..., return_coef=True) (models/gat.py:132-203): shared inputs, and per
+    meta-path the attention coefficients averaged over heads (:165-167), here on edges."""
+    import han_b200 as hb
+    cfg = synth.tiny(seed=71, n=90, f=22, p=2, deg=6.0)
+    rng = np.random.default_rng(72)
+    params = O.init_params(rng, [cfg.F] * 2, cfg.C)
+    X64 = torch.from_numpy(cfg.X).double()[None]
+    biases = [torch.from_numpy(O.adj_to_bias(a, [cfg.N], 1)) for a in cfg.adjs()]
+    lo, fe, av, coefs = O.HeteGAT_multi_inference([X64, X64], cfg.C, cfg.N, False, 0.0, 0.0, biases, [8], [8, 1], params,
+                                                  return_coef=True)
+    dev = torch.device("cuda")
+    hp = hb.HANParams([cfg.F] * 2, cfg.C, device=dev).load_dict(params)
+    graphs = [hb.process.adj_to_bias(a, [cfg.N]) for a in cfg.adjs()]
+    with torch.no_grad():
+        lp, fp, ap, cl = hb.HeteGAT.inference(torch.from_numpy(cfg.X).to(dev)[None], cfg.C, cfg.N, False, 0.0, 0.0, graphs,
+                                              [8], [8, 1], return_coef=True, params=hp)
+    assert_close(lp, lo, "logits"); assert_close(fp, fe, "final_embed"); assert_close(ap, av, "att_val")
+    for p in range(2):
+        ref = torch.stack([coefs[p * 8 + k][0] for k in range(8)]).mean(0)      # concat heads, reduce_mean
+        assert_close(cl[p].to_dense()[0], ref, f"head-averaged coefs[{p}]")
+
+
+def test_full_size_acm3025_shaped_parity():
+    """BASELINE.json configs[0] at FULL size: 3025 papers, 1870 0/1 features, PAP (sparse) + PLP (56
+    skewed subject cliques, ~2 M edges), 8 heads x 8 hid.  Forward outputs and the loss against the dense
+    fp64 oracle (the N x N path of the reference: 16 heads x 9.15 M logits); gradients against the dense
+    oracle for the classifier / semantic variables and one meta-path's attention variables (the full
+    fp64 autograd graph of all 16 heads is ~10 GB of host memory, so W / a1 / a2 of meta-path 0 only)."""
+    cfg = synth.acm_like()
+    assert cfg.N == 3025 and cfg.F == 1870 and cfg.P == 2
+    rng = np.random.default_rng(2025)
+    params = O.init_params(rng, [cfg.F] * cfg.P, cfg.C)
+    out_p, grads_p, _ = product_step(cfg, params, project_mode=2)          # tcgen05 2xTF32: 0/1 features are exact
+    # oracle forward in fp64, no autograd
+    X = torch.from_numpy(cfg.X).double().unsqueeze(0)
+    biases = [torch.from_numpy(O.adj_to_bias(a, [cfg.N], 1)) for a in cfg.adjs()]
+    labels = torch.from_numpy(cfg.labels).double()
+    mask = torch.from_numpy(cfg.train_mask.astype(np.float64))
+    with torch.no_grad():
+        total, ce, logits, fe, av = O.step_loss([X] * cfg.P, biases, labels, mask, O.params_to(params, torch.float64),
+                                                cfg.C, [8], [8, 1])
+    assert_close(out_p["logits"], logits, "logits")
+    assert_close(out_p["final_embed"], fe, "final_embed")
+    assert_close(out_p["att_val"], av, "att_val")
+    assert_close(out_p["ce"], ce, "ce")
+    assert_close(out_p["total"], total, "total")
+    # gradients: everything downstream of Z, plus meta-path 1's heads (the cheap sparse PAP-like graph is p=0;
+    # take p=0 for the attention variables so the saved N x N tensors stay ~1.2 GB)
+    p = O.params_to(params, torch.float64)
+    for k in ("w_omega", "b_omega", "u_omega"):
+        p[k].requires_grad_(True)
+    for k in ("Wc", "bc"):
+        p[k][0].requires_grad_(True)
+    for k in ("W", "a1", "b1", "a2", "b2", "bias"):
+        p[k][0].requires_grad_(True)
+    total, *_ = O.step_loss([X] * cfg.P, biases, labels, mask, p, cfg.C, [8], [8, 1])
+    total.backward()
+    for k in ("w_omega", "b_omega", "u_omega"):
+        assert_close(grads_p[k], p[k].grad, "d" + k)
+    for k in ("Wc", "bc", "W", "a1", "b1", "a2", "b2", "bias"):
+        assert_close(grads_p[k][0], p[k][0].grad, f"d{k}[0]")
