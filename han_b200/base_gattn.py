@@ -43,13 +43,74 @@ class AdamTF1:
         torch._foreach_addcdiv_(ps, ms, den, value=-lr_t)
 
 
-class TrainOp:
-    """What ``training(loss, lr, l2_coef)`` returns in place of a TF train_op."""
+class FusedAdamTF1:
+    """The same update as ``AdamTF1`` plus the L2 term of ``training`` (models/base_gattn.py:14-16), as
+    ONE kernel launch (``han_adam_l2_step``) over a flat buffer that holds every variable.
 
-    def __init__(self, params, lr, l2_coef):
+    ``flatten()`` (called on first use) moves the parameters into the flat buffer -- each ``p.data``
+    becomes a view at a 256-byte aligned offset -- and gives every parameter a ``.grad`` view of a flat
+    gradient buffer, which autograd then accumulates into in place.  Sharded runs all-reduce that one
+    buffer.  The step counter is a device word, so forward + backward + update capture into one CUDA graph.
+    """
+    ALIGN = 64   # floats: keeps every view 256-byte aligned (TMA descriptors need 16)
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float, l2_coef: float,
+                 beta1=0.9, beta2=0.999, eps=1e-8):
+        self.params: List[torch.nn.Parameter] = [p for p in params]
+        self.lr, self.l2_coef, self.beta1, self.beta2, self.eps = lr, l2_coef, beta1, beta2, eps
+        self.flat_p = None
+
+    def flatten(self):
+        if self.flat_p is not None:
+            return
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedAdamTF1 needs CUDA parameters (han_adam_l2_step has no host twin)")
+        offs, n = [], 0
+        for p in self.params:
+            offs.append(n)
+            n += -(-p.numel() // self.ALIGN) * self.ALIGN
+        self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros_like(self.flat_p)
+        self.m = torch.zeros_like(self.flat_p)
+        self.v = torch.zeros_like(self.flat_p)
+        self.t = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._gviews = []
+        with torch.no_grad():
+            for p, o in zip(self.params, offs):
+                view = self.flat_p[o:o + p.numel()].view(p.shape)
+                view.copy_(p.detach())
+                p.data = view
+                self._gviews.append(self.flat_g[o:o + p.numel()].view(p.shape))
+
+    def zero_grad(self):
+        self.flatten()
+        self.flat_g.zero_()
+        for p, g in zip(self.params, self._gviews):
+            p.grad = g
+
+    @torch.no_grad()
+    def step(self):
+        from . import _lib
+        self.t.add_(1)
+        _lib.call("han_adam_l2_step", _lib.ptr(self.flat_p), _lib.ptr(self.flat_g), _lib.ptr(self.m),
+                  _lib.ptr(self.v), self.flat_p.numel(), _lib.ptr(self.t), self.lr, self.beta1, self.beta2,
+                  self.eps, self.l2_coef, _lib.stream_ptr())
+
+
+class TrainOp:
+    """What ``training(loss, lr, l2_coef)`` returns in place of a TF train_op.
+
+    ``run(loss)`` is one ``sess.run(train_op)``.  On CUDA parameters the L2 gradient and the Adam update are
+    one fused launch (``FusedAdamTF1``) and ``run`` returns the loss it was given (the reference fetches the
+    cross-entropy, not the L2-augmented objective, ex_acm3025.py:190); ``l2_loss()`` stays available as an
+    autograd term for callers that want the objective itself (the parity tests and ``bench.py``)."""
+
+    def __init__(self, params, lr, l2_coef, fused=None):
         self.params = [p for p in params]
         self.l2_coef = l2_coef
-        self.opt = AdamTF1(self.params, lr)
+        self.fused = all(p.is_cuda for p in self.params) if fused is None else fused
+        self.opt = FusedAdamTF1(self.params, lr, l2_coef) if self.fused else AdamTF1(self.params, lr)
 
     def l2_loss(self) -> torch.Tensor:
         # models/base_gattn.py:14-16: tf.nn.l2_loss(v) = sum(v^2)/2 over ALL trainable variables
@@ -57,13 +118,23 @@ class TrainOp:
         sq = torch._foreach_norm(self.params)
         return torch.stack(sq).pow(2).sum() * (0.5 * self.l2_coef)
 
-    def run(self, loss: torch.Tensor) -> torch.Tensor:
-        """One ``sess.run(train_op)``: backward of loss + L2, then the Adam update."""
+    def run(self, loss: torch.Tensor, dist=None) -> torch.Tensor:
+        """One ``sess.run(train_op)``: backward of loss (+ L2), then the Adam update.  ``dist``: the
+        row-shard context of a multi-GPU run (gradients are summed over ranks before the update; pass
+        this rank's share of the loss, ``dist.masked_loss(..., train_op=None)``)."""
         self.opt.zero_grad()
+        if self.fused:
+            loss.backward()
+            if dist is not None:
+                dist.all_reduce_flat(self.opt.flat_g)
+            self.opt.step()
+            return loss.detach()
         total = loss + self.l2_loss()
         total.backward()
+        if dist is not None:
+            raise NotImplementedError("sharded training uses the fused optimizer (CUDA parameters)")
         self.opt.step()
-        return total
+        return total.detach()
 
 
 class BaseGAttN:

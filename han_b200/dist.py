@@ -350,7 +350,14 @@ class RowShard:
         mask_total = self.all_reduce_sum(mask.sum().reshape(1))          # stays on the device: no host sync
         labels = labels.to(logits.dtype)
         xent = -(labels * torch.log_softmax(logits, dim=-1)).sum(-1)
-        return ((xent * mask).sum() / mask_total).squeeze(0) + train_op.l2_loss() / self.world
+        ce = ((xent * mask).sum() / mask_total).squeeze(0)
+        return ce if train_op is None else ce + train_op.l2_loss() / self.world
+
+    def all_reduce_flat(self, flat: torch.Tensor) -> None:
+        """Sum one flat gradient buffer over ranks (the fused optimizer's layout): a single collective."""
+        _lib.trace_mark("all_reduce grads >")
+        td.all_reduce(flat, op=td.ReduceOp.SUM, group=self.group)
+        _lib.trace_mark("all_reduce grads <")
 
     def all_reduce_grads(self, module: torch.nn.Module) -> None:
         grads = [p.grad for p in module.parameters() if p.grad is not None]

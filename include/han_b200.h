@@ -207,6 +207,15 @@ int han_project_bwd_drop(const float* X, int64_t n, int64_t F, int64_t ldx, cons
 /* Deterministic column sums of partial buffers: outv[c] = sum_b part[b][c]. */
 int han_reduce_partials(const float* part, int nblocks, int64_t cols, float* outv, han_stream_t stream);
 
+/* ---- Training update. Replaces models/base_gattn.py:12-24 (L2 on every variable + tf.train.AdamOptimizer) */
+/* p, g, m, v: flat FP32 buffers of n elements (n % 4 == 0, 16-byte aligned) holding every trainable variable
+ * at padded offsets.  step_ptr: device int32, the 1-based step count t of THIS update (the caller bumps it
+ * on the stream before the call, so a captured CUDA graph advances it too).
+ *   g' = g + l2_coef*p;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;
+ *   p -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)        (epsilon outside the bias correction) */
+int han_adam_l2_step(float* p, const float* g, float* m, float* v, int64_t n, const int* step_ptr,
+                     float lr, float beta1, float beta2, float eps, float l2_coef, han_stream_t stream);
+
 /* ---- K-C / K-F: semantic attention. Replaces utils/layers.py:152-159 ------------------------ */
 /* Z [n][P][D], w [D][A], b [A], u [A].  Supported (D,A): han_semantic_shape_supported.
  * HAN_SEM_REFERENCE: writes out [n][D] and beta [n][P] (per-node softmax over meta-paths, :156).

@@ -240,3 +240,51 @@ def test_full_size_acm3025_shaped_parity():
         assert_close(grads_p[k], p[k].grad, "d" + k)
     for k in ("Wc", "bc", "W", "a1", "b1", "a2", "b2", "bias"):
         assert_close(grads_p[k][0], p[k][0].grad, f"d{k}[0]")
+
+
+def test_fused_adam_l2_matches_unfused_update_and_captures_into_one_graph():
+    """han_adam_l2_step (one launch: L2 gradient + TF1 Adam on the flat variable buffer) against the
+    stock-op update (autograd L2 term + AdamTF1) over several steps; then forward + backward + update
+    captured as ONE CUDA graph keeps training (device-resident step counter)."""
+    import han_b200 as hb
+    from han_b200.graphs import GraphedStep
+    cfg = synth.tiny(seed=81, n=150, f=28, p=2, deg=7.0)
+    params = O.init_params(np.random.default_rng(82), [cfg.F] * cfg.P, cfg.C)
+    dev = torch.device("cuda")
+    X = torch.from_numpy(cfg.X).to(dev)[None]
+    graphs = [hb.process.adj_to_bias(a, [cfg.N]) for a in cfg.adjs()]
+    for g in graphs:
+        g.transpose()
+    labels = torch.from_numpy(cfg.labels).to(dev)
+    mask = torch.from_numpy(cfg.train_mask.astype(np.float32)).to(dev)
+
+    from han_b200.base_gattn import TrainOp
+    hp_a = hb.HANParams([cfg.F] * cfg.P, cfg.C, device=dev).load_dict(params)
+    hp_b = hb.HANParams([cfg.F] * cfg.P, cfg.C, device=dev).load_dict(params)
+    op_a, op_b = TrainOp(hp_a.parameters(), 0.005, 0.001, fused=True), TrainOp(hp_b.parameters(), 0.005, 0.001, fused=False)
+
+    def loss_of(hp):
+        logits, _, _ = hb.HeteGAT_multi.inference([X] * cfg.P, cfg.C, cfg.N, True, 0.0, 0.0, graphs, [8], [8, 1], params=hp)
+        return hb.BaseGAttN.masked_softmax_cross_entropy(logits.reshape(-1, cfg.C), labels, mask)
+
+    for _ in range(4):
+        op_a.run(loss_of(hp_a))
+        op_b.run(loss_of(hp_b))
+    assert op_a.opt.flat_p.numel() % 64 == 0 and int(op_a.opt.t.item()) == 4
+    for (name, pa), pb in zip(hp_a.named_parameters(), hp_b.parameters()):
+        assert pa.data_ptr() % 256 == 0, name
+        assert torch.allclose(pa, pb, rtol=1e-4, atol=2e-6), (name, float((pa - pb).abs().max()))
+    # the padding between the views never moves
+    used = torch.zeros_like(op_a.opt.flat_p, dtype=torch.bool)
+    base = op_a.opt.flat_p.data_ptr()
+    for p in hp_a.parameters():
+        o = (p.data_ptr() - base) // 4
+        used[o:o + p.numel()] = True
+    assert float(op_a.opt.flat_p[~used].abs().max()) == 0.0
+
+    step = GraphedStep(lambda: op_a.run(loss_of(hp_a)), warmup=2)
+    l0 = float(step())
+    for _ in range(20):
+        l1 = float(step())
+    assert l1 < l0
+    assert int(op_a.opt.t.item()) == 4 + 2 + 21            # eager + warm-up + replays (capture itself runs nothing)
