@@ -146,6 +146,53 @@ def tiny(seed: int = 7, n: int = 96, f: int = 40, p: int = 2, c: int = 3, deg: f
     return SmallConfig(f"tiny{n}", n, f, c, [f"MP{i}" for i in range(p)], X, masks, y, tr, va, te)
 
 
+def planted(seed: int = 4000, n: int = 1200, f: int = 240, c: int = 3, homophily: float = 0.85,
+            deg: float = 8.0, groups: int = 12, n_train: Optional[int] = None, n_val: Optional[int] = None) -> SmallConfig:
+    """A LEARNABLE ACM-shaped heterograph for the training-loop example and its test (the shape-only
+    configs above have uniform random labels): class-dependent bag-of-words features, a sparse
+    homophilous meta-path ("PAP": a fraction ``homophily`` of the edges stay inside a class) and a
+    clique meta-path ("PSP": ``groups`` subjects, each with a home class)."""
+    rng = np.random.default_rng(seed)
+    y = rng.integers(0, c, size=n)
+    X = rng.random((n, f)) < 0.02
+    w = f // (2 * c)
+    for k in range(c):
+        rows = np.nonzero(y == k)[0]
+        X[np.ix_(rows, np.arange(k * w, (k + 1) * w))] |= rng.random((rows.size, w)) < 0.12
+    X = X.astype(np.float32)
+    by_class = [np.nonzero(y == k)[0] for k in range(c)]
+    n_pairs = int(max(0.0, deg - 1.0) * n / 2)
+    a = rng.integers(0, n, size=n_pairs)
+    same = rng.random(n_pairs) < homophily
+    b = rng.integers(0, n, size=n_pairs)
+    for k in range(c):
+        sel = np.nonzero(same & (y[a] == k))[0]
+        b[sel] = by_class[k][rng.integers(0, by_class[k].size, size=sel.size)]
+    pap = np.zeros((n, n), dtype=bool)
+    pap[a, b] = True
+    pap[b, a] = True
+    np.fill_diagonal(pap, True)
+    home = np.arange(groups) % c
+    grp = rng.integers(0, groups, size=n)
+    stay = rng.random(n) < homophily
+    for k in range(c):
+        sel = np.nonzero(stay & (y == k))[0]
+        own = np.nonzero(home == k)[0]
+        grp[sel] = own[rng.integers(0, own.size, size=sel.size)]
+    psp = grp[:, None] == grp[None, :]
+    np.fill_diagonal(psp, True)
+    onehot = np.zeros((n, c), dtype=np.float32)
+    onehot[np.arange(n), y] = 1.0
+    n_train = n // 5 if n_train is None else n_train
+    n_val = n // 10 if n_val is None else n_val
+    perm = rng.permutation(n)
+    tr, va, te = (np.zeros(n, dtype=bool) for _ in range(3))
+    tr[perm[:n_train]] = True
+    va[perm[n_train:n_train + n_val]] = True
+    te[perm[n_train + n_val:]] = True
+    return SmallConfig(f"planted{n}", n, f, c, ["PAP", "PSP"], X, [pap, psp], onehot, tr, va, te)
+
+
 SMALL = {"acm": acm_like, "dblp": dblp_like, "imdb": imdb_like}
 
 

@@ -288,3 +288,33 @@ def test_fused_adam_l2_matches_unfused_update_and_captures_into_one_graph():
         l1 = float(step())
     assert l1 < l0
     assert int(op_a.opt.t.item()) == 4 + 2 + 21            # eager + warm-up + replays (capture itself runs nothing)
+
+
+@pytest.mark.parametrize("cuda_graph", [False, True])
+def test_training_protocol_learns_a_planted_graph(cuda_graph, tmp_path):
+    """han_b200.train.fit = the reference driver's loop (ex_acm3025.py:161-270): dropout 0.6 training steps,
+    dropout-free validation, the OR / AND early-stopping rule, checkpoint restore, test pass.  On a graph
+    with planted classes the restored model must classify the held-out nodes; captured and eager loops
+    must agree on the protocol's bookkeeping."""
+    import han_b200 as hb
+    from han_b200 import train
+    cfg = synth.planted(seed=4001, n=600, f=120)
+    graphs = [hb.process.adj_to_bias(a, [cfg.N]) for a in cfg.adjs()]
+    splits = [np.where(m[:, None], cfg.labels, 0.0).astype(np.float32) for m in (cfg.train_mask, cfg.val_mask, cfg.test_mask)]
+    hp = hb.HANParams([cfg.F] * cfg.P, cfg.C, device="cuda", generator=torch.Generator().manual_seed(9))
+    ck = tmp_path / "han.pt"
+    res = train.fit([cfg.X] * cfg.P, graphs, *splits, cfg.train_mask, cfg.val_mask, cfg.test_mask, nb_epochs=60,
+                    patience=100, params=hp, checkpt_file=str(ck), cuda_graph=cuda_graph, log=None)
+    assert res.epochs_run == 60 and not res.stopped_early
+    h = res.history
+    assert h[-1]["train_loss"] < 0.6 * h[0]["train_loss"]
+    assert res.test_acc > 0.8, res.test_acc
+    rule = train.EarlyStopping(100)
+    for e in h:
+        rule.update(e["val_loss"], e["val_acc"])
+    assert (res.checkpoint_val_loss, res.checkpoint_val_acc) == (rule.ck_loss, rule.ck_acc)
+    assert res.best_val_loss == min(e["val_loss"] for e in h) and res.best_val_acc == max(e["val_acc"] for e in h)
+    assert abs(sum(h[-1]["att_val"]) - 1.0) < 1e-4                   # semantic attention sums to 1 over meta-paths
+    saved = torch.load(str(ck))
+    for k, v in hp.state_dict().items():                            # the model was left at the checkpoint
+        assert torch.equal(saved[k].to(v.device), v), k
