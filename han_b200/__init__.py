@@ -7,8 +7,8 @@ CUDA-only: every op calls hand-written kernels in libhan_sm100.so through ctypes
 """
 from . import _lib, base_gattn, gat, graph, layers, ops, process, variables  # noqa: F401
 from .base_gattn import BaseGAttN  # noqa: F401
-from .gat import HeteGAT, HeteGAT_multi  # noqa: F401
+from .gat import GAT, HeteGAT, HeteGAT_multi  # noqa: F401
 from .graph import MetaPathGraph  # noqa: F401
-from .variables import HANParams  # noqa: F401
+from .variables import GATParams, HANParams  # noqa: F401
 
-__all__ = ["HeteGAT", "HeteGAT_multi", "BaseGAttN", "MetaPathGraph", "HANParams", "layers", "process"]
+__all__ = ["GAT", "GATParams", "HeteGAT", "HeteGAT_multi", "BaseGAttN", "MetaPathGraph", "HANParams", "layers", "process"]

@@ -25,6 +25,63 @@ def _group_by_input(xs: Sequence[torch.Tensor]) -> List[List[int]]:
     return groups
 
 
+def _pad_heads(lay, K: int, H: int, Hp: int):
+    """Zero-pad every head from H to Hp columns (the kernels are instantiated for H in {4, 8, 16}); the pad
+    columns project to 0, add 0 to f1/f2 and come out as act(0) -- sliced away by the caller."""
+    if Hp == H:
+        return lay["W"], lay["a1"], lay["a2"], lay["bias"]
+    pad = torch.nn.functional.pad
+    F = lay["W"].shape[0]
+    return (pad(lay["W"].view(F, K, H), (0, Hp - H)).reshape(F, K * Hp), pad(lay["a1"], (0, Hp - H)),
+            pad(lay["a2"], (0, Hp - H)), pad(lay["bias"].view(K, H), (0, Hp - H)).reshape(K * Hp))
+
+
+class GAT(BaseGAttN):
+    """The homogeneous baseline, models/gat.py:8-32: ``len(hid_units)`` attention layers (heads concatenated),
+    then ``n_heads[-1]`` output heads of width ``nb_classes`` with the identity activation, averaged (:25-30).
+    Same kernels as HAN with one graph and no semantic layer."""
+
+    @staticmethod
+    def inference(inputs, nb_classes, nb_nodes, training, attn_drop, ffd_drop, bias_mat, hid_units, n_heads,
+                  activation=elu, residual=False, *, params: Optional[variables.GATParams] = None,
+                  project_mode: int = 0):
+        attn_drop, ffd_drop = float(attn_drop), float(ffd_drop)
+        x = layers._squeeze_batch(inputs)
+        _lib.require_cuda(x)
+        graph = layers.as_graph(bias_mat, x.device)
+        if params is None:
+            params = variables.GATParams(x.shape[1], nb_classes, hid_units, n_heads, device=x.device, residual=residual)
+        if residual and ffd_drop and any("W_res" in lay for lay in params.hidden):
+            raise NotImplementedError("residual conv1d on a per-head dropped input (layers.py:19,40) is not built")
+        seed = None
+        if attn_drop or ffd_drop:
+            seed = params.drop_seed
+            seed.add_(1)
+        act = ops.activation_code(activation)
+
+        def layer(h, lay, K, H, act_code, stream_id, mode):
+            Hp = next(c for c in (4, 8, 16) if c >= H) if H <= 16 else H
+            W, a1, a2, bias = _pad_heads(lay, K, H, Hp)
+            plan = ops.NodeAttentionPlan(graphs=[graph], K=K, H=Hp, act=act_code, project_mode=mode, in_drop=ffd_drop,
+                                         coef_drop=attn_drop, seed=seed, metapath_ids=[stream_id])
+            z = ops.node_attention(plan, h, W, a1.unsqueeze(0), lay["b1"].unsqueeze(0), a2.unsqueeze(0),
+                                   lay["b2"].unsqueeze(0), bias.unsqueeze(0))[:, 0, :]
+            return z if Hp == H else z.view(-1, K, Hp)[:, :, :H].reshape(-1, K * H)
+
+        h = x
+        for l, (lay, (K, H)) in enumerate(zip(params.hidden, params.layer_dims)):   # :11-23
+            use_res = "W_res" in lay
+            z = layer(h, lay, K, H, _lib.ACT_IDENTITY if use_res else act, l, project_mode if l == 0 else 0)
+            if use_res:
+                z = torch.addmm(lay["b_res"], h, lay["W_res"]) + z
+                z = z if act == _lib.ACT_IDENTITY else torch.nn.functional.elu(z)
+            h = z
+        K, C = params.out_heads, params.C
+        out = layer(h, params.out, K, C, _lib.ACT_IDENTITY, len(params.hidden), 0)     # :25-29
+        logits = out.view(-1, K, C).sum(1) / K                                        # :30
+        return logits.unsqueeze(0)
+
+
 class HeteGAT(BaseGAttN):
     """models/gat.py:132-203: one shared feature tensor for every meta-path and, with
     ``return_coef=True``, the head-averaged attention coefficients of every meta-path
@@ -67,10 +124,11 @@ class HeteGAT_multi(BaseGAttN):
         attn_drop, ffd_drop = float(attn_drop), float(ffd_drop)
         if not (0.0 <= attn_drop < 1.0 and 0.0 <= ffd_drop < 1.0):
             raise ValueError("attn_drop and ffd_drop are probabilities of dropping, in [0, 1)")
-        if residual:
-            raise NotImplementedError("residual=True is dead code for hid_units=[8] (gat.py:45) and not built")
-        if len(hid_units) != 1:
-            raise NotImplementedError("stacked attention layers (models/gat.py:48-57) are not built yet")
+        if len(n_heads) < len(hid_units) + 1:
+            raise ValueError("n_heads needs one entry per attention layer plus the output-layer entry")
+        if residual and len(hid_units) > 1 and ffd_drop:
+            raise NotImplementedError("residual=True with ffd_drop > 0: the residual conv1d reads each head's own "
+                                      "dropped copy of the input (layers.py:19,40); not built")
         pairs = list(zip(inputs_list, bias_mat_list))                      # :39
         P = len(pairs)
         xs = [layers._squeeze_batch(x) for x, _ in pairs]
@@ -82,7 +140,7 @@ class HeteGAT_multi(BaseGAttN):
             params = variables.get_default_store()
             if params is None:
                 params = variables.HANParams([x.shape[1] for x in xs], nb_classes, hid_units, n_heads,
-                                             mp_att_size, device=dev)
+                                             mp_att_size, device=dev, residual=residual)
                 variables.set_default_store(params)
         act = ops.activation_code(activation)
         seed = None
@@ -118,6 +176,29 @@ class HeteGAT_multi(BaseGAttN):
             order = [p for grp in groups for p in grp]
             inv = sorted(range(P), key=lambda i: order[i])
             multi_embed = torch.cat(z_parts, dim=1)[:, inv, :].contiguous()
+
+        # stacked layers (:48-57): every meta-path feeds its own concatenated heads to its next layer
+        for l in range(1, len(hid_units)):
+            Kl, Hl = int(n_heads[l]), int(hid_units[l])
+            lay = params.deep[l - 1]
+            use_res = residual and "W_res" in lay                           # layers.py:38-40 (no-op when widths agree, :42)
+            nxt = []
+            for p in range(P):
+                h_old = multi_embed[:, p, :].contiguous()                   # :49
+                plan = ops.NodeAttentionPlan(graphs=[graphs[p]], K=Kl, H=Hl,
+                                             act=_lib.ACT_IDENTITY if use_res else act, project_mode=0, dist=dist,
+                                             want_coefs=return_coef, in_drop=ffd_drop, coef_drop=attn_drop,
+                                             seed=seed, metapath_ids=[l * P + p])
+                h = ops.node_attention(plan, h_old, lay["W"][p], lay["a1"][p].unsqueeze(0), lay["b1"][p].unsqueeze(0),
+                                       lay["a2"][p].unsqueeze(0), lay["b2"][p].unsqueeze(0),
+                                       lay["bias"][p].unsqueeze(0))[:, 0, :]
+                if use_res:                                                 # ret + conv1d(seq, H, 1), then the activation
+                    h = torch.addmm(lay["b_res"][p], h_old, lay["W_res"][p]) + h
+                    h = h if act == _lib.ACT_IDENTITY else torch.nn.functional.elu(h)
+                if return_coef:
+                    coef_out[p] = layers.EdgeCoefs(graphs[p], plan.coefs[0])
+                nxt.append(h)
+            multi_embed = torch.stack(nxt, dim=1)                           # (N,P,K_l*H_l)
 
         final_embed, att_val = layers.SimpleAttLayer(                       # :61-63
             multi_embed, mp_att_size, time_major=False, return_alphas=True,

@@ -92,8 +92,6 @@ def attn_head(seq, out_sz, bias_mat, activation, in_drop=0.0, coef_drop=0.0, res
     ``params``: dict W (F,H), a1 (H,), b1 (), a2 (H,), b2 (), bias (H,); created with the
     reference initialisers when omitted and returned as ``attn_head.last_params``.
     """
-    if residual:
-        raise NotImplementedError("residual=True (layers.py:38-42) needs the input-gradient path; not built yet")
     x = _squeeze_batch(seq)
     _lib.require_cuda(x)
     graph = as_graph(bias_mat, x.device)
@@ -101,23 +99,92 @@ def attn_head(seq, out_sz, bias_mat, activation, in_drop=0.0, coef_drop=0.0, res
     if params is None:
         params = new_head_params(x.shape[1], H, x.device)
     attn_head.last_params = params
+    use_res = bool(residual) and x.shape[1] != H                     # :39-40; equal widths: a dead store (:42)
+    if use_res:
+        if in_drop:
+            raise NotImplementedError("residual conv1d on the dropped input (layers.py:19,40) is not built")
+        if "W_res" not in params:                                    # conv1d(seq, H, 1): glorot kernel, zero bias
+            lim = math.sqrt(6.0 / (x.shape[1] + H))
+            params["W_res"] = torch.nn.Parameter(torch.empty(x.shape[1], H).uniform_(-lim, lim).to(x.device))
+            params["b_res"] = torch.nn.Parameter(torch.zeros(H, device=x.device))
     seed = None
     if in_drop or coef_drop:
         seed = _drop_seed(x.device)
         seed.add_(1)
-    plan = ops.NodeAttentionPlan(graphs=[graph], K=1, H=H, act=ops.activation_code(activation),
+    act = ops.activation_code(activation)
+    plan = ops.NodeAttentionPlan(graphs=[graph], K=1, H=H, act=_lib.ACT_IDENTITY if use_res else act,
                                  want_coefs=bool(return_coef), in_drop=float(in_drop), coef_drop=float(coef_drop),
                                  seed=seed)
     Z = ops.node_attention(plan, x, params["W"], params["a1"].reshape(1, 1, H), params["b1"].reshape(1, 1),
                            params["a2"].reshape(1, 1, H), params["b2"].reshape(1, 1),
                            params["bias"].reshape(1, H))
     ret = Z.reshape(1, x.shape[0], H)
+    if use_res:                                                      # ret + conv1d(seq, H, 1), then the activation
+        ret = ret + torch.addmm(params["b_res"], x, params["W_res"]).unsqueeze(0)
+        ret = ret if act == _lib.ACT_IDENTITY else torch.nn.functional.elu(ret)
     if return_coef:
         return ret, EdgeCoefs(graph, plan.coefs[0])
     return ret
 
 
 attn_head.last_params = None
+
+
+def attn_head_const_1(seq, out_sz, bias_mat, activation, in_drop=0.0, coef_drop=0.0, residual=False, *,
+                      params: Optional[Dict[str, torch.Tensor]] = None):
+    """The HAN_nd ablation head (utils/layers.py:49-81): logits = the 0/1 adjacency itself, so after the
+    -1e9 mask every neighbour gets the same weight 1/deg(i) -- node-level attention switched off.
+    Runs the same kernels with constant scores (a1 = a2 = 0, b1 = 0, b2 = 1: e_ij = leaky_relu(1) on every
+    edge); only W and the output bias are variables (:56,70)."""
+    x = _squeeze_batch(seq)
+    _lib.require_cuda(x)
+    H = int(out_sz)
+    if params is None:
+        full = new_head_params(x.shape[1], H, x.device)
+        params = {"W": full["W"], "bias": full["bias"]}
+    attn_head_const_1.last_params = params
+    dev = x.device
+    const = {"W": params["W"], "bias": params["bias"], "a1": torch.zeros(H, device=dev), "b1": torch.zeros((), device=dev),
+             "a2": torch.zeros(H, device=dev), "b2": torch.ones((), device=dev)}
+    for k in ("W_res", "b_res"):
+        if k in params:
+            const[k] = params[k]
+    out = attn_head(seq, out_sz, bias_mat, activation, in_drop=in_drop, coef_drop=coef_drop, residual=residual,
+                    params=const)
+    for k in ("W_res", "b_res"):
+        if k in const:
+            params[k] = const[k]
+    return out
+
+
+attn_head_const_1.last_params = None
+
+
+def sp_attn_head(seq, out_sz, adj_mat, activation, nb_nodes, in_drop=0.0, coef_drop=0.0, residual=False, *,
+                 params: Optional[Dict[str, torch.Tensor]] = None):
+    """Sparse-adjacency head (utils/layers.py:85-127): logits ``adj_ij * (f1_i + f2_j)`` on the stored
+    entries, ``sparse_softmax`` over each row's entries.  With the 0/1 adjacency the reference's drivers
+    build this is ``attn_head`` exactly, which already works on the edge list; weighted adjacencies
+    (entries != 1 scale the logits) are rejected rather than silently treated as 1.
+
+    adj_mat: a ``MetaPathGraph``, or a torch sparse COO/CSR tensor (N,N) whose stored values are all 1."""
+    x = _squeeze_batch(seq)
+    if isinstance(adj_mat, torch.Tensor) and adj_mat.layout != torch.strided:
+        coo = adj_mat.to_sparse_coo().coalesce()
+        vals = coo.values()
+        if vals.numel() and not bool((vals == 1).all()):
+            raise NotImplementedError("sp_attn_head with edge weights != 1 (logits scaled per edge) is not built")
+        idx = coo.indices()
+        n = int(nb_nodes)
+        order = torch.argsort(idx[0] * n + idx[1])
+        rows, cols = idx[0][order], idx[1][order]
+        indptr = torch.zeros(n + 1, dtype=torch.int64, device=rows.device)
+        indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
+        adj_mat = MetaPathGraph.from_csr(indptr.to(x.device), cols.to(torch.int32).to(x.device), n_cols=n, device=x.device)
+    elif not isinstance(adj_mat, MetaPathGraph):
+        raise TypeError("adj_mat: MetaPathGraph or a torch sparse tensor")
+    return attn_head(seq, out_sz, adj_mat, activation, in_drop=in_drop, coef_drop=coef_drop, residual=residual,
+                     params=params)
 
 
 def SimpleAttLayer(inputs, attention_size, time_major=False, return_alphas=False, *,

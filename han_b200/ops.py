@@ -167,6 +167,7 @@ class NodeAttentionFn(torch.autograd.Function):
                     plan.coefs.append(alpha)
         ctx.plan = plan
         ctx.S_keep = S_keep
+        ctx.W = W if ctx.needs_input_grad[1] else None     # only a stacked layer needs W again (for dX)
         ctx.save_for_backward(X, a1, a2, T, R, V, Z)
         ctx.mark_non_differentiable()
         return Z
@@ -271,10 +272,17 @@ class NodeAttentionFn(torch.autograd.Function):
         da2 = dpar[:, D:2 * D].reshape(G, K, H)
         db1 = dpar[:, 2 * D:2 * D + K]
         db2 = dpar[:, 2 * D + K:]
+        dX = None
         if ctx.needs_input_grad[1]:
-            raise _lib.HanError("gradient w.r.t. the input features is not implemented "
-                                "(single attention layer: hid_units=[8], models/gat.py:48-57 unused)")
-        return None, None, dW, da1, db1, da2, db2, dbias
+            # stacked layers (models/gat.py:48-57): the layer below needs dX = sum_g sum_k (m_gk/keep) * dS_gk W_gk^T
+            W = ctx.W
+            dX = _empty((n, F), dev)
+            with torch.cuda.device(dev):
+                for g in range(G):
+                    call("han_project_dx", ptr(dS[g]), n, K, H, ptr(W[:, g * D:]), G * D, F, ptr(dX), F, 1 if g else 0,
+                         ptr(plan.seed) if plan.in_drop else None, 1.0 - plan.in_drop, plan.metapath_id(g), lo_row,
+                         stream_ptr())
+        return None, dX, dW, da1, db1, da2, db2, dbias
 
 
 class SemanticAttentionFn(torch.autograd.Function):

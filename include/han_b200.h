@@ -204,6 +204,16 @@ int han_project_bwd_drop(const float* X, int64_t n, int64_t F, int64_t ldx, cons
                          int H, float* dW, int64_t ldw, void* ws, size_t ws_bytes, const uint32_t* seed_ptr,
                          float in_keep, int metapath0, int64_t row0, han_stream_t stream);
 
+/* Gradient of the projection w.r.t. its input, for stacked attention layers (models/gat.py:48-57 feed the
+ * concatenated heads of one layer to the next; utils/layers.py:18-20 for the per-head input dropout):
+ *   dX[n][f] (+)= sum_k m_k(n,f)/keep * sum_h dS[n][k*H+h] * W[f][k*H+h]          (one meta-path per call)
+ * dS [n][K*H]; W points at the meta-path's first column of the (F x ldw) weight matrix; dX [n][ldx];
+ * accumulate != 0 adds to dX (meta-paths that share an input).  seed_ptr (device uint32, nullable) and
+ * in_keep < 1 regenerate the forward's masks of han_project_fwd_drop; otherwise plain dS W^T. */
+int han_project_dx(const float* dS, int64_t n, int K, int H, const float* W, int64_t ldw, int64_t F,
+                   float* dX, int64_t ldx, int accumulate, const void* seed_ptr, float in_keep,
+                   int metapath, int64_t row0, han_stream_t stream);
+
 /* Deterministic column sums of partial buffers: outv[c] = sum_b part[b][c]. */
 int han_reduce_partials(const float* part, int nblocks, int64_t cols, float* outv, han_stream_t stream);
 

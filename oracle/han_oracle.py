@@ -171,6 +171,19 @@ def attn_head(seq: torch.Tensor, out_sz: int, bias_mat: torch.Tensor, activation
     return activation(ret)                                                 # :46
 
 
+def attn_head_const_1(seq: torch.Tensor, out_sz: int, bias_mat: torch.Tensor, activation: Callable,
+                      hp: Dict[str, torch.Tensor], residual: bool = False) -> torch.Tensor:
+    """Restates ``attn_head_const_1`` (utils/layers.py:49-81), dropout off: the logits are the 0/1
+    adjacency recovered from the bias (:55), so every neighbour weighs 1/deg.  ``hp``: W (F,H), bias (H,)."""
+    adj_mat = 1.0 - bias_mat / -1e9                                          # :55
+    seq_fts = _conv1d_k1(seq, hp["W"], None)                                 # :59
+    coefs = torch.softmax(F.leaky_relu(adj_mat, LEAKY_SLOPE) + bias_mat, dim=-1)   # :62-63
+    ret = torch.matmul(coefs, seq_fts) + hp["bias"]                          # :70-71
+    if residual and seq.shape[-1] != ret.shape[-1]:                          # :74-76
+        ret = ret + _conv1d_k1(seq, hp["W_res"], hp.get("b_res"))
+    return activation(ret)                                                   # :81
+
+
 # ----------------------------------------------------------------------------
 # utils/layers.py:132-164
 # ----------------------------------------------------------------------------
@@ -212,11 +225,14 @@ def head_params(params: Dict, p: int, k: int, layer: int = 0) -> Dict[str, torch
     ``params['W'][p]`` (F,K*H) with head k in columns k*H:(k+1)*H, ``a1/a2[p]`` (K,H),
     ``b1/b2[p]`` (K,), ``bias[p]`` (K*H,).
     """
-    assert layer == 0
-    H = params["a1"][p].shape[1]
+    src = params if layer == 0 else params["deep"][layer - 1]      # stacked layers keep the same keys
+    H = src["a1"][p].shape[1]
     sl = slice(k * H, (k + 1) * H)
-    return {"W": params["W"][p][:, sl], "a1": params["a1"][p][k], "b1": params["b1"][p][k],
-            "a2": params["a2"][p][k], "b2": params["b2"][p][k], "bias": params["bias"][p][sl]}
+    hp = {"W": src["W"][p][:, sl], "a1": src["a1"][p][k], "b1": src["b1"][p][k],
+          "a2": src["a2"][p][k], "b2": src["b2"][p][k], "bias": src["bias"][p][sl]}
+    if "W_res" in src:
+        hp["W_res"], hp["b_res"] = src["W_res"][p][:, sl], src["b_res"][p][sl]
+    return hp
 
 
 def HeteGAT_multi_inference(inputs_list, nb_classes, nb_nodes, training, attn_drop, ffd_drop,
@@ -229,7 +245,6 @@ def HeteGAT_multi_inference(inputs_list, nb_classes, nb_nodes, training, attn_dr
     Returns ``(logits (1,N,C), final_embed (N,D), att_val (N,P))`` (:76-77); with
     ``return_coef`` additionally the per-(meta-path, head) dense coefficient list.
     """
-    assert len(hid_units) == 1, "oracle covers the shipped config hid_units=[8] (gat.py:48-57 not exercised)"
     embed_list = []
     coef_list = []
     for p, (inputs, bias_mat) in enumerate(zip(inputs_list, bias_mat_list)):     # :39
@@ -243,6 +258,17 @@ def HeteGAT_multi_inference(inputs_list, nb_classes, nb_nodes, training, attn_dr
             else:
                 attns.append(r)
         h_1 = torch.cat(attns, dim=-1)                                           # :46  (1,N,D)
+        for i in range(1, len(hid_units)):                                       # :48-57
+            attns = []
+            for k in range(n_heads[i]):
+                r = attn_head(h_1, hid_units[i], bias_mat, activation, head_params(params, p, k, layer=i),
+                              in_drop=ffd_drop, coef_drop=attn_drop, residual=residual,
+                              return_coef=return_coef, gen=gen)                  # :52-56
+                if return_coef:
+                    attns.append(r[0]); coef_list.append(r[1])
+                else:
+                    attns.append(r)
+            h_1 = torch.cat(attns, dim=-1)                                       # :57
         embed_list.append(h_1.squeeze(0).unsqueeze(1))                           # :58  (N,1,D)
     multi_embed = torch.cat(embed_list, dim=1)                                   # :60  (N,P,D)
     final_embed, att_val = SimpleAttLayer(multi_embed, mp_att_size, params, time_major=False,
@@ -255,6 +281,53 @@ def HeteGAT_multi_inference(inputs_list, nb_classes, nb_nodes, training, attn_dr
     if return_coef:
         return logits, final_embed, att_val, coef_list
     return logits, final_embed, att_val
+
+
+def GAT_inference(inputs, nb_classes, nb_nodes, training, attn_drop, ffd_drop, bias_mat, hid_units, n_heads,
+                  params: Dict, activation: Callable = elu, residual: bool = False,
+                  gen: Optional[torch.Generator] = None):
+    """Restates ``GAT.inference`` (models/gat.py:9-32).  ``params``: {"hidden": [layer dicts], "out": layer dict},
+    each layer dict in the concatenated-heads layout of ``head_params`` (W (F,K*H), a1/a2 (K,H), b1/b2 (K,), bias)."""
+    def head(lay, k, H):
+        sl = slice(k * H, (k + 1) * H)
+        hp = {"W": lay["W"][:, sl], "a1": lay["a1"][k], "b1": lay["b1"][k], "a2": lay["a2"][k], "b2": lay["b2"][k],
+              "bias": lay["bias"][sl]}
+        if "W_res" in lay:
+            hp["W_res"], hp["b_res"] = lay["W_res"][:, sl], lay["b_res"][sl]
+        return hp
+    h_1 = inputs
+    for i in range(len(hid_units)):                                              # :11-23
+        attns = [attn_head(h_1, hid_units[i], bias_mat, activation, head(params["hidden"][i], k, hid_units[i]),
+                           in_drop=ffd_drop, coef_drop=attn_drop, residual=residual and i >= 1, gen=gen)
+                 for k in range(n_heads[i])]
+        h_1 = torch.cat(attns, dim=-1)
+    out = [attn_head(h_1, nb_classes, bias_mat, identity, head(params["out"], k, nb_classes),
+                     in_drop=ffd_drop, coef_drop=attn_drop, residual=False, gen=gen)
+           for k in range(n_heads[-1])]                                          # :25-29
+    return sum(out) / n_heads[-1]                                                # :30
+
+
+def init_gat_params(rng: np.random.Generator, ft_size: int, nb_classes: int, hid_units: Sequence[int],
+                    n_heads: Sequence[int], dtype=torch.float64, residual: bool = False) -> Dict:
+    def glorot(fan_in, fan_out, shape):
+        lim = math.sqrt(6.0 / (fan_in + fan_out))
+        return torch.from_numpy(rng.uniform(-lim, lim, size=shape)).to(dtype)
+
+    def small(shape):
+        return torch.from_numpy(rng.normal(0, 0.1, size=shape)).to(dtype)
+
+    def layer(F, K, H, res):
+        lay = {"W": torch.cat([glorot(F, H, (F, H)) for _ in range(K)], dim=1), "a1": glorot(H, 1, (K, H)),
+               "b1": small((K,)), "a2": glorot(H, 1, (K, H)), "b2": small((K,)), "bias": small((K * H,))}
+        if res:
+            lay["W_res"] = torch.cat([glorot(F, H, (F, H)) for _ in range(K)], dim=1)
+            lay["b_res"] = small((K * H,))
+        return lay
+    hidden, F = [], ft_size
+    for l, H in enumerate(hid_units):
+        hidden.append(layer(F, n_heads[l], H, residual and l >= 1 and F != H))
+        F = n_heads[l] * H
+    return {"hidden": hidden, "out": layer(F, n_heads[-1], nb_classes, False)}
 
 
 # ----------------------------------------------------------------------------
@@ -283,6 +356,9 @@ def flat_params(params: Dict) -> List[torch.Tensor]:
     for key in ("W", "a1", "b1", "a2", "b2", "bias", "Wc", "bc"):
         out.extend(params[key])
     out.extend([params["w_omega"], params["b_omega"], params["u_omega"]])
+    for lay in params.get("deep", []):
+        for v in lay.values():
+            out.extend(v)
     return out
 
 
@@ -304,12 +380,13 @@ def adam_step_tf1(param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: t
 
 
 def step_loss(inputs_list, bias_mat_list, labels, mask, params, nb_classes, hid_units, n_heads,
-              l2_coef: float = 0.001, semantic_mode: str = "reference"):
+              l2_coef: float = 0.001, semantic_mode: str = "reference", residual: bool = False):
     """One forward of the training objective the driver builds (ex_acm3025.py:139-152):
     inference -> reshape -> masked CE -> + L2.  Returns (total, ce, logits, final_embed, att_val)."""
     logits, final_embed, att_val = HeteGAT_multi_inference(
         inputs_list, nb_classes, inputs_list[0].shape[1], True, 0.0, 0.0, bias_mat_list,
-        hid_units, n_heads, params, mp_att_size=params["w_omega"].shape[1], semantic_mode=semantic_mode)
+        hid_units, n_heads, params, mp_att_size=params["w_omega"].shape[1], semantic_mode=semantic_mode,
+        residual=residual)
     log_resh = logits.reshape(-1, nb_classes)                                    # ex_acm3025.py:146
     ce = masked_softmax_cross_entropy(log_resh, labels.reshape(-1, nb_classes), mask.reshape(-1))
     total = ce + l2_loss_all(params, l2_coef)
@@ -362,7 +439,8 @@ def inference_edges(x_list, csr_list, params, n_heads, hid_units, mp_att_size=12
 # ----------------------------------------------------------------------------
 def init_params(rng: np.random.Generator, ft_sizes: Sequence[int], nb_classes: int, hid: int = 8,
                 heads: int = 8, mp_att_size: int = 128, out_heads: int = 1,
-                dtype=torch.float64, zero_bias: bool = False) -> Dict:
+                dtype=torch.float64, zero_bias: bool = False, deep: Sequence[Tuple[int, int]] = (),
+                residual: bool = False) -> Dict:
     """Glorot-uniform conv1d/dense kernels, N(0,0.1^2) semantic variables.  The reference
     zero-initialises b1,b2,bias,bc; ``zero_bias=False`` draws them small-random instead so
     parity tests exercise them."""
@@ -385,6 +463,24 @@ def init_params(rng: np.random.Generator, ft_sizes: Sequence[int], nb_classes: i
         params["a2"].append(glorot(hid, 1, (heads, hid)))
         params["b2"].append(small((heads,)))
         params["bias"].append(small((D,)))
+    Fl = D
+    for (Kl, Hl) in deep:            # stacked layers (heads, hid) after the first, models/gat.py:48-57
+        lay = {k: [] for k in ("W", "a1", "b1", "a2", "b2", "bias")}
+        if residual and Fl != Hl:
+            lay["W_res"], lay["b_res"] = [], []
+        for _ in ft_sizes:
+            lay["W"].append(torch.cat([glorot(Fl, Hl, (Fl, Hl)) for _ in range(Kl)], dim=1))
+            lay["a1"].append(glorot(Hl, 1, (Kl, Hl)))
+            lay["b1"].append(small((Kl,)))
+            lay["a2"].append(glorot(Hl, 1, (Kl, Hl)))
+            lay["b2"].append(small((Kl,)))
+            lay["bias"].append(small((Kl * Hl,)))
+            if "W_res" in lay:
+                lay["W_res"].append(torch.cat([glorot(Fl, Hl, (Fl, Hl)) for _ in range(Kl)], dim=1))
+                lay["b_res"].append(small((Kl * Hl,)))
+        params.setdefault("deep", []).append(lay)
+        Fl = Kl * Hl
+    D = Fl
     params["w_omega"] = torch.from_numpy(rng.normal(0, 0.1, size=(D, mp_att_size))).to(dtype)
     params["b_omega"] = torch.from_numpy(rng.normal(0, 0.1, size=(mp_att_size,))).to(dtype)
     params["u_omega"] = torch.from_numpy(rng.normal(0, 0.1, size=(mp_att_size,))).to(dtype)
@@ -401,5 +497,8 @@ def params_to(params: Dict, dtype=None, requires_grad: bool = False) -> Dict:
         return t.requires_grad_(requires_grad)
     out = {}
     for k, v in params.items():
-        out[k] = [conv(t) for t in v] if isinstance(v, list) else conv(v)
+        if k == "deep":
+            out[k] = [{kk: [conv(t) for t in vv] for kk, vv in lay.items()} for lay in v]
+        else:
+            out[k] = [conv(t) for t in v] if isinstance(v, list) else conv(v)
     return out

@@ -318,3 +318,19 @@ def test_training_protocol_learns_a_planted_graph(cuda_graph, tmp_path):
     saved = torch.load(str(ck))
     for k, v in hp.state_dict().items():                            # the model was left at the checkpoint
         assert torch.equal(saved[k].to(v.device), v), k
+
+
+@pytest.mark.parametrize("residual", [False, True])
+def test_stacked_attention_layers_and_residual_match_oracle(residual):
+    """models/gat.py:48-57: hid_units=[8,8], n_heads=[4,2,1] -- every meta-path feeds its concatenated heads
+    to a second attention layer (needs the input gradient of the projection, han_project_dx); with
+    ``residual`` the second layer adds conv1d(seq, H, 1) before the activation (utils/layers.py:38-40)."""
+    cfg = synth.tiny(seed=91, n=110, f=26, p=2, deg=6.0)
+    rng = np.random.default_rng(92)
+    params = O.init_params(rng, [cfg.F] * cfg.P, cfg.C, hid=8, heads=4, mp_att_size=32, deep=[(2, 8)], residual=residual)
+    assert ("W_res" in params["deep"][0]) == residual
+    kw = dict(hid_units=(8, 8), n_heads=(4, 2, 1), residual=residual)
+    out_o, grads_o = oracle_step(cfg, params, **kw)
+    out_p, grads_p, _ = product_step(cfg, params, **kw)
+    assert out_p["final_embed"].shape == (cfg.N, 16)
+    compare_step(out_o, grads_o, out_p, grads_p)

@@ -34,8 +34,18 @@ def assert_close(a, b, name="", rel=REL_TOL, rtol=RTOL, atol=ATOL):
     assert ok, f"{name}: allclose(rtol={rtol}) failed, max abs diff {(a - b).abs().max().item():.3e}"
 
 
+def _grads_of(p):
+    out = {}
+    for k, v in p.items():
+        if k == "deep":
+            out[k] = [{kk: [t.grad for t in vv] for kk, vv in lay.items()} for lay in v]
+        else:
+            out[k] = [t.grad for t in v] if isinstance(v, list) else v.grad
+    return out
+
+
 def oracle_step(cfg, params64, hid_units=(8,), n_heads=(8, 1), semantic_mode="reference", l2_coef=0.001,
-                mask=None):
+                mask=None, residual=False):
     """fp64 dense oracle forward + autograd backward of (masked CE + L2).  Returns dict of outputs
     and a params-shaped dict of gradients."""
     p = O.params_to(params64, torch.float64, requires_grad=True)
@@ -44,20 +54,22 @@ def oracle_step(cfg, params64, hid_units=(8,), n_heads=(8, 1), semantic_mode="re
     labels = torch.from_numpy(cfg.labels).double()
     m = torch.from_numpy((cfg.train_mask if mask is None else mask).astype(np.float64))
     total, ce, logits, final_embed, att_val = O.step_loss(
-        [X] * cfg.P, biases, labels, m, p, cfg.C, list(hid_units), list(n_heads), l2_coef, semantic_mode)
+        [X] * cfg.P, biases, labels, m, p, cfg.C, list(hid_units), list(n_heads), l2_coef, semantic_mode,
+        residual=residual)
     total.backward()
-    grads = {k: ([t.grad for t in v] if isinstance(v, list) else v.grad) for k, v in p.items()}
+    grads = _grads_of(p)
     return {"total": total.detach(), "ce": ce.detach(), "logits": logits.detach(),
             "final_embed": final_embed.detach(), "att_val": att_val.detach()}, grads
 
 
 def product_step(cfg, params64, hid_units=(8,), n_heads=(8, 1), semantic_mode="reference", l2_coef=0.001,
-                 mask=None, graphs=None, project_mode=0):
+                 mask=None, graphs=None, project_mode=0, residual=False):
     """The CUDA product on the same inputs through the reference-shaped API."""
     import han_b200 as hb
     dev = torch.device("cuda")
     K, H = n_heads[0], hid_units[0]
-    hp = hb.HANParams([cfg.F] * cfg.P, cfg.C, hid_units, n_heads, params64["w_omega"].shape[1], device=dev)
+    hp = hb.HANParams([cfg.F] * cfg.P, cfg.C, hid_units, n_heads, params64["w_omega"].shape[1], device=dev,
+                      residual=residual)
     hp.load_dict(params64)
     X = torch.from_numpy(cfg.X).to(dev).unsqueeze(0)
     if graphs is None:
@@ -67,7 +79,7 @@ def product_step(cfg, params64, hid_units=(8,), n_heads=(8, 1), semantic_mode="r
     logits, final_embed, att_val = hb.HeteGAT_multi.inference(
         [X] * cfg.P, cfg.C, cfg.N, True, 0.0, 0.0, graphs, list(hid_units), list(n_heads),
         mp_att_size=params64["w_omega"].shape[1], params=hp, semantic_mode=semantic_mode,
-        project_mode=project_mode)
+        project_mode=project_mode, residual=residual)
     ce = hb.BaseGAttN.masked_softmax_cross_entropy(logits.reshape(-1, cfg.C), labels, m)
     train = hb.BaseGAttN.training(hp, 0.005, l2_coef)
     total = ce + train.l2_loss()
@@ -81,7 +93,12 @@ def compare_step(out_o, grads_o, out_p, grads_p, rel=REL_TOL):
     for k in ("logits", "final_embed", "att_val", "ce", "total"):
         assert_close(out_p[k], out_o[k], k, rel=rel)
     for k, v in grads_o.items():
-        if isinstance(v, list):
+        if k == "deep":
+            for l, lay in enumerate(v):
+                for kk, vv in lay.items():
+                    for i, g in enumerate(vv):
+                        assert_close(grads_p[k][l][kk][i], g, f"deep[{l}].d{kk}[{i}]", rel=rel)
+        elif isinstance(v, list):
             for i, g in enumerate(v):
                 assert_close(grads_p[k][i], g, f"d{k}[{i}]", rel=rel)
         else:
