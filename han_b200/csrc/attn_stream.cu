@@ -27,6 +27,16 @@ struct DropCoef {
   int64_t row0;               // global id of local row 0 (destination rows forward, source rows backward)
 };
 
+// Heavy rows (power-law graphs: a row with 10^5..10^6 edges would keep ONE warp busy for milliseconds) are cut
+// into segments of at most `split` edges.  The kernels then walk a VIRTUAL-row CSR (same column array, extra
+// offsets): a virtual row that is a whole real row is finished as usual; a segment of a cut row leaves its
+// partial state (forward: running max, normaliser, un-normalised aggregate; backward: plain sums) in
+// part[slot][K][H+2], and a small merge kernel (one warp per cut row) combines the segments.
+struct SplitRows {
+  const int2* vmap;   // per virtual row: x = real row, y = partial slot, or -1 when the row is whole
+  float* part;        // [n_slots][K][H + 2]
+};
+
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
@@ -59,13 +69,13 @@ __global__ void chunk_rows_kernel(const int64_t* __restrict__ indptr, int64_t n_
 // -------------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------------
-template <int K, int H, int STAGES>
+template <int K, int H, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(kStreamWarps * 32, 4)
 attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                         const int32_t* __restrict__ chunk_rows, int64_t n_chunks,
                         const float* __restrict__ T, float* __restrict__ R, const float* __restrict__ bias,
                         int act, float* __restrict__ out, int64_t out_stride, float* __restrict__ vsave,
-                        const float* __restrict__ colmean, DropCoef dc) {
+                        const float* __restrict__ colmean, DropCoef dc, SplitRows sp) {
   constexpr int D = K * H;
   constexpr int TS = ((D + K + 3) / 4) * 4;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
@@ -113,10 +123,16 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) issue();
 
-  int row = r_lo;
+  int row = r_lo;     // row of the (virtual) CSR being streamed; rr = the real row it belongs to
+  int rr = row, pslot = -1;
+  if constexpr (SPLIT) {
+    const int2 v = __ldg(sp.vmap + row);
+    rr = v.x;
+    pslot = v.y;
+  }
   int64_t row_start = e_lo;
   int64_t row_end = indptr[row + 1];
-  float f1v = R[(int64_t)row * RS + D + head];
+  float f1v = R[(int64_t)rr * RS + D + head];
   float m = -INFINITY, l = 0.f;
   float acc[H];
 #pragma unroll
@@ -139,6 +155,18 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
       }
       m = mn;
     }
+    if constexpr (SPLIT) {
+      if (pslot >= 0) {   // a segment of a cut row: leave (max, normaliser, un-normalised aggregate) for the merge
+        if (slot == 0) {
+          float* pp = sp.part + ((int64_t)pslot * K + head) * (H + 2);
+          pp[0] = m;
+          pp[1] = l;
+#pragma unroll
+          for (int h = 0; h < H; ++h) pp[2 + h] = acc[h];
+        }
+        return;
+      }
+    }
     if (slot == 0) {
       float lse;
       if (row_end > row_start) {
@@ -152,9 +180,9 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
 #pragma unroll
         for (int h = 0; h < H; ++h) acc[h] = colmean ? colmean[head * H + h] : 0.f;
       }
-      R[(int64_t)row * RS + D + K + head] = lse;
-      float* vp = vsave + (int64_t)row * D + head * H;
-      float* op = out + (int64_t)row * out_stride + head * H;
+      R[(int64_t)rr * RS + D + K + head] = lse;
+      float* vp = vsave + (int64_t)rr * D + head * H;
+      float* op = out + (int64_t)rr * out_stride + head * H;
 #pragma unroll
       for (int qv = 0; qv < HV; ++qv) {
         float4 a = make_float4(acc[4 * qv], acc[4 * qv + 1], acc[4 * qv + 2], acc[4 * qv + 3]);
@@ -176,7 +204,13 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
     row_start = row_end;
     if (row < r_hi) {
       row_end = indptr[row + 1];
-      f1v = R[(int64_t)row * RS + D + head];
+      rr = row;
+      if constexpr (SPLIT) {
+        const int2 v = __ldg(sp.vmap + row);
+        rr = v.x;
+        pslot = v.y;
+      }
+      f1v = R[(int64_t)rr * RS + D + head];
     }
     m = -INFINITY;
     l = 0.f;
@@ -207,7 +241,7 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
           float pk = p;              // ... the aggregate only the kept ones, scaled 1/keep (no re-normalisation)
           if (dc.thr) {
             const uint32_t src = (uint32_t)cbuf[(int)(ei - bs)];
-            pk = keep24(cseed, (uint32_t)(row + dc.row0), src, dc.thr) ? p * dc.inv_keep : 0.f;
+            pk = keep24(cseed, (uint32_t)(rr + dc.row0), src, dc.thr) ? p * dc.inv_keep : 0.f;
           }
 #pragma unroll
           for (int qv = 0; qv < HV; ++qv) {
@@ -238,13 +272,13 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
 // -------------------------------------------------------------------------------------------------
 // backward, by source (transposed structure)
 // -------------------------------------------------------------------------------------------------
-template <int K, int H, int STAGES>
+template <int K, int H, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(kStreamWarps * 32, 3)
 attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t* __restrict__ t_indices,
                             const int32_t* __restrict__ perm, const int32_t* __restrict__ chunk_rows,
                             int64_t n_chunks, const float* __restrict__ Tsrc, const float* __restrict__ R,
                             float* __restrict__ dS_agg, float* __restrict__ df2,
-                            float* __restrict__ dl_edge, DropCoef dc) {
+                            float* __restrict__ dl_edge, DropCoef dc, SplitRows sp) {
   constexpr int D = K * H;
   constexpr int TS = ((D + K + 3) / 4) * 4;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
@@ -314,7 +348,13 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
     }
     f2 = __ldg(Tsrc + (int64_t)r * TS + D + head);
   };
-  load_src(row);
+  int rr = row, pslot = -1;
+  if constexpr (SPLIT) {
+    const int2 v = __ldg(sp.vmap + row);
+    rr = v.x;
+    pslot = v.y;
+  }
+  load_src(rr);
   float acc[H];
 #pragma unroll
   for (int h = 0; h < H; ++h) acc[h] = 0.f;
@@ -327,11 +367,22 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
 #pragma unroll
       for (int h = 0; h < H; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], off);
     }
+    if constexpr (SPLIT) {
+      if (pslot >= 0) {   // a segment of a cut row: partial sums for the merge
+        if (slot == 0) {
+          float* pp = sp.part + ((int64_t)pslot * K + head) * (H + 2);
+          pp[0] = df2acc;
+#pragma unroll
+          for (int h = 0; h < H; ++h) pp[2 + h] = acc[h];
+        }
+        return;
+      }
+    }
     if (slot == 0) {
-      df2[(int64_t)row * K + head] = df2acc;
+      df2[(int64_t)rr * K + head] = df2acc;
 #pragma unroll
       for (int qv = 0; qv < HV; ++qv)
-        *reinterpret_cast<float4*>(dS_agg + (int64_t)row * D + head * H + 4 * qv) =
+        *reinterpret_cast<float4*>(dS_agg + (int64_t)rr * D + head * H + 4 * qv) =
             make_float4(acc[4 * qv], acc[4 * qv + 1], acc[4 * qv + 2], acc[4 * qv + 3]);
     }
   };
@@ -339,7 +390,13 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
     ++row;
     if (row < r_hi) {
       row_end = t_indptr[row + 1];
-      load_src(row);
+      rr = row;
+      if constexpr (SPLIT) {
+        const int2 v = __ldg(sp.vmap + row);
+        rr = v.x;
+        pslot = v.y;
+      }
+      load_src(rr);
     }
     df2acc = 0.f;
 #pragma unroll
@@ -369,7 +426,7 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
           // coefficient dropout: alpha~ = alpha * m / keep feeds the aggregate; d alpha = d alpha~ * m / keep
           float mk = 1.f;
           if (dc.thr)
-            mk = keep24(cseed, (uint32_t)rbuf[rec], (uint32_t)(row + dc.row0), dc.thr) ? dc.inv_keep : 0.f;
+            mk = keep24(cseed, (uint32_t)rbuf[rec], (uint32_t)(rr + dc.row0), dc.thr) ? dc.inv_keep : 0.f;
           const float am = a * mk;
           float da = 0.f;
 #pragma unroll
@@ -404,6 +461,96 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
   cp_async_wait<0>();
 }
 
+// one warp per cut row: combine its segments' partial states, then the forward's row epilogue
+template <int K, int H>
+__global__ void __launch_bounds__(128)
+attn_fwd_merge_kernel(const int32_t* __restrict__ heavy_rows, const int32_t* __restrict__ heavy_ptr, int n_heavy,
+                      const float* __restrict__ part, float* __restrict__ R, const float* __restrict__ bias, int act,
+                      float* __restrict__ out, int64_t out_stride, float* __restrict__ vsave) {
+  constexpr int D = K * H;
+  constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
+  constexpr int SLOTS = 32 / K;
+  const int hw = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (hw >= n_heavy) return;
+  const int lane = threadIdx.x & 31, head = lane % K, slot = lane / K;
+  const int rr = heavy_rows[hw];
+  const int s_lo = heavy_ptr[hw], s_hi = heavy_ptr[hw + 1];
+  float m = -INFINITY, l = 0.f, acc[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) acc[h] = 0.f;
+  auto combine = [&](float mo, float lo, const float* ao) {
+    const float mn = fmaxf(m, mo);
+    const float s0 = (m == -INFINITY) ? 0.f : __expf(m - mn);
+    const float s1 = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+    l = l * s0 + lo * s1;
+#pragma unroll
+    for (int h = 0; h < H; ++h) acc[h] = acc[h] * s0 + ao[h] * s1;
+    m = mn;
+  };
+  for (int sgm = s_lo + slot; sgm < s_hi; sgm += SLOTS) {
+    const float* pp = part + ((int64_t)sgm * K + head) * (H + 2);
+    float ao[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) ao[h] = pp[2 + h];
+    combine(pp[0], pp[1], ao);
+  }
+#pragma unroll
+  for (int off = K; off < 32; off <<= 1) {
+    const float mo = __shfl_xor_sync(0xffffffffu, m, off);
+    const float lo = __shfl_xor_sync(0xffffffffu, l, off);
+    float ao[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) ao[h] = __shfl_xor_sync(0xffffffffu, acc[h], off);
+    combine(mo, lo, ao);
+  }
+  if (slot == 0) {
+    const float rinv = 1.f / l;
+    R[(int64_t)rr * RS + D + K + head] = m + __logf(l);
+    float* vp = vsave + (int64_t)rr * D + head * H;
+    float* op = out + (int64_t)rr * out_stride + head * H;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float a = acc[h] * rinv;
+      vp[h] = a;
+      const float z = a + bias[head * H + h];
+      op[h] = (act == HAN_ACT_ELU && z <= 0.f) ? expm1f(z) : z;
+    }
+  }
+}
+
+template <int K, int H>
+__global__ void __launch_bounds__(128)
+attn_bwd_src_merge_kernel(const int32_t* __restrict__ heavy_rows, const int32_t* __restrict__ heavy_ptr, int n_heavy,
+                          const float* __restrict__ part, float* __restrict__ dS_agg, float* __restrict__ df2) {
+  constexpr int D = K * H;
+  constexpr int SLOTS = 32 / K;
+  const int hw = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (hw >= n_heavy) return;
+  const int lane = threadIdx.x & 31, head = lane % K, slot = lane / K;
+  const int rr = heavy_rows[hw];
+  const int s_lo = heavy_ptr[hw], s_hi = heavy_ptr[hw + 1];
+  float d2 = 0.f, acc[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) acc[h] = 0.f;
+  for (int sgm = s_lo + slot; sgm < s_hi; sgm += SLOTS) {
+    const float* pp = part + ((int64_t)sgm * K + head) * (H + 2);
+    d2 += pp[0];
+#pragma unroll
+    for (int h = 0; h < H; ++h) acc[h] += pp[2 + h];
+  }
+#pragma unroll
+  for (int off = K; off < 32; off <<= 1) {
+    d2 += __shfl_xor_sync(0xffffffffu, d2, off);
+#pragma unroll
+    for (int h = 0; h < H; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], off);
+  }
+  if (slot == 0) {
+    df2[(int64_t)rr * K + head] = d2;
+#pragma unroll
+    for (int h = 0; h < H; ++h) dS_agg[(int64_t)rr * D + head * H + h] = acc[h];
+  }
+}
+
 static DropCoef make_drop(const uint32_t* seed_ptr, float keep, int metapath, int64_t row0) {
   DropCoef dc;
   dc.seed_ptr = seed_ptr;
@@ -426,39 +573,50 @@ struct StreamCfg {
   static constexpr size_t bwd_smem = (size_t)kStreamWarps * BWD_STAGES * kBatch * (RS * 4 + 8);
 };
 
-template <int K, int H>
+struct HeavyRows {   // the cut rows of a virtual-row view (all null / 0: no splitting)
+  const int32_t* rows;
+  const int32_t* ptr;
+  int n;
+};
+
+template <int K, int H, bool SPLIT>
 static int launch_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
                               int64_t n_chunks, const float* T, float* R, const float* bias, int act,
                               float* out, int64_t out_stride, float* vsave, const float* colmean,
-                              DropCoef dc, cudaStream_t st) {
+                              DropCoef dc, SplitRows sp, HeavyRows hv, cudaStream_t st) {
   using C = StreamCfg<K, H>;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(attn_fwd_chunked_kernel<K, H, C::FWD_STAGES>,
+    cudaFuncSetAttribute(attn_fwd_chunked_kernel<K, H, C::FWD_STAGES, SPLIT>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::fwd_smem);
     attr = true;
   }
   unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
-  attn_fwd_chunked_kernel<K, H, C::FWD_STAGES><<<grid, kStreamWarps * 32, C::fwd_smem, st>>>(
-      indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, dc);
+  attn_fwd_chunked_kernel<K, H, C::FWD_STAGES, SPLIT><<<grid, kStreamWarps * 32, C::fwd_smem, st>>>(
+      indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, dc, sp);
+  if (SPLIT && hv.n > 0)
+    attn_fwd_merge_kernel<K, H><<<(unsigned)ceil_div64(hv.n, 4), 128, 0, st>>>(hv.rows, hv.ptr, hv.n, sp.part, R, bias, act,
+                                                                            out, out_stride, vsave);
   return check_launch("han_attn_fwd_chunked");
 }
 
-template <int K, int H>
+template <int K, int H, bool SPLIT>
 static int launch_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
                                   const int32_t* chunk_rows, int64_t n_chunks, const float* Tsrc,
                                   const float* R, float* dS_agg, float* df2, float* dl_edge, DropCoef dc,
-                                  cudaStream_t st) {
+                                  SplitRows sp, HeavyRows hv, cudaStream_t st) {
   using C = StreamCfg<K, H>;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES>,
+    cudaFuncSetAttribute(attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bwd_smem);
     attr = true;
   }
   unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
-  attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES><<<grid, kStreamWarps * 32, C::bwd_smem, st>>>(
-      t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, dc);
+  attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT><<<grid, kStreamWarps * 32, C::bwd_smem, st>>>(
+      t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, dc, sp);
+  if (SPLIT && hv.n > 0)
+    attn_bwd_src_merge_kernel<K, H><<<(unsigned)ceil_div64(hv.n, 4), 128, 0, st>>>(hv.rows, hv.ptr, hv.n, sp.part, dS_agg, df2);
   return check_launch("han_attn_bwd_src_chunked");
 }
 
@@ -507,7 +665,7 @@ int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const in
               ((uintptr_t)bias % 16 == 0), "16-byte alignment");
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_fwd_chunked<k, h>(indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, dc, as_stream(stream));
+    return launch_fwd_chunked<k, h, false>(indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, dc, SplitRows{nullptr, nullptr}, HeavyRows{nullptr, nullptr, 0}, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
@@ -525,7 +683,55 @@ int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, 
   HAN_REQUIRE(((uintptr_t)R % 16 == 0) && ((uintptr_t)Tsrc % 16 == 0) && ((uintptr_t)dS_agg % 16 == 0), "16-byte alignment");
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_bwd_src_chunked<k, h>(t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, dc, as_stream(stream));
+    return launch_bwd_src_chunked<k, h, false>(t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, dc, SplitRows{nullptr, nullptr}, HeavyRows{nullptr, nullptr, 0}, as_stream(stream));
+  HAN_FOR_SHAPES(X)
+#undef X
+  return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
+}
+
+int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, const int32_t* chunk_rows,
+                               int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
+                               int K, int H, int act, float* out, int64_t out_stride, float* vsave,
+                               const float* colmean, const uint32_t* seed_ptr, float coef_keep, int metapath,
+                               int64_t row0, const int32_t* vmap, float* part, const int32_t* heavy_rows,
+                               const int32_t* heavy_ptr, int n_heavy, han_stream_t stream) {
+  HAN_REQUIRE(indptr_v && chunk_rows && T && R && bias && out && vsave, "null pointer");
+  HAN_REQUIRE(vmap && part && heavy_rows && heavy_ptr && n_heavy > 0, "split view: vmap, part, heavy rows");
+  HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
+  const DropCoef dc = make_drop(seed_ptr, coef_keep, metapath, row0);
+  HAN_REQUIRE(n_dst > 0 && n_chunks > 0, "sizes");
+  HAN_REQUIRE(act == HAN_ACT_ELU || act == HAN_ACT_IDENTITY, "activation");
+  HAN_REQUIRE(out_stride >= (int64_t)K * H && out_stride % 4 == 0, "out_stride");
+  HAN_REQUIRE(((uintptr_t)T % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)vsave % 16 == 0) &&
+              ((uintptr_t)bias % 16 == 0) && ((uintptr_t)vmap % 8 == 0), "alignment");
+  const SplitRows sp{reinterpret_cast<const int2*>(vmap), part};
+  const HeavyRows hv{heavy_rows, heavy_ptr, n_heavy};
+#define X(k, h)         \
+  if (K == k && H == h) \
+    return launch_fwd_chunked<k, h, true>(indptr_v, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, dc, sp, hv, as_stream(stream));
+  HAN_FOR_SHAPES(X)
+#undef X
+  return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
+}
+
+int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_indices, const int32_t* perm,
+                                   const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
+                                   const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
+                                   float* dl_edge, const uint32_t* seed_ptr, float coef_keep, int metapath,
+                                   int64_t row0, const int32_t* vmap, float* part, const int32_t* heavy_rows,
+                                   const int32_t* heavy_ptr, int n_heavy, han_stream_t stream) {
+  HAN_REQUIRE(t_indptr_v && chunk_rows && Tsrc && R && dS_agg && df2 && dl_edge, "null pointer");
+  HAN_REQUIRE(vmap && part && heavy_rows && heavy_ptr && n_heavy > 0, "split view: vmap, part, heavy rows");
+  HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
+  const DropCoef dc = make_drop(seed_ptr, coef_keep, metapath, row0);
+  HAN_REQUIRE(n_src > 0 && n_chunks > 0, "sizes");
+  HAN_REQUIRE(((uintptr_t)R % 16 == 0) && ((uintptr_t)Tsrc % 16 == 0) && ((uintptr_t)dS_agg % 16 == 0) &&
+              ((uintptr_t)vmap % 8 == 0), "alignment");
+  const SplitRows sp{reinterpret_cast<const int2*>(vmap), part};
+  const HeavyRows hv{heavy_rows, heavy_ptr, n_heavy};
+#define X(k, h)         \
+  if (K == k && H == h) \
+    return launch_bwd_src_chunked<k, h, true>(t_indptr_v, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, dc, sp, hv, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");

@@ -5,6 +5,8 @@ Built on the device by the K-0 kernels; bit-exact against ``np.nonzero(bias == 0
 """
 from __future__ import annotations
 
+import os
+from dataclasses import dataclass
 from typing import Optional
 
 import numpy as np
@@ -28,6 +30,24 @@ def _as_device_tensor(a, device, dtype=None) -> torch.Tensor:
     if dtype is not None and a.dtype != dtype:
         a = a.to(dtype)
     return a.to(device, non_blocking=True).contiguous()
+
+
+# rows longer than this are cut into segments for the edge-stream kernels (MetaPathGraph.split_view)
+SPLIT_ROW_EDGES = int(os.environ.get("HAN_SPLIT_ROW_EDGES", "4096"))
+
+
+@dataclass
+class SplitView:
+    indptr_v: torch.Tensor      # int64 [n_v+1]: the CSR offsets with the cut points inserted
+    vptr: torch.Tensor          # int64 [n_rows+1]: virtual rows of each real row
+    vmap: torch.Tensor          # int32 [n_v][2]: (real row, partial slot or -1)
+    heavy_rows: torch.Tensor    # int32 [n_heavy]
+    heavy_ptr: torch.Tensor     # int32 [n_heavy+1]: partial slots of each cut row
+    chunk_rows: torch.Tensor    # int32 [n_chunks+1] over the virtual rows
+    n_chunks: int
+    n_v: int
+    n_heavy: int
+    n_slots: int
 
 
 class MetaPathGraph:
@@ -180,6 +200,42 @@ class MetaPathGraph:
                 call("han_csr_chunk_rows", ptr(self.indptr), self.n_rows, self.nnz, ptr(cr), stream_ptr())
             self._chunks = (cr, n_chunks)
         return self._chunks
+
+    def split_view(self):
+        """Virtual-row view for graphs with heavy rows (power-law meta-paths): every row with more than
+        ``SPLIT_ROW_EDGES`` edges is cut into segments of at most that many, so that no single warp of the
+        edge-stream kernels is left with a 10^5-edge row.  Returns None when no row is that long (the
+        common case: nothing changes), else a ``SplitView``.  Built once per graph, cached; the one
+        device->host read (the maximum degree) happens here, outside any captured step."""
+        if getattr(self, "_split", False) is False:
+            self._split = None
+            S = SPLIT_ROW_EDGES
+            deg = self.indptr[1:] - self.indptr[:-1]
+            if self.nnz > 0 and int(deg.max().item()) > S:
+                dev, n = self.device, self.n_rows
+                with torch.cuda.device(dev):
+                    nseg = torch.clamp((deg + (S - 1)) // S, min=1)
+                    vptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+                    vptr[1:] = torch.cumsum(nseg, 0)
+                    vrow = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), nseg)
+                    n_v = int(vrow.numel())
+                    seg = torch.arange(n_v, device=dev, dtype=torch.int64) - vptr[vrow]
+                    indptr_v = torch.empty(n_v + 1, dtype=torch.int64, device=dev)
+                    indptr_v[:-1] = self.indptr[vrow] + seg * S
+                    indptr_v[-1] = self.nnz
+                    heavy = nseg > 1
+                    hv_v = heavy[vrow]
+                    slot = torch.cumsum(hv_v.to(torch.int64), 0) - 1
+                    vmap = torch.stack([vrow, torch.where(hv_v, slot, torch.full_like(slot, -1))], 1).to(torch.int32).contiguous()
+                    heavy_rows = torch.nonzero(heavy).reshape(-1).to(torch.int32)
+                    heavy_ptr = torch.zeros(heavy_rows.numel() + 1, dtype=torch.int32, device=dev)
+                    heavy_ptr[1:] = torch.cumsum(nseg[heavy], 0).to(torch.int32)
+                    n_chunks = int(query("han_csr_num_chunks", self.nnz))
+                    cr = torch.empty(n_chunks + 1, dtype=torch.int32, device=dev)
+                    call("han_csr_chunk_rows", ptr(indptr_v), n_v, self.nnz, ptr(cr), stream_ptr())
+                self._split = SplitView(indptr_v, vptr, vmap, heavy_rows, heavy_ptr, cr, n_chunks, n_v,
+                                        int(heavy_rows.numel()), int(hv_v.sum().item()))
+        return self._split
 
     def row_slice(self, lo: int, hi: int) -> "MetaPathGraph":
         """Destination-row shard [lo, hi) (column ids stay global)."""

@@ -147,7 +147,16 @@ class NodeAttentionFn(torch.autograd.Function):
                 if graph.has_empty_rows():
                     # dense-path semantics of an all -1e9 row: uniform 1/N over all nodes
                     colmean = T_src[g][:, :D].mean(0).contiguous()
-                if CHUNKED:
+                sv = graph.split_view() if CHUNKED else None
+                if sv is not None:
+                    # heavy rows are cut into segments; a merge kernel combines their partial softmax states
+                    part = _empty((sv.n_slots, K, H + 2), dev)
+                    call("han_attn_fwd_chunked_split", ptr(sv.indptr_v), ptr(graph.indices), ptr(sv.chunk_rows),
+                         sv.n_chunks, n, ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]),
+                         G * D, ptr(V[g]), ptr(colmean), ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g),
+                         row0, ptr(sv.vmap), ptr(part), ptr(sv.heavy_rows), ptr(sv.heavy_ptr), sv.n_heavy,
+                         stream_ptr())
+                elif CHUNKED:
                     cr, n_chunks = graph.chunks()
                     call("han_attn_fwd_chunked", ptr(graph.indptr), ptr(graph.indices), ptr(cr), n_chunks, n,
                          ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D,
@@ -216,7 +225,14 @@ class NodeAttentionFn(torch.autograd.Function):
                     gt = graph.transpose()
                     dl = _empty((max(graph.nnz, 1), K), dev)
                     df1 = _empty((n, K), dev)
-                    if CHUNKED:
+                    tv = gt.split_view() if CHUNKED else None
+                    if tv is not None:
+                        part = _empty((tv.n_slots, K, H + 2), dev)
+                        call("han_attn_bwd_src_chunked_split", ptr(tv.indptr_v), ptr(gt.indices), ptr(gt.perm),
+                             ptr(tv.chunk_rows), tv.n_chunks, n, ptr(T[g]), ptr(R[g]), K, H, ptr(dS[g]), ptr(df2),
+                             ptr(dl), ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), 0, ptr(tv.vmap),
+                             ptr(part), ptr(tv.heavy_rows), ptr(tv.heavy_ptr), tv.n_heavy, stream_ptr())
+                    elif CHUNKED:
                         cr, n_chunks = gt.chunks()
                         call("han_attn_bwd_src_chunked", ptr(gt.indptr), ptr(gt.indices), ptr(gt.perm), ptr(cr),
                              n_chunks, n, ptr(T[g]), ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(dl),
@@ -224,7 +240,14 @@ class NodeAttentionFn(torch.autograd.Function):
                     else:
                         call("han_attn_bwd_src", ptr(gt.indptr), ptr(gt.indices), ptr(gt.perm), n, ptr(T[g]),
                              ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(dl), stream_ptr())
-                    call("han_attn_bwd_dst", ptr(graph.indptr), n, graph.nnz, ptr(dl), K, ptr(df1), stream_ptr())
+                    sv = graph.split_view() if CHUNKED else None
+                    if sv is not None:
+                        # df1 of a cut row: segment sums first, then the sum of its segments (same kernel)
+                        df1_v = _empty((sv.n_v, K), dev)
+                        call("han_attn_bwd_dst", ptr(sv.indptr_v), sv.n_v, graph.nnz, ptr(dl), K, ptr(df1_v), stream_ptr())
+                        call("han_attn_bwd_dst", ptr(sv.vptr), n, sv.n_v, ptr(df1_v), K, ptr(df1), stream_ptr())
+                    else:
+                        call("han_attn_bwd_dst", ptr(graph.indptr), n, graph.nnz, ptr(dl), K, ptr(df1), stream_ptr())
                     del dl
                 else:
                     # sharded: df1 comes back from a reduce-scatter that runs on the side stream while the

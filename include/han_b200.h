@@ -177,6 +177,27 @@ int han_attn_bwd_src(const int64_t* t_indptr, const int32_t* t_indices, const in
                      int64_t n_src, const float* Tsrc, const float* R, int K, int H, float* dS_agg,
                      float* df2, float* dl_edge, han_stream_t stream);
 
+/* Heavy rows (power-law meta-paths).  The same two passes over a VIRTUAL-row CSR: indptr_v [n_v+1] is the
+ * CSR's offsets with cut points inserted so that no row exceeds a fixed number of edges (column array and
+ * perm unchanged; chunk_rows built over indptr_v).  vmap [n_v][2] = (real row, partial slot or -1 for a row
+ * that was not cut); part [n_slots][K][H+2] receives the per-segment partial state (forward: running max,
+ * normaliser, un-normalised aggregate; backward: df2 and dS sums); heavy_rows [n_heavy] / heavy_ptr
+ * [n_heavy+1] list the cut rows and their slot ranges for the merge kernel (one warp per cut row), which is
+ * launched right after the stream kernel.  Results are identical to the un-split entry points up to the
+ * order of floating-point additions inside a cut row. */
+int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, const int32_t* chunk_rows,
+                               int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
+                               int K, int H, int act, float* out, int64_t out_stride, float* vsave,
+                               const float* colmean, const uint32_t* seed_ptr, float coef_keep, int metapath,
+                               int64_t row0, const int32_t* vmap, float* part, const int32_t* heavy_rows,
+                               const int32_t* heavy_ptr, int n_heavy, han_stream_t stream);
+int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_indices, const int32_t* perm,
+                                   const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
+                                   const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
+                                   float* dl_edge, const uint32_t* seed_ptr, float coef_keep, int metapath,
+                                   int64_t row0, const int32_t* vmap, float* part, const int32_t* heavy_rows,
+                                   const int32_t* heavy_ptr, int n_heavy, han_stream_t stream);
+
 /* by-destination pass: df1_i = sum_j dl_edge[e] over CSR row i -> df1 [n_dst][K]. */
 int han_attn_bwd_dst(const int64_t* indptr, int64_t n_dst, int64_t nnz, const float* dl_edge, int K, float* df1,
                      han_stream_t stream);

@@ -7,7 +7,7 @@ import torch
 
 from han_b200 import synth
 from oracle import han_oracle as O
-from tests.util import assert_close
+from tests.util import assert_close, compare_step, oracle_step, product_step
 
 pytestmark = pytest.mark.gpu
 
@@ -241,3 +241,39 @@ def test_attn_head_reference_signature():
     # the reference's training-time call shape (in_drop = coef_drop = 0.6) runs and differs from eval
     dropped = hb.layers.attn_head(seq, H, torch.from_numpy(bias.astype(np.float32)), hb.layers.elu, 0.6, 0.6, params=hp)
     assert dropped.shape == out.shape and torch.isfinite(dropped).all() and not torch.equal(dropped, out)
+
+
+@pytest.mark.parametrize("split", [16, 50])
+def test_heavy_rows_cut_into_segments_match_oracle(split, monkeypatch):
+    """Power-law meta-paths (BASELINE.json configs[4]): hub rows AND hub columns far longer than the
+    split length are processed as several virtual rows + a merge (MetaPathGraph.split_view,
+    han_attn_*_chunked_split); the whole step must still match the dense fp64 oracle, and equal the
+    un-split kernels up to summation order."""
+    import han_b200 as hb
+    from han_b200 import graph as hg
+    cfg = synth.tiny(seed=141, n=260, f=20, p=2, deg=5.0)
+    rng = np.random.default_rng(142)
+    for m in cfg.masks:                       # hubs: 3 nodes linked to (almost) everyone, both directions
+        hubs = rng.choice(cfg.N, size=3, replace=False)
+        for h in hubs:
+            sel = rng.random(cfg.N) < 0.9
+            m[h, sel] = True
+            m[sel, h] = True
+        m[rng.integers(0, cfg.N), :] = True   # one row that is exactly full
+    params = O.init_params(np.random.default_rng(143), [cfg.F] * cfg.P, cfg.C)
+    out_o, grads_o = oracle_step(cfg, params)
+    out_u, grads_u, _ = product_step(cfg, params)                  # default split length: nothing is cut
+    monkeypatch.setattr(hg, "SPLIT_ROW_EDGES", split)
+    graphs = [hb.process.adj_to_bias(a, [cfg.N]) for a in cfg.adjs()]
+    sv, tv = graphs[0].split_view(), graphs[0].transpose().split_view()
+    assert sv is not None and tv is not None and sv.n_heavy >= 4 and tv.n_heavy >= 3
+    indptr = graphs[0].indptr.cpu().numpy()
+    iv = sv.indptr_v.cpu().numpy()
+    assert set(indptr) <= set(iv) and np.diff(iv).max() <= split and iv[-1] == graphs[0].nnz
+    vm = sv.vmap.cpu().numpy()
+    assert (np.bincount(vm[:, 0], minlength=cfg.N) == np.maximum(1, -(-np.diff(indptr) // split))).all()
+    assert sv.n_slots == int((vm[:, 1] >= 0).sum()) == int(sv.heavy_ptr[-1])
+    out_p, grads_p, _ = product_step(cfg, params, graphs=graphs)
+    compare_step(out_o, grads_o, out_p, grads_p)
+    assert torch.allclose(out_p["logits"], out_u["logits"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(grads_p["W"][0], grads_u["W"][0], rtol=1e-4, atol=1e-7)
