@@ -160,9 +160,9 @@ def algorithmic_bytes(name, wl):
     E = sum(g.nnz for g in wl["graphs"])
     n = wl["hi"] - wl["lo"]
     P = wl["P"]
-    if name in ("han_attn_fwd", "han_attn_fwd_chunked"):
+    if name in ("han_attn_fwd", "han_attn_fwd_chunked", "han_attn_fwd_chunked_split"):
         return (4 + 4 * TS) * E + (8 + 4 * K + 8 * D + 4 * K) * n * P
-    if name in ("han_attn_bwd_src", "han_attn_bwd_src_chunked"):
+    if name in ("han_attn_bwd_src", "han_attn_bwd_src_chunked", "han_attn_bwd_src_chunked_split"):
         return (8 + 4 * RS + 4 * K) * E + (8 + 4 * TS + 4 * D + 4 * K) * n * P
     return None
 
@@ -377,17 +377,47 @@ def run_e2e(args, wl, hp, train, dist, dev, step):
         hG = [(g.indptr.cpu().pin_memory(), g.indices.cpu().pin_memory()) for g in wl["graphs"]]
         h2d = hX.numel() * 4 + sum(a.numel() * 8 + b.numel() * 4 for a, b in hG)
 
+        copy_s, prep_s = torch.cuda.Stream(), torch.cuda.Stream()
+
         def one():
-            X = hX.to(dev, non_blocking=True).unsqueeze(0)
-            graphs = [hb.MetaPathGraph.from_csr(a, b, n_cols=wl["N"], device=dev, row_offset=wl["lo"]) for a, b in hG]
+            # staging pipeline: features first, then the graphs, all on a copy stream; each graph's by-source
+            # view is built on a third stream as soon as that graph has landed.  The kernels wait per graph
+            # (MetaPathGraph.ready), so meta-path g is attended while g+1 is still on PCIe.
+            main = torch.cuda.current_stream()
+            copy_s.wait_stream(main)
+            with torch.cuda.stream(copy_s):
+                X = hX.to(dev, non_blocking=True).unsqueeze(0)
+                x_ready = torch.cuda.Event()
+                x_ready.record(copy_s)
+            graphs = [hb.MetaPathGraph.from_csr(a, b, n_cols=wl["N"], device=dev, row_offset=wl["lo"], stream=copy_s)
+                      for a, b in hG]
             if dist:
+                main.wait_stream(copy_s)
                 dist._bwd = {}
                 dist.bind(graphs, wl["N"])
-            return step(X, graphs)
+            else:
+                for g in graphs:
+                    g.transpose(stream=prep_s)
+            main.wait_event(x_ready)
+            out = step(X, graphs)
+            X.record_stream(main)
+            return out
     one()                                   # warm-up (allocator, pinned staging)
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
+    # what the host link gives this process for a plain pinned copy (explains the e2e floor: h2d bytes / this)
+    probe_h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    probe_d = torch.empty_like(probe_h, device=dev)
+    probe_d.copy_(probe_h, non_blocking=True)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(4):
+        probe_d.copy_(probe_h, non_blocking=True)
+    e.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 4 * probe_h.numel() / (s.elapsed_time(e) * 1e-3) / 1e9
+    del probe_h, probe_d
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     s.record()
@@ -400,7 +430,8 @@ def run_e2e(args, wl, hp, train, dist, dev, step):
     if dist:
         ms = dist.all_reduce_max(torch.tensor([ms], dtype=torch.float64, device=dev)).item()
     return {"value": wl["edges"] / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": 4, "ms_per_step": ms, "steps": n_e2e, "loss": host_loss}
+            "d2h_bytes_per_step": 4, "ms_per_step": ms, "steps": n_e2e, "loss": host_loss,
+            "h2d_link_gbs": round(h2d_gbs, 1), "h2d_floor_ms": round(h2d / (h2d_gbs * 1e9) * 1e3, 1)}
 
 
 # --------------------------------------------------------------------------------------------------

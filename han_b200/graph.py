@@ -70,6 +70,14 @@ class MetaPathGraph:
         self._t: Optional["MetaPathGraph"] = None
         self.perm: Optional[torch.Tensor] = None  # set on the transposed view
         self._empty_rows: Optional[bool] = None
+        # set when the arrays were produced on another stream (host->device staging, transposition on a
+        # side stream): consumers call wait_ready() before their first kernel that reads this graph
+        self.ready: Optional[torch.cuda.Event] = None
+
+    def wait_ready(self) -> "MetaPathGraph":
+        if self.ready is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.ready)
+        return self
 
     # the reference hands around a (1,N,N) array; keep that visible for call-site compatibility
     @property
@@ -150,10 +158,25 @@ class MetaPathGraph:
 
     @staticmethod
     def from_csr(indptr, indices, n_cols: Optional[int] = None, device=None, sort: bool = False,
-                 row_offset: int = 0) -> "MetaPathGraph":
+                 row_offset: int = 0, stream: Optional[torch.cuda.Stream] = None) -> "MetaPathGraph":
         """From host or device CSR arrays.  ``sort=True`` sorts columns within rows on the device
-        and rejects duplicate edges."""
+        and rejects duplicate edges.  ``stream``: stage the (pinned) host arrays on that stream instead of
+        the current one -- the handle carries a ``ready`` event and the kernels wait for it, so the copy
+        overlaps whatever the compute stream is doing."""
         device = _dev(device)
+        if stream is not None:
+            if sort:
+                raise ValueError("sort=True needs the arrays on the current stream")
+            nnz_host = int(indices.numel() if isinstance(indices, torch.Tensor) else len(indices))
+            with torch.cuda.stream(stream):
+                indptr = _as_device_tensor(indptr, device, torch.int64)
+                indices = _as_device_tensor(indices, device, torch.int32)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+            g = MetaPathGraph(indptr, indices, indptr.numel() - 1, indptr.numel() - 1 if n_cols is None else n_cols,
+                              nnz_host, row_offset=row_offset)
+            g.ready = ev
+            return g
         indptr = _as_device_tensor(indptr, device, torch.int64)
         indices = _as_device_tensor(indices, device, torch.int32)
         n_rows = indptr.numel() - 1
@@ -171,11 +194,20 @@ class MetaPathGraph:
         return g
 
     # ---- derived structures -----------------------------------------------------------------
-    def transpose(self) -> "MetaPathGraph":
+    def transpose(self, stream: Optional[torch.cuda.Stream] = None) -> "MetaPathGraph":
         """By-source view: row j lists the destinations i of edges (i,j), ascending, with
-        ``perm`` = position of that edge in this CSR.  Built once, cached."""
+        ``perm`` = position of that edge in this CSR.  Built once, cached.  ``stream``: build it on that
+        stream (after this graph is ready there); the view then carries its own ``ready`` event."""
+        if self._t is None and stream is not None:
+            with torch.cuda.stream(stream):
+                self.wait_ready()
+                t = self.transpose()
+                t.ready = torch.cuda.Event()
+                t.ready.record(stream)
+            return t
         if self._t is None:
             device = self.device
+            self.wait_ready()
             with torch.cuda.device(device):
                 t_indptr = torch.empty(self.n_cols + 1, dtype=torch.int64, device=device)
                 t_indices = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=device)[:self.nnz]
@@ -194,6 +226,7 @@ class MetaPathGraph:
         """(chunk_rows int32[n_chunks+1], n_chunks): whole-row work items of ~2048 edges for the
         chunked edge-stream kernels.  Built once per graph, cached."""
         if getattr(self, "_chunks", None) is None:
+            self.wait_ready()
             n_chunks = int(query("han_csr_num_chunks", self.nnz))
             with torch.cuda.device(self.device):
                 cr = torch.empty(n_chunks + 1, dtype=torch.int32, device=self.device)
@@ -209,6 +242,7 @@ class MetaPathGraph:
         device->host read (the maximum degree) happens here, outside any captured step."""
         if getattr(self, "_split", False) is False:
             self._split = None
+            self.wait_ready()
             S = SPLIT_ROW_EDGES
             deg = self.indptr[1:] - self.indptr[:-1]
             if self.nnz > 0 and int(deg.max().item()) > S:

@@ -143,6 +143,7 @@ class NodeAttentionFn(torch.autograd.Function):
             plan.coefs = []
             for g, graph in enumerate(plan.graphs):
                 assert graph.n_rows == n, "graph rows must match the local rows of X"
+                graph.wait_ready()                     # staged on another stream (host-fed graphs)
                 colmean = None
                 if graph.has_empty_rows():
                     # dense-path semantics of an all -1e9 row: uniform 1/N over all nodes
@@ -222,7 +223,7 @@ class NodeAttentionFn(torch.autograd.Function):
             pending = []
             for g, graph in enumerate(plan.graphs):
                 if dist is None:
-                    gt = graph.transpose()
+                    gt = graph.transpose().wait_ready()
                     dl = _empty((max(graph.nnz, 1), K), dev)
                     df1 = _empty((n, K), dev)
                     tv = gt.split_view() if CHUNKED else None
