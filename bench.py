@@ -380,26 +380,42 @@ def run_e2e(args, wl, hp, train, dist, dev, step):
         copy_s, prep_s = torch.cuda.Stream(), torch.cuda.Stream()
 
         def one():
-            # staging pipeline: features first, then the graphs, all on a copy stream; each graph's by-source
-            # view is built on a third stream as soon as that graph has landed.  The kernels wait per graph
-            # (MetaPathGraph.ready), so meta-path g is attended while g+1 is still on PCIe.
+            # staging pipeline on a copy stream: the graphs first, the features last -- each graph's by-source
+            # view is built on a third stream as soon as that graph has landed, i.e. while the (larger)
+            # feature matrix is still on PCIe and the SMs would otherwise idle.  The kernels wait per
+            # graph / per view (MetaPathGraph.ready).
             main = torch.cuda.current_stream()
             copy_s.wait_stream(main)
+            marks = one.marks = []
+            if os.environ.get("HAN_E2E_TRACE"):
+                def mark(label, stream):
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record(stream)
+                    marks.append((label, ev))
+            else:
+                mark = lambda label, stream: None
+            mark("start", main)
+            graphs = []
+            for i, (a, b) in enumerate(hG):
+                graphs.append(hb.MetaPathGraph.from_csr(a, b, n_cols=wl["N"], device=dev, row_offset=wl["lo"], stream=copy_s))
+                mark(f"graph {i} on device", copy_s)
             with torch.cuda.stream(copy_s):
                 X = hX.to(dev, non_blocking=True).unsqueeze(0)
                 x_ready = torch.cuda.Event()
                 x_ready.record(copy_s)
-            graphs = [hb.MetaPathGraph.from_csr(a, b, n_cols=wl["N"], device=dev, row_offset=wl["lo"], stream=copy_s)
-                      for a, b in hG]
+                mark("X on device", copy_s)
             if dist:
                 main.wait_stream(copy_s)
                 dist._bwd = {}
                 dist.bind(graphs, wl["N"])
+                mark("bind done", main)
             else:
-                for g in graphs:
+                for i, g in enumerate(graphs):
                     g.transpose(stream=prep_s)
+                    mark(f"by-source view {i} built", prep_s)
             main.wait_event(x_ready)
             out = step(X, graphs)
+            mark("step done", main)
             X.record_stream(main)
             return out
     one()                                   # warm-up (allocator, pinned staging)
@@ -421,12 +437,22 @@ def run_e2e(args, wl, hp, train, dist, dev, step):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     s.record()
+    walls = []
     for _ in range(n_e2e):
+        t1 = time.perf_counter()
         loss = one()
+        t2 = time.perf_counter()
         host_loss = float(loss.detach())    # D2H read of the step's result (synchronises the step)
+        walls.append((round((t2 - t1) * 1e3, 1), round((time.perf_counter() - t2) * 1e3, 1)))
     e.record()
     torch.cuda.synchronize()
     ms = max(s.elapsed_time(e), (time.perf_counter() - t0) * 1e3) / n_e2e
+    if os.environ.get("HAN_E2E_TRACE"):
+        sys.stderr.write(f"e2e per step (host issue ms, wait-for-loss ms): {walls}; events {s.elapsed_time(e):.1f} ms\n")
+    if getattr(one, "marks", None):
+        t_0 = one.marks[0][1]
+        sys.stderr.write("e2e timeline of the last step (ms): " +
+                         ", ".join(f"{lab} {t_0.elapsed_time(ev):.1f}" for lab, ev in one.marks[1:]) + "\n")
     if dist:
         ms = dist.all_reduce_max(torch.tensor([ms], dtype=torch.float64, device=dev)).item()
     return {"value": wl["edges"] / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
