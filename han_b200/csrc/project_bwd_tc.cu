@@ -18,7 +18,8 @@ constexpr int BT_BM = 128;      // features per CTA (MMA M)
 constexpr int BT_BK = 32;       // rows of X / dS per stage (MMA K, one 128-byte swizzle span)
 constexpr int BT_STAGES = 2;
 constexpr int BT_MAXN = 256;
-constexpr int BT_THREADS = 160; // warp 0: MMA issuer + TMEM; warps 1-4: producers, then epilogue
+constexpr int BT_PRODUCERS = 256;                 // warps 1-8: every load of a stage is in flight before the first store
+constexpr int BT_THREADS = 32 + BT_PRODUCERS;     // warp 0: MMA issuer + TMEM; warps 1-4 also run the epilogue
 constexpr uint32_t BT_A_BYTES = BT_BM * BT_BK * 4;
 constexpr uint32_t BT_B_BYTES = BT_MAXN * BT_BK * 4;
 constexpr uint32_t BT_STAGE_BYTES = 2 * BT_A_BYTES + 2 * BT_B_BYTES;
@@ -116,7 +117,7 @@ project_bwd_tc_kernel(const float* __restrict__ X, int64_t n, int64_t F, int64_t
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < BT_STAGES; ++s) {
-      bt_mbar_init(full0 + 8 * s, 128);
+      bt_mbar_init(full0 + 8 * s, BT_PRODUCERS);
       bt_mbar_init(empty0 + 8 * s, 1);
     }
     bt_mbar_init(accum, 1);
@@ -157,49 +158,52 @@ project_bwd_tc_kernel(const float* __restrict__ X, int64_t n, int64_t F, int64_t
       bt_umma_commit(accum);
     }
   } else {
-    // ===== producers (warps 1-4), then epilogue =====
-    const int t = threadIdx.x - 32;   // 0..127
+    // ===== producers (warps 1-8), then epilogue (warps 1-4) =====
+    // Per 32-row stage a thread owns half a feature column of X (16 values: feature fa, rows 16*half..) and one
+    // column of dS (32 values); all 48 loads are issued before the first transposing store, so a CTA keeps a
+    // whole 48 KB stage in flight instead of 4-8 loads per thread.
+    const int t = threadIdx.x - 32;   // 0..255
+    const int fa = t & 127, half = t >> 7;
+    const int64_t f_a = f0 + fa;
+    const bool fok = f_a < F;
+    const bool cok = t < NC;
+    const float* bsrc = dS + ((int64_t)(t >> 6) * n) * D + (t & 63);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % BT_STAGES;
       const uint32_t ph = (kb / BT_STAGES) & 1;
+      const int64_t n0 = r_begin + (int64_t)kb * BT_BK;
+      float va[16], vb[32];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int64_t r = n0 + 16 * half + j;
+        va[j] = (fok && r < r_end) ? __ldg(X + r * ldx + f_a) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int64_t r = n0 + j;
+        vb[j] = (cok && r < r_end) ? __ldg(bsrc + r * D) : 0.f;
+      }
       bt_mbar_wait(empty0 + 8 * s, ph ^ 1);
       uint8_t* a_hi = gen + s * BT_STAGE_BYTES;
       uint8_t* a_lo = a_hi + BT_A_BYTES;
       uint8_t* b_hi = a_hi + 2 * BT_A_BYTES;
       uint8_t* b_lo = b_hi + BT_B_BYTES;
-      const int64_t n0 = r_begin + (int64_t)kb * BT_BK;
-      // A = X^T tile: row m = feature f0 + t, K = 32 node rows
-      {
-        const int64_t f = f0 + t;
-        const bool fok = f < F;
+      // A = X^T tile: row m = feature, K = 32 node rows (this thread: K chunks 4*half .. 4*half+3)
 #pragma unroll
-        for (int kc = 0; kc < 8; ++kc) {
-          float v[4];
+      for (int kc = 0; kc < 4; ++kc)
+        split_store(a_hi, a_lo, sw128_chunk(fa, 4 * half + kc), va[4 * kc], va[4 * kc + 1], va[4 * kc + 2],
+                    va[4 * kc + 3], MODE == 1);
+      // B = dS^T tile: row = output column c (meta-path c/64, feature c%64), K = the same 32 node rows
+      if (cok) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int64_t r = n0 + 4 * kc + j;
-            v[j] = (fok && r < r_end) ? __ldg(X + r * ldx + f) : 0.f;
-          }
-          split_store(a_hi, a_lo, sw128_chunk(t, kc), v[0], v[1], v[2], v[3], MODE == 1);
-        }
-      }
-      // B = dS^T tile: row nn = output column c (meta-path c/64, feature c%64), K = the same 32 node rows
-      for (int c = t; c < NC; c += 128) {
-        const float* src = dS + ((int64_t)(c >> 6) * n) * D + (c & 63);
-#pragma unroll
-        for (int kc = 0; kc < 8; ++kc) {
-          float v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int64_t r = n0 + 4 * kc + j;
-            v[j] = (r < r_end) ? __ldg(src + r * D) : 0.f;
-          }
-          split_store(b_hi, b_lo, sw128_chunk(c, kc), v[0], v[1], v[2], v[3], MODE != 3);
-        }
+        for (int kc = 0; kc < 8; ++kc)
+          split_store(b_hi, b_lo, sw128_chunk(t, kc), vb[4 * kc], vb[4 * kc + 1], vb[4 * kc + 2], vb[4 * kc + 3],
+                      MODE != 3);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core reads
       bt_mbar_arrive(full0 + 8 * s);
     }
+    if (warp > 4) goto done;   // warps 5-8 have no accumulator rows to drain
     // ---- epilogue: thread = accumulator row = feature ----
     const int q = warp & 3;
     const int64_t f = f0 + q * 32 + lane;
@@ -224,6 +228,7 @@ project_bwd_tc_kernel(const float* __restrict__ X, int64_t n, int64_t F, int64_t
       for (int c = 0; c < NC; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+done:
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {

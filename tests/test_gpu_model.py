@@ -334,3 +334,26 @@ def test_stacked_attention_layers_and_residual_match_oracle(residual):
     out_p, grads_p, _ = product_step(cfg, params, **kw)
     assert out_p["final_embed"].shape == (cfg.N, 16)
     compare_step(out_o, grads_o, out_p, grads_p)
+
+
+@pytest.mark.parametrize("name", ["dblp", "imdb"])
+def test_full_size_dblp_and_imdb_shaped_forward_parity(name):
+    """BASELINE.json configs[1] / configs[2] at FULL size (DBLP: 4057 authors, 3 meta-paths up to 41 % dense,
+    ~12 M edges; IMDB: 4780 movies, 2 sparse meta-paths): forward outputs and the loss of the whole model
+    against the dense fp64 oracle (24 / 16 heads of N x N logits).  Gradients at full size are covered for
+    the ACM shape above and at reduced scale for these shapes (golden fixtures)."""
+    cfg = synth.SMALL[name]()
+    rng = np.random.default_rng(7)
+    params = O.init_params(rng, [cfg.F] * cfg.P, cfg.C)
+    out_p, _, _ = product_step(cfg, params, project_mode=2)
+    X = torch.from_numpy(cfg.X).double().unsqueeze(0)
+    biases = [torch.from_numpy(O.adj_to_bias(a, [cfg.N], 1)) for a in cfg.adjs()]
+    labels = torch.from_numpy(cfg.labels).double()
+    mask = torch.from_numpy(cfg.train_mask.astype(np.float64))
+    with torch.no_grad():
+        total, ce, logits, fe, av = O.step_loss([X] * cfg.P, biases, labels, mask, O.params_to(params, torch.float64),
+                                                cfg.C, [8], [8, 1])
+    assert_close(out_p["logits"], logits, "logits")
+    assert_close(out_p["final_embed"], fe, "final_embed")
+    assert_close(out_p["att_val"], av, "att_val")
+    assert_close(out_p["total"], total, "total")
