@@ -52,6 +52,7 @@ _SIGNATURES = {
     "han_attn_bwd_src_chunked": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P, FL, I, I64, P]),
     "han_attn_fwd_chunked_split": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, FL, I, I64,
                                            P, P, P, P, I, P]),
+    "han_attn_fwd_merge": (c_int, [P, P, I64, P, P, P, I, I, I, P, I64, P, P]),
     "han_attn_bwd_src_chunked_split": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P, FL, I, I64,
                                                P, P, P, P, I, P]),
     "han_project_fwd_drop": (c_int, [P, I64, I64, I64, P, I64, I, I, I, P, P, P, P, P, P, P, P, FL, I, I64, P]),
@@ -120,7 +121,7 @@ KERNELS_PER_CALL = {
     "han_csr_chunk_rows": 1, "han_attn_fwd_chunked": 1, "han_attn_bwd_src_chunked": 1, "han_attn_bwd_dst": 1,
     "han_attn_bwd_finish": 1, "han_reduce_partials": 1, "han_semantic_fwd": 1, "han_semantic_combine": 1,
     "han_semantic_bwd": 2, "han_adam_l2_step": 1, "han_project_dx": 1,
-    "han_attn_fwd_chunked_split": 2, "han_attn_bwd_src_chunked_split": 2,
+    "han_attn_fwd_chunked_split": 2, "han_attn_bwd_src_chunked_split": 2, "han_attn_fwd_merge": 1,
 }
 
 

@@ -696,7 +696,7 @@ int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, 
                                int64_t row0, const int32_t* vmap, float* part, const int32_t* heavy_rows,
                                const int32_t* heavy_ptr, int n_heavy, han_stream_t stream) {
   HAN_REQUIRE(indptr_v && chunk_rows && T && R && bias && out && vsave, "null pointer");
-  HAN_REQUIRE(vmap && part && heavy_rows && heavy_ptr && n_heavy > 0, "split view: vmap, part, heavy rows");
+  HAN_REQUIRE(vmap && part && n_heavy >= 0 && (n_heavy == 0 || (heavy_rows && heavy_ptr)), "split view: vmap, part, heavy rows");
   HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
   const DropCoef dc = make_drop(seed_ptr, coef_keep, metapath, row0);
   HAN_REQUIRE(n_dst > 0 && n_chunks > 0, "sizes");
@@ -721,7 +721,7 @@ int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_i
                                    int64_t row0, const int32_t* vmap, float* part, const int32_t* heavy_rows,
                                    const int32_t* heavy_ptr, int n_heavy, han_stream_t stream) {
   HAN_REQUIRE(t_indptr_v && chunk_rows && Tsrc && R && dS_agg && df2 && dl_edge, "null pointer");
-  HAN_REQUIRE(vmap && part && heavy_rows && heavy_ptr && n_heavy > 0, "split view: vmap, part, heavy rows");
+  HAN_REQUIRE(vmap && part && n_heavy >= 0 && (n_heavy == 0 || (heavy_rows && heavy_ptr)), "split view: vmap, part, heavy rows");
   HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
   const DropCoef dc = make_drop(seed_ptr, coef_keep, metapath, row0);
   HAN_REQUIRE(n_src > 0 && n_chunks > 0, "sizes");
@@ -732,6 +732,26 @@ int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_i
 #define X(k, h)         \
   if (K == k && H == h) \
     return launch_bwd_src_chunked<k, h, true>(t_indptr_v, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, dc, sp, hv, as_stream(stream));
+  HAN_FOR_SHAPES(X)
+#undef X
+  return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
+}
+
+/* The merge step on its own (n_heavy == 0 in the calls above skips it): used when one real row's segments
+ * come from SEVERAL launches -- the source-blocked forward, where each launch walks the edges of one block of
+ * source nodes (a slab of the node table small enough to stay in L2) and every row is cut at block borders. */
+int han_attn_fwd_merge(const int32_t* heavy_rows, const int32_t* heavy_ptr, int64_t n_heavy, const float* part,
+                       float* R, const float* bias, int K, int H, int act, float* out, int64_t out_stride,
+                       float* vsave, han_stream_t stream) {
+  HAN_REQUIRE(heavy_rows && heavy_ptr && part && R && bias && out && vsave, "null pointer");
+  HAN_REQUIRE(n_heavy > 0 && n_heavy < ((int64_t)1 << 31), "n_heavy");
+  HAN_REQUIRE(act == HAN_ACT_ELU || act == HAN_ACT_IDENTITY, "activation");
+#define X(k, h)                                                                                                  \
+  if (K == k && H == h) {                                                                                        \
+    attn_fwd_merge_kernel<k, h><<<(unsigned)ceil_div64(n_heavy, 4), 128, 0, as_stream(stream)>>>(                \
+        heavy_rows, heavy_ptr, (int)n_heavy, part, R, bias, act, out, out_stride, vsave);                        \
+    return check_launch(__func__);                                                                               \
+  }
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");

@@ -20,6 +20,8 @@ _ACT = {"elu": _lib.ACT_ELU, "identity": _lib.ACT_IDENTITY}
 # register kernels (HAN_ATTN_CHUNKED=0; kept for A/B measurements, identical results).
 import os as _os
 CHUNKED = _os.environ.get("HAN_ATTN_CHUNKED", "1") != "0"
+# EXPERIMENTAL: forward gather in passes over blocks of source nodes whose node-table slab stays in L2
+L2_BLOCKS = int(_os.environ.get("HAN_L2_BLOCKS", "0"))
 
 
 def _empty(shape, device, dtype=torch.float32):
@@ -149,7 +151,19 @@ class NodeAttentionFn(torch.autograd.Function):
                     # dense-path semantics of an all -1e9 row: uniform 1/N over all nodes
                     colmean = T_src[g][:, :D].mean(0).contiguous()
                 sv = graph.split_view() if CHUNKED else None
-                if sv is not None:
+                if CHUNKED and L2_BLOCKS > 1 and sv is None and dist is None and not graph.has_empty_rows():
+                    B = L2_BLOCKS
+                    subs, vmaps, all_rows, all_ptr = graph.source_blocks(B)
+                    part = _empty((n * B, K, H + 2), dev)
+                    for b, sub in enumerate(subs):
+                        cr, n_chunks = sub.chunks()
+                        call("han_attn_fwd_chunked_split", ptr(sub.indptr), ptr(sub.indices), ptr(cr), n_chunks, n,
+                             ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D, ptr(V[g]),
+                             None, ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), row0, ptr(vmaps[b]),
+                             ptr(part), None, None, 0, stream_ptr(), kernels=1)
+                    call("han_attn_fwd_merge", ptr(all_rows), ptr(all_ptr), n, ptr(part), ptr(R[g]), ptr(bias[g]), K, H,
+                         plan.act, ptr(Z[:, g, :]), G * D, ptr(V[g]), stream_ptr())
+                elif sv is not None:
                     # heavy rows are cut into segments; a merge kernel combines their partial softmax states
                     part = _empty((sv.n_slots, K, H + 2), dev)
                     call("han_attn_fwd_chunked_split", ptr(sv.indptr_v), ptr(graph.indices), ptr(sv.chunk_rows),

@@ -191,6 +191,12 @@ int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, 
                                const float* colmean, const uint32_t* seed_ptr, float coef_keep, int metapath,
                                int64_t row0, const int32_t* vmap, float* part, const int32_t* heavy_rows,
                                const int32_t* heavy_ptr, int n_heavy, han_stream_t stream);
+/* The forward merge on its own (pass n_heavy = 0 above to skip the built-in one): for rows whose segments come
+ * from several launches (source-blocked forward: one launch per block of source nodes whose node-table slab
+ * stays in L2; every row is cut at the block borders). */
+int han_attn_fwd_merge(const int32_t* heavy_rows, const int32_t* heavy_ptr, int64_t n_heavy, const float* part,
+                       float* R, const float* bias, int K, int H, int act, float* out, int64_t out_stride,
+                       float* vsave, han_stream_t stream);
 int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_indices, const int32_t* perm,
                                    const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                                    const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,

@@ -277,3 +277,15 @@ def test_heavy_rows_cut_into_segments_match_oracle(split, monkeypatch):
     compare_step(out_o, grads_o, out_p, grads_p)
     assert torch.allclose(out_p["logits"], out_u["logits"], rtol=1e-5, atol=1e-6)
     assert torch.allclose(grads_p["W"][0], grads_u["W"][0], rtol=1e-4, atol=1e-7)
+
+
+def test_source_blocked_forward_matches_oracle(monkeypatch):
+    """The experimental L2-blocked forward (HAN_L2_BLOCKS: one pass per block of source nodes, every row cut
+    at the block borders, han_attn_fwd_merge at the end) computes the same step."""
+    from han_b200 import ops
+    cfg = synth.tiny(seed=151, n=210, f=18, p=2, deg=9.0)
+    params = O.init_params(np.random.default_rng(152), [cfg.F] * cfg.P, cfg.C)
+    out_o, grads_o = oracle_step(cfg, params)
+    monkeypatch.setattr(ops, "L2_BLOCKS", 4)
+    out_p, grads_p, _ = product_step(cfg, params)
+    compare_step(out_o, grads_o, out_p, grads_p)
