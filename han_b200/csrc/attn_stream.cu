@@ -272,13 +272,13 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
 // -------------------------------------------------------------------------------------------------
 // backward, by source (transposed structure)
 // -------------------------------------------------------------------------------------------------
-template <int K, int H, int STAGES, bool SPLIT>
+template <int K, int H, int STAGES, bool SPLIT, bool RED>
 __global__ void __launch_bounds__(kStreamWarps * 32, 3)
 attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t* __restrict__ t_indices,
                             const int32_t* __restrict__ perm, const int32_t* __restrict__ chunk_rows,
                             int64_t n_chunks, const float* __restrict__ Tsrc, const float* __restrict__ R,
                             float* __restrict__ dS_agg, float* __restrict__ df2,
-                            float* __restrict__ dl_edge, DropCoef dc, SplitRows sp) {
+                            float* __restrict__ dl_edge, float* __restrict__ df1_red, DropCoef dc, SplitRows sp) {
   constexpr int D = K * H;
   constexpr int TS = ((D + K + 3) / 4) * 4;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
@@ -418,6 +418,9 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
       const int64_t seg_end = min(row_end, be);
       for (int64_t g = pos; g < seg_end; g += SLOTS) {
         const int64_t ei = g + slot;
+        float dl = 0.f;
+        int drow = 0;
+        (void)drow;
         if (ei < seg_end) {
           const int rec = (int)(ei - bs);
           const float* rp = buf + rec * RS;
@@ -441,9 +444,27 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
             acc[4 * qv + 2] = fmaf(am, g4.z, acc[4 * qv + 2]);
             acc[4 * qv + 3] = fmaf(am, g4.w, acc[4 * qv + 3]);
           }
-          const float dl = a * (da * mk - rp[D + 2 * K + head]) * (lg > 0.f ? 1.f : kLeakySlope);
+          dl = a * (da * mk - rp[D + 2 * K + head]) * (lg > 0.f ? 1.f : kLeakySlope);
           df2acc += dl;
-          dl_edge[(int64_t)pbuf[rec] * K + head] = dl;
+          if constexpr (RED) drow = rbuf[rec];
+          else dl_edge[(int64_t)pbuf[rec] * K + head] = dl;
+        }
+        if constexpr (RED) {
+          // df1[dst] += dl without the per-edge round trip through memory: one 16-byte vector reduction per
+          // 4 heads, resolved in L2 (the whole df1 array is N*K*4 bytes).  Summation order is not fixed.
+          constexpr int VEC = K >= 4 ? 4 : K;
+          const float d1 = __shfl_down_sync(0xffffffffu, dl, 1);
+          const float d2 = __shfl_down_sync(0xffffffffu, dl, 2);
+          const float d3 = __shfl_down_sync(0xffffffffu, dl, 3);
+          if (ei < seg_end && (head % VEC) == 0) {
+            float* dp = df1_red + (int64_t)drow * K + head;
+            if (VEC == 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dp), "f"(dl), "f"(d1), "f"(d2), "f"(d3) : "memory");
+            else if (VEC == 2)
+              asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(dp), "f"(dl), "f"(d1) : "memory");
+            else
+              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dp), "f"(dl) : "memory");
+          }
         }
       }
       pos = seg_end;
@@ -603,18 +624,24 @@ static int launch_fwd_chunked(const int64_t* indptr, const int32_t* indices, con
 template <int K, int H, bool SPLIT>
 static int launch_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
                                   const int32_t* chunk_rows, int64_t n_chunks, const float* Tsrc,
-                                  const float* R, float* dS_agg, float* df2, float* dl_edge, DropCoef dc,
-                                  SplitRows sp, HeavyRows hv, cudaStream_t st) {
+                                  const float* R, float* dS_agg, float* df2, float* dl_edge, float* df1_red,
+                                  DropCoef dc, SplitRows sp, HeavyRows hv, cudaStream_t st) {
   using C = StreamCfg<K, H>;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT>,
+    cudaFuncSetAttribute(attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, false>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bwd_smem);
+    cudaFuncSetAttribute(attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, true>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bwd_smem);
     attr = true;
   }
   unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
-  attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT><<<grid, kStreamWarps * 32, C::bwd_smem, st>>>(
-      t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, dc, sp);
+  if (df1_red != nullptr)
+    attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, true><<<grid, kStreamWarps * 32, C::bwd_smem, st>>>(
+        t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, dc, sp);
+  else
+    attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, false><<<grid, kStreamWarps * 32, C::bwd_smem, st>>>(
+        t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, dc, sp);
   if (SPLIT && hv.n > 0)
     attn_bwd_src_merge_kernel<K, H><<<(unsigned)ceil_div64(hv.n, 4), 128, 0, st>>>(hv.rows, hv.ptr, hv.n, sp.part, dS_agg, df2);
   return check_launch("han_attn_bwd_src_chunked");
@@ -674,16 +701,17 @@ int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const in
 int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
                              const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                              const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                             float* dl_edge, const uint32_t* seed_ptr, float coef_keep, int metapath,
+                             float* dl_edge, float* df1_red, const uint32_t* seed_ptr, float coef_keep, int metapath,
                              int64_t row0, han_stream_t stream) {
-  HAN_REQUIRE(t_indptr && chunk_rows && Tsrc && R && dS_agg && df2 && dl_edge, "null pointer");
+  HAN_REQUIRE(t_indptr && chunk_rows && Tsrc && R && dS_agg && df2 && (dl_edge || df1_red), "null pointer");
+  HAN_REQUIRE(!df1_red || (uintptr_t)df1_red % 16 == 0, "df1_red must be 16-byte aligned");
   HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
   const DropCoef dc = make_drop(seed_ptr, coef_keep, metapath, row0);
   HAN_REQUIRE(n_src > 0 && n_chunks > 0, "sizes");
   HAN_REQUIRE(((uintptr_t)R % 16 == 0) && ((uintptr_t)Tsrc % 16 == 0) && ((uintptr_t)dS_agg % 16 == 0), "16-byte alignment");
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_bwd_src_chunked<k, h, false>(t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, dc, SplitRows{nullptr, nullptr}, HeavyRows{nullptr, nullptr, 0}, as_stream(stream));
+    return launch_bwd_src_chunked<k, h, false>(t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, dc, SplitRows{nullptr, nullptr}, HeavyRows{nullptr, nullptr, 0}, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
@@ -717,10 +745,12 @@ int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, 
 int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_indices, const int32_t* perm,
                                    const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                                    const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                                   float* dl_edge, const uint32_t* seed_ptr, float coef_keep, int metapath,
-                                   int64_t row0, const int32_t* vmap, float* part, const int32_t* heavy_rows,
-                                   const int32_t* heavy_ptr, int n_heavy, han_stream_t stream) {
-  HAN_REQUIRE(t_indptr_v && chunk_rows && Tsrc && R && dS_agg && df2 && dl_edge, "null pointer");
+                                   float* dl_edge, float* df1_red, const uint32_t* seed_ptr, float coef_keep,
+                                   int metapath, int64_t row0, const int32_t* vmap, float* part,
+                                   const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
+                                   han_stream_t stream) {
+  HAN_REQUIRE(t_indptr_v && chunk_rows && Tsrc && R && dS_agg && df2 && (dl_edge || df1_red), "null pointer");
+  HAN_REQUIRE(!df1_red || (uintptr_t)df1_red % 16 == 0, "df1_red must be 16-byte aligned");
   HAN_REQUIRE(vmap && part && n_heavy >= 0 && (n_heavy == 0 || (heavy_rows && heavy_ptr)), "split view: vmap, part, heavy rows");
   HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
   const DropCoef dc = make_drop(seed_ptr, coef_keep, metapath, row0);
@@ -731,7 +761,7 @@ int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_i
   const HeavyRows hv{heavy_rows, heavy_ptr, n_heavy};
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_bwd_src_chunked<k, h, true>(t_indptr_v, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, dc, sp, hv, as_stream(stream));
+    return launch_bwd_src_chunked<k, h, true>(t_indptr_v, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, dc, sp, hv, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");

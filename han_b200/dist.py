@@ -317,14 +317,23 @@ class RowShard:
         dev = T_local.device
         n_loc = T_local.shape[0]
         bs = be.by_src
-        dl = torch.empty(max(bs.nnz, 1), K, dtype=torch.float32, device=dev)
+        from . import ops as _ops
         cr, n_chunks = bs.chunks()
-        call("han_attn_bwd_src_chunked", ptr(bs.indptr), ptr(bs.indices), ptr(be.pos_in_dst), ptr(cr), n_chunks,
-             n_loc, ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), ptr(dl), ptr(plan.seed),
-             1.0 - plan.coef_drop, plan.metapath_id(g), self.row_range(self.n_total)[0], stream_ptr())
         n_all = self.world * self.n_pad
-        df1_part = torch.empty(n_all, K, dtype=torch.float32, device=dev)
-        call("han_attn_bwd_dst", ptr(be.by_dst_indptr), n_all, bs.nnz, ptr(dl), K, ptr(df1_part), stream_ptr())
+        row0 = self.row_range(self.n_total)[0]
+        if not _ops.DETERMINISTIC:
+            # per-destination partial sums accumulated inside the gather pass (vector reductions in L2)
+            df1_part = torch.zeros(n_all, K, dtype=torch.float32, device=dev)
+            call("han_attn_bwd_src_chunked", ptr(bs.indptr), ptr(bs.indices), ptr(be.pos_in_dst), ptr(cr), n_chunks,
+                 n_loc, ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), None, ptr(df1_part), ptr(plan.seed),
+                 1.0 - plan.coef_drop, plan.metapath_id(g), row0, stream_ptr())
+        else:
+            dl = torch.empty(max(bs.nnz, 1), K, dtype=torch.float32, device=dev)
+            call("han_attn_bwd_src_chunked", ptr(bs.indptr), ptr(bs.indices), ptr(be.pos_in_dst), ptr(cr), n_chunks,
+                 n_loc, ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), ptr(dl), None, ptr(plan.seed),
+                 1.0 - plan.coef_drop, plan.metapath_id(g), row0, stream_ptr())
+            df1_part = torch.empty(n_all, K, dtype=torch.float32, device=dev)
+            call("han_attn_bwd_dst", ptr(be.by_dst_indptr), n_all, bs.nnz, ptr(dl), K, ptr(df1_part), stream_ptr())
         # reduce-scatter on the side stream: it overlaps the next meta-path's gather pass; the caller
         # waits on the returned event before the row-local finish
         cur = torch.cuda.current_stream()

@@ -151,8 +151,12 @@ int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const in
 int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
                              const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                              const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                             float* dl_edge, const uint32_t* seed_ptr, float coef_keep, int metapath,
-                             int64_t row0, han_stream_t stream);
+                             float* dl_edge, float* df1_red, const uint32_t* seed_ptr, float coef_keep,
+                             int metapath, int64_t row0, han_stream_t stream);
+/* df1_red (nullable): when given, df1[dst][k] += dl is accumulated right here with 16-byte vector reductions
+ * (red.global.add.v4.f32, resolved in L2; the caller zeroes df1 first) instead of writing dl per edge for
+ * han_attn_bwd_dst: 64 bytes per edge less memory traffic, at the price of a summation order that is not
+ * fixed run to run.  dl_edge may then be NULL.  Deterministic mode: df1_red = NULL. */
 /* Training-mode dropout of the attention coefficients (utils/layers.py:29-30: coefs scaled 1/keep where
  * kept, zeroed elsewhere, NOT re-normalised): coef_keep = 1 - coef_drop in (0,1]; 1 disables it.  The
  * mask bit of edge (dst i, src j), head k of meta-path `metapath` is a pure function of (*seed_ptr, i, j,
@@ -200,9 +204,10 @@ int han_attn_fwd_merge(const int32_t* heavy_rows, const int32_t* heavy_ptr, int6
 int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_indices, const int32_t* perm,
                                    const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                                    const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                                   float* dl_edge, const uint32_t* seed_ptr, float coef_keep, int metapath,
-                                   int64_t row0, const int32_t* vmap, float* part, const int32_t* heavy_rows,
-                                   const int32_t* heavy_ptr, int n_heavy, han_stream_t stream);
+                                   float* dl_edge, float* df1_red, const uint32_t* seed_ptr, float coef_keep,
+                                   int metapath, int64_t row0, const int32_t* vmap, float* part,
+                                   const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
+                                   han_stream_t stream);
 
 /* by-destination pass: df1_i = sum_j dl_edge[e] over CSR row i -> df1 [n_dst][K]. */
 int han_attn_bwd_dst(const int64_t* indptr, int64_t n_dst, int64_t nnz, const float* dl_edge, int K, float* df1,

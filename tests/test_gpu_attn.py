@@ -289,3 +289,20 @@ def test_source_blocked_forward_matches_oracle(monkeypatch):
     monkeypatch.setattr(ops, "L2_BLOCKS", 4)
     out_p, grads_p, _ = product_step(cfg, params)
     compare_step(out_o, grads_o, out_p, grads_p)
+
+
+def test_vector_reduction_df1_mode_matches_oracle(monkeypatch):
+    """HAN_DF1_RED=1: df1 accumulated inside the by-source pass with red.global.add.v4.f32 instead of the
+    per-edge dl array + han_attn_bwd_dst.  Same gradients up to summation order (plain and heavy-row graphs)."""
+    from han_b200 import graph as hg, ops
+    cfg = synth.tiny(seed=161, n=230, f=18, p=2, deg=7.0)
+    cfg.masks[0][5, :] = True
+    cfg.masks[0][:, 9] = True
+    params = O.init_params(np.random.default_rng(162), [cfg.F] * cfg.P, cfg.C)
+    out_o, grads_o = oracle_step(cfg, params)
+    monkeypatch.setattr(ops, "DETERMINISTIC", False)
+    out_p, grads_p, _ = product_step(cfg, params)
+    compare_step(out_o, grads_o, out_p, grads_p)
+    monkeypatch.setattr(hg, "SPLIT_ROW_EDGES", 32)          # and through the virtual-row kernels
+    out_s, grads_s, _ = product_step(cfg, params)
+    compare_step(out_o, grads_o, out_s, grads_s)
