@@ -68,7 +68,9 @@ class NodeAttentionFn(torch.autograd.Function):
     concat / stack of models/gat.py:46,58,60) for the G meta-paths of one plan.
 
     Inputs: X (n,F); W (F, G*D); a1,a2 (G,K,H); b1,b2 (G,K); bias (G,D).  Output Z (n,G,D).
-    Dropout-free (ffd_drop = attn_drop = 0), residual=False: the shipped HAN configuration.
+    Training-mode dropout (plan.in_drop / plan.coef_drop, counter-based masks), the input gradient for
+    stacked layers (han_project_dx) and heavy-row splitting are handled here; the residual branch of
+    utils/layers.py:38-42 is added by the callers (gat.py / layers.py).
     """
 
     @staticmethod
