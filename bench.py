@@ -112,26 +112,36 @@ def build_workload(name, dev, dist):
     import han_b200 as hb
     from han_b200 import synth
     lo, hi = (0, None)
+    tile = dist if (dist is not None and hasattr(dist, "paths")) else None     # tiles.TileShard
+
+    def spans(N, P):
+        """-> (attention rows, label rows, meta-paths) of this rank."""
+        if tile is not None:
+            a, srows = tile.rows(N)
+            return a, srows, tile.paths
+        r = dist.row_range(N) if dist else (0, N)
+        return r, r, list(range(P))
+
     if name in synth.SMALL:
         cfg = synth.SMALL[name]()
         N, F, C, P = cfg.N, cfg.F, cfg.C, cfg.P
-        lo, hi = dist.row_range(N) if dist else (0, N)
+        (lo, hi), (s_lo, s_hi), paths = spans(N, P)
         full = [hb.process.adj_to_bias(a, [N]) for a in cfg.adjs()]
         X = torch.from_numpy(cfg.X[lo:hi]).to(dev)
-        labels = torch.from_numpy(cfg.labels[lo:hi]).to(dev)
-        mask = torch.from_numpy(cfg.train_mask[lo:hi].astype(np.float32)).to(dev)
+        labels = torch.from_numpy(cfg.labels[s_lo:s_hi]).to(dev)
+        mask = torch.from_numpy(cfg.train_mask[s_lo:s_hi].astype(np.float32)).to(dev)
         edges = cfg.n_edges()
         host = {"X": torch.from_numpy(cfg.X[lo:hi]).pin_memory(),
                 "bias": [torch.from_numpy(hb_bias(m[lo:hi])).pin_memory() for m in cfg.masks] if dist is None else None}
     else:
         spec = synth.LARGE[name]
         N, F, C, P = spec.N, spec.F, spec.C, spec.P
-        lo, hi = dist.row_range(N) if dist else (0, N)
+        (lo, hi), (s_lo, s_hi), paths = spans(N, P)
         X = synth.device_features(hi - lo, F, spec.seed, dev, row_lo=lo)
-        labels, mask = synth.device_labels(hi - lo, C, spec.seed, dev, row_lo=lo)
+        labels, mask = synth.device_labels(s_hi - s_lo, C, spec.seed, dev, row_lo=s_lo)
         full = None
         graphs_local, edges = [], 0
-        for p in range(P):
+        for p in paths:
             ip, ix = synth.device_random_csr(hi - lo, N, spec.mean_degree, spec.seed + 17 * (p + 1), dev, row_lo=lo,
                                              powerlaw=spec.powerlaw)
             graphs_local.append(hb.MetaPathGraph.from_csr(ip, ix, n_cols=N, row_offset=lo))
@@ -140,8 +150,8 @@ def build_workload(name, dev, dist):
             edges = int(dist.all_reduce_sum(torch.tensor([edges], dtype=torch.float64, device=dev)).item())
         host = None
     if name in synth.SMALL:
-        graphs_local = [g.row_slice(lo, hi) if dist else g for g in full]
-    ws = X.numel() * 4 + sum(g.nnz * 4 * 3 for g in graphs_local) + (hi - lo) * P * (72 + 96 + 64 * 3) * 4
+        graphs_local = [full[p].row_slice(lo, hi) if dist else full[p] for p in paths]
+    ws = X.numel() * 4 + sum(g.nnz * 4 * 3 for g in graphs_local) + (hi - lo) * len(graphs_local) * (72 + 96 + 64 * 3) * 4
     return dict(N=N, F=F, C=C, P=P, X=X, graphs=graphs_local, labels=labels, mask=mask, edges=edges, host=host,
                 lo=lo, hi=hi, working_set_bytes=ws, full_graphs=full)
 
@@ -159,7 +169,7 @@ def algorithmic_bytes(name, wl):
     TS, RS = 72, 88
     E = sum(g.nnz for g in wl["graphs"])
     n = wl["hi"] - wl["lo"]
-    P = wl["P"]
+    P = len(wl["graphs"])
     if name in ("han_attn_fwd", "han_attn_fwd_chunked", "han_attn_fwd_chunked_split"):
         return (4 + 4 * TS) * E + (8 + 4 * K + 8 * D + 4 * K) * n * P
     if name in ("han_attn_bwd_src", "han_attn_bwd_src_chunked", "han_attn_bwd_src_chunked_split"):
@@ -182,7 +192,12 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
-    if world > 1:
+    if world > 1 and args.partition == "tile":
+        # (meta-path x row-block) tiles: han_b200/tiles.py (opt-in; 4.4x less exchange traffic at 8 GPUs)
+        from han_b200 import synth as _sy, tiles as ht
+        n_paths = _sy.LARGE[args.workload].P if args.workload in _sy.LARGE else _sy.SMALL[args.workload]().P
+        dist = ht.TileShard.init_process_group(n_paths)
+    elif world > 1:
         from han_b200 import dist as hd
         dist = hd.RowShard.init_process_group()
     if args.gpus != world:
@@ -205,7 +220,7 @@ def run_ours(args):
 
     def step(Xin, graphs):
         hp.zero_grad(set_to_none=True)
-        logits, _, _ = hb.HeteGAT_multi.inference([Xin] * P, C, N, True, args.dropout, args.dropout, graphs, [HID], [K_HEADS, 1],
+        logits, _, _ = hb.HeteGAT_multi.inference([Xin] * len(graphs), C, N, True, args.dropout, args.dropout, graphs, [HID], [K_HEADS, 1],
                                                   params=hp, dist=dist, project_mode=pmode)
         if dist is None:
             ce = hb.BaseGAttN.masked_softmax_cross_entropy(logits.reshape(-1, C), wl["labels"], wl["mask"])
@@ -336,7 +351,8 @@ def run_ours(args):
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": WORKLOADS[args.workload], "nodes": N, "features": F, "meta_paths": P,
                       "edges": wl["edges"], "heads": K_HEADS, "hid": HID, "mp_att_size": ATT, "classes": C,
-                      "parallelism": f"dst-row shards x{world}" if world > 1 else "single GPU",
+                      "parallelism": (f"(meta-path x row-block) tiles x{world}" if args.partition == "tile" else
+                                      f"dst-row shards x{world}") if world > 1 else "single GPU",
                       "l2_policy": "inputs larger than L2" if flush is None else "L2 flushed between timed steps",
                       "dropout": args.dropout, "projection": PROJ_NAMES[pmode] if not args.dropout else "fp32 FFMA with per-head input masks"},
            "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
@@ -406,7 +422,10 @@ def run_e2e(args, wl, hp, train, dist, dev, step):
                 mark("X on device", copy_s)
             if dist:
                 main.wait_stream(copy_s)
-                dist._bwd = {}
+                if hasattr(dist, "reset"):
+                    dist.reset()
+                else:
+                    dist._bwd = {}
                 dist.bind(graphs, wl["N"])
                 mark("bind done", main)
             else:
@@ -523,6 +542,8 @@ def main():
     ap.add_argument("--workload", default="syn2m", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--partition", choices=["row", "tile"], default=os.environ.get("HAN_DIST_PARTITION", "row"),
+                    help="multi-GPU partitioning: destination-row shards (default) or (meta-path x row-block) tiles")
     ap.add_argument("--dropout", type=float, default=0.0,
                     help="attn_drop = ffd_drop (the reference trains with 0.6); 0 = parity / headline setting")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",

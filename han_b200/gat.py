@@ -119,8 +119,19 @@ class HeteGAT_multi(BaseGAttN):
         (:39) is kept.  ``nb_nodes`` and ``training`` are accepted and ignored, as in the reference.
         Keyword-only extras: ``params`` (else the process-wide default store, like TF's default
         graph), ``semantic_mode`` ("reference" per-node beta | "paper" node-mean beta), ``dist``
-        (row-shard context for multi-GPU), ``project_mode``, ``return_coef``.
+        (multi-GPU context: ``dist.RowShard`` -- the lists hold this rank's rows of every meta-path -- or
+        ``tiles.TileShard`` -- the lists hold only the meta-paths this rank owns, rows of its attention
+        block, and the outputs are this rank's semantic rows), ``project_mode``, ``return_coef``.
         """
+        from .tiles import TileShard
+        tile = dist if isinstance(dist, TileShard) else None
+        if tile is not None:
+            if params is None:
+                raise ValueError("tile sharding needs params= (the variables of ALL meta-paths, replicated)")
+            if len(inputs_list) != len(tile.paths) or len(bias_mat_list) != len(tile.paths):
+                raise ValueError(f"tile sharding: pass this rank's meta-paths {tile.paths} only")
+            dist = tile.attn                                             # row exchange inside the meta-path's ranks
+        gid = (lambda p: tile.paths[p]) if tile is not None else (lambda p: p)
         attn_drop, ffd_drop = float(attn_drop), float(ffd_drop)
         if not (0.0 <= attn_drop < 1.0 and 0.0 <= ffd_drop < 1.0):
             raise ValueError("attn_drop and ffd_drop are probabilities of dropping, in [0, 1)")
@@ -156,16 +167,18 @@ class HeteGAT_multi(BaseGAttN):
         for grp in groups:
             plan = ops.NodeAttentionPlan(graphs=[graphs[p] for p in grp], K=K, H=H, act=act,
                                          project_mode=project_mode, dist=dist, want_coefs=return_coef,
-                                         in_drop=ffd_drop, coef_drop=attn_drop, seed=seed, metapath_ids=list(grp))
+                                         in_drop=ffd_drop, coef_drop=attn_drop, seed=seed,
+                                         metapath_ids=[gid(p) for p in grp])
             if len(grp) == 1:
-                p = grp[0]
+                p = gid(grp[0])
                 W, a1, b1 = params.W[p], params.a1[p].unsqueeze(0), params.b1[p].unsqueeze(0)
                 a2, b2, bias = params.a2[p].unsqueeze(0), params.b2[p].unsqueeze(0), params.bias[p].unsqueeze(0)
             else:
-                W = torch.cat([params.W[p] for p in grp], dim=1)
-                a1 = torch.stack([params.a1[p] for p in grp]); b1 = torch.stack([params.b1[p] for p in grp])
-                a2 = torch.stack([params.a2[p] for p in grp]); b2 = torch.stack([params.b2[p] for p in grp])
-                bias = torch.stack([params.bias[p] for p in grp])
+                ids = [gid(p) for p in grp]
+                W = torch.cat([params.W[p] for p in ids], dim=1)
+                a1 = torch.stack([params.a1[p] for p in ids]); b1 = torch.stack([params.b1[p] for p in ids])
+                a2 = torch.stack([params.a2[p] for p in ids]); b2 = torch.stack([params.b2[p] for p in ids])
+                bias = torch.stack([params.bias[p] for p in ids])
             z_parts.append(ops.node_attention(plan, xs[grp[0]], W, a1, b1, a2, b2, bias))   # :42-58
             if return_coef:
                 for p, alpha in zip(grp, plan.coefs):
@@ -185,25 +198,30 @@ class HeteGAT_multi(BaseGAttN):
             nxt = []
             for p in range(P):
                 h_old = multi_embed[:, p, :].contiguous()                   # :49
+                q = gid(p)
                 plan = ops.NodeAttentionPlan(graphs=[graphs[p]], K=Kl, H=Hl,
                                              act=_lib.ACT_IDENTITY if use_res else act, project_mode=0, dist=dist,
                                              want_coefs=return_coef, in_drop=ffd_drop, coef_drop=attn_drop,
-                                             seed=seed, metapath_ids=[l * P + p])
-                h = ops.node_attention(plan, h_old, lay["W"][p], lay["a1"][p].unsqueeze(0), lay["b1"][p].unsqueeze(0),
-                                       lay["a2"][p].unsqueeze(0), lay["b2"][p].unsqueeze(0),
-                                       lay["bias"][p].unsqueeze(0))[:, 0, :]
+                                             seed=seed, metapath_ids=[l * params.P + q])
+                h = ops.node_attention(plan, h_old, lay["W"][q], lay["a1"][q].unsqueeze(0), lay["b1"][q].unsqueeze(0),
+                                       lay["a2"][q].unsqueeze(0), lay["b2"][q].unsqueeze(0),
+                                       lay["bias"][q].unsqueeze(0))[:, 0, :]
                 if use_res:                                                 # ret + conv1d(seq, H, 1), then the activation
-                    h = torch.addmm(lay["b_res"][p], h_old, lay["W_res"][p]) + h
+                    h = torch.addmm(lay["b_res"][q], h_old, lay["W_res"][q]) + h
                     h = h if act == _lib.ACT_IDENTITY else torch.nn.functional.elu(h)
                 if return_coef:
                     coef_out[p] = layers.EdgeCoefs(graphs[p], plan.coefs[0])
                 nxt.append(h)
             multi_embed = torch.stack(nxt, dim=1)                           # (N,P,K_l*H_l)
 
+        if tile is not None:
+            # (rows of my attention block, my meta-paths, D) -> (my semantic rows, ALL meta-paths, D): one all-to-all
+            multi_embed = tile.exchange_Z(multi_embed.contiguous())
+
         final_embed, att_val = layers.SimpleAttLayer(                       # :61-63
             multi_embed, mp_att_size, time_major=False, return_alphas=True,
             params={"w_omega": params.w_omega, "b_omega": params.b_omega, "u_omega": params.u_omega},
-            mode=semantic_mode, dist=dist)
+            mode=semantic_mode, dist=tile if tile is not None else dist)
 
         out = []
         for i in range(n_heads[-1]):                                        # :66-68

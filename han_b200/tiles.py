@@ -1,0 +1,184 @@
+"""(meta-path x row-block) tile sharding -- the low-traffic alternative to ``dist.RowShard``.
+
+Row sharding (dist.py) gives every rank a block of destination rows of EVERY meta-path, so every rank
+must fetch every other rank's node-table rows ``T`` and row records ``R`` of every meta-path: at 8 GPUs
+on the 2M-node graph 4.46 GB per rank and step, and the step is bound by that exchange (DESIGN.md
+section 8).  Here rank ``r = h*P + p`` owns ONE meta-path p and, when there are more ranks than
+meta-paths, one of ``Hn = W/P`` row blocks h of it (with fewer ranks than meta-paths a rank owns
+``P/W`` whole meta-paths):
+
+  * node-level attention of meta-path p needs ``T_p`` / ``R_p`` only: they are exchanged inside the Hn
+    ranks that share p (an ordinary ``RowShard`` on that sub-group; no exchange at all when Hn == 1);
+  * the semantic layer needs all P meta-path embeddings of a node on one rank: ``exchange_Z`` re-shards
+    ``Z`` from (meta-path, row block h) tiles to row sub-blocks with ONE all-to-all inside the ranks
+    that share h (and the backward sends ``dZ`` the way back);
+  * parameters are replicated; a rank's gradients for the meta-paths it does not own are zero and the
+    usual all-reduce sums the rest.
+
+Traffic per rank and step on the 2M graph at 8 GPUs: 288 + 352 MB inside the pair, 2 x 192 MB of
+``Z`` / ``dZ`` = about 1.0 GB instead of 4.46 GB.  Equal-size tiles assume meta-paths of similar weight;
+edge-balanced tile assignment is future work.
+
+Opt-in (``HAN_DIST_PARTITION=tile`` in bench.py / tests/dist_check.py); host arithmetic is covered by
+gloo tests (tests/test_dist_cpu.py), the whole step by tests/dist_check.py.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as td
+
+from . import _lib
+from .dist import RowShard
+
+
+def tile_layout(rank: int, world: int, P: int) -> Tuple[int, int, int, int, List[int]]:
+    """-> (Hn row blocks per meta-path, h = this rank's row block, Wz = ranks sharing h, member = index
+    inside those, paths = the meta-paths this rank owns)."""
+    if world >= P:
+        if world % P:
+            raise ValueError(f"tile sharding needs the rank count ({world}) to be a multiple of the meta-paths ({P})")
+        Hn, per = world // P, 1
+        h, member = rank // P, rank % P
+    else:
+        if P % world:
+            raise ValueError(f"tile sharding needs the meta-paths ({P}) to be a multiple of the rank count ({world})")
+        Hn, per = 1, P // world
+        h, member = 0, rank
+    return Hn, h, world // Hn, member, list(range(member * per, (member + 1) * per))
+
+
+def tile_rows(N: int, Hn: int, h: int, Wz: int, member: int) -> Tuple[Tuple[int, int], Tuple[int, int], int, int]:
+    """-> ((attention rows lo, hi), (semantic rows lo, hi), n_hpad, n_sub): attention block h of
+    ceil(N/Hn) rows, cut into Wz semantic sub-blocks of ceil(n_hpad/Wz) rows."""
+    n_hpad = -(-N // Hn)
+    a_lo = min(N, h * n_hpad)
+    a_hi = min(N, a_lo + n_hpad)
+    n_sub = -(-n_hpad // Wz)
+    s_lo = min(a_hi, a_lo + member * n_sub)
+    s_hi = min(a_hi, s_lo + n_sub)
+    return (a_lo, a_hi), (s_lo, s_hi), n_hpad, n_sub
+
+
+class _ZExchange(torch.autograd.Function):
+    """Z (rows of block h, this rank's meta-paths, D)  ->  (this rank's semantic rows, ALL P meta-paths, D)."""
+
+    @staticmethod
+    def forward(ctx, Z, tile: "TileShard"):
+        n_h, per, D = Z.shape
+        Wz, n_sub = tile.Wz, tile.n_sub
+        send = Z.new_zeros(Wz * n_sub, per, D)
+        send[:n_h] = Z
+        recv = torch.empty_like(send)
+        _lib.trace_mark("all_to_all Z >")
+        td.all_to_all_single(recv, send, group=tile.z_group)
+        _lib.trace_mark("all_to_all Z <")
+        ctx.tile, ctx.n_h = tile, n_h
+        n_sem = tile.sem_rows[1] - tile.sem_rows[0]
+        # recv[j] = member j's meta-paths for MY sub-block: (Wz, n_sub, per, D) -> (n_sub, Wz*per = P, D)
+        return recv.view(Wz, n_sub, per, D).permute(1, 0, 2, 3).reshape(n_sub, Wz * per, D)[:n_sem].contiguous()
+
+    @staticmethod
+    def backward(ctx, dOut):
+        tile, n_h = ctx.tile, ctx.n_h
+        Wz, n_sub = tile.Wz, tile.n_sub
+        n_sem, P, D = dOut.shape
+        per = P // Wz
+        pad = dOut.new_zeros(n_sub, P, D)
+        pad[:n_sem] = dOut
+        send = pad.view(n_sub, Wz, per, D).permute(1, 0, 2, 3).contiguous()
+        recv = torch.empty_like(send)
+        _lib.trace_mark("all_to_all dZ >")
+        td.all_to_all_single(recv, send, group=tile.z_group)
+        _lib.trace_mark("all_to_all dZ <")
+        return recv.view(Wz * n_sub, per, D)[:n_h].contiguous(), None
+
+
+class TileShard:
+    def __init__(self, rank: int, world: int, P: int, device: torch.device):
+        self.rank, self.world, self.P, self.device = rank, world, P, device
+        self.Hn, self.h, self.Wz, self.member, self.paths = tile_layout(rank, world, P)
+        self.z_group = None                      # WORLD when every rank shares the one row block
+        self.attn: Optional[RowShard] = None     # exchange of T / R inside the ranks that share a meta-path
+        if self.Hn > 1:
+            # collective: every rank creates every group, in the same order
+            zg = [td.new_group([h * P + p for p in range(P)]) for h in range(self.Hn)]
+            ag = [td.new_group([h * P + p for h in range(self.Hn)]) for p in range(P)]
+            self.z_group = zg[self.h]
+            self.attn = RowShard(self.h, self.Hn, device, group=ag[self.member])
+            self.attn.comm, self.attn.use_multicast = "nccl", False    # symmetric-memory pull on a sub-group: next step
+        self.n_total = None
+        self.attn_rows = self.sem_rows = (0, 0)
+        self.n_hpad = self.n_sub = 0
+
+    @staticmethod
+    def init_process_group(P: int) -> "TileShard":
+        shard = RowShard.init_process_group()    # same backend / device set-up as row sharding
+        return TileShard(shard.rank, shard.world, P, shard.device)
+
+    # ---- set-up ------------------------------------------------------------------------------
+    def rows(self, N: int):
+        """-> (attention rows (lo, hi), semantic rows (lo, hi)) of this rank for an N-node graph."""
+        a, s, _, _ = tile_rows(N, self.Hn, self.h, self.Wz, self.member)
+        return a, s
+
+    def bind(self, graphs: Sequence, N: int) -> None:
+        """Once per graph set (graphs = this rank's meta-paths, rows = its attention block)."""
+        self.n_total = N
+        self.attn_rows, self.sem_rows, self.n_hpad, self.n_sub = tile_rows(N, self.Hn, self.h, self.Wz, self.member)
+        if self.attn is not None:
+            self.attn.bind(graphs, N)
+        else:
+            for g in graphs:
+                g.transpose()
+
+    def reset(self) -> None:
+        if self.attn is not None:
+            self.attn._bwd = {}
+
+    # ---- the one exchange of the forward / backward ------------------------------------------------
+    def exchange_Z(self, Z: torch.Tensor) -> torch.Tensor:
+        return _ZExchange.apply(Z, self)
+
+    # ---- collectives over all ranks ------------------------------------------------------------------
+    def barrier(self):
+        td.barrier()
+
+    def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        td.all_reduce(t, op=td.ReduceOp.SUM)
+        return t
+
+    def all_reduce_max(self, t: torch.Tensor) -> torch.Tensor:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return t
+
+    def masked_loss(self, logits, labels, mask, train_op):
+        """This rank's share of masked CE over the GLOBAL mask (models/base_gattn.py:41-48) plus 1/W of the L2
+        term; logits / labels / mask are this rank's SEMANTIC rows."""
+        mask = mask.to(logits.dtype)
+        mask_total = self.all_reduce_sum(mask.sum().reshape(1))
+        labels = labels.to(logits.dtype)
+        xent = -(labels * torch.log_softmax(logits, dim=-1)).sum(-1)
+        ce = ((xent * mask).sum() / mask_total).squeeze(0)
+        return ce if train_op is None else ce + train_op.l2_loss() / self.world
+
+    def all_reduce_grads(self, module: torch.nn.Module) -> None:
+        """Variables of the meta-paths this rank does not own have no gradient here: they count as zero."""
+        params = list(module.parameters())
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+        _lib.trace_mark("all_reduce grads >")
+        td.all_reduce(flat, op=td.ReduceOp.SUM)
+        _lib.trace_mark("all_reduce grads <")
+        off = 0
+        for p in params:
+            n = p.numel()
+            g = flat[off:off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+
+    def all_reduce_flat(self, flat: torch.Tensor) -> None:
+        td.all_reduce(flat, op=td.ReduceOp.SUM)

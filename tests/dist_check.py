@@ -106,7 +106,66 @@ def run_dropout_case(shard):
         assert_close(p[k].grad, p64[k].grad, "d" + k + " (dropout)")
 
 
+def run_tile_case(tile, cfg, params, mode):
+    """(meta-path x row-block) tiles (han_b200/tiles.py): this rank's meta-paths on its attention rows, the
+    all-to-all of Z, semantic layer and loss on its semantic rows -- against the whole-graph oracle."""
+    dev = tile.device
+    N, P, C = cfg.N, cfg.P, cfg.C
+    (a_lo, a_hi), (s_lo, s_hi) = tile.rows(N)
+    out_o, grads_o = oracle_step(cfg, params, semantic_mode=mode)
+    hp = hb.HANParams([cfg.F] * P, C, device=dev).load_dict(params)
+    full = [hb.process.adj_to_bias(a, [N]) for a in cfg.adjs()]
+    graphs = [full[p].row_slice(a_lo, a_hi) for p in tile.paths]
+    tile.reset()
+    tile.bind(graphs, N)
+    X = torch.from_numpy(cfg.X[a_lo:a_hi]).to(dev)[None]
+    labels = torch.from_numpy(cfg.labels[s_lo:s_hi]).to(dev)
+    mask = torch.from_numpy(cfg.train_mask[s_lo:s_hi].astype(np.float32)).to(dev)
+    train = hb.BaseGAttN.training(hp, 0.005, 0.001)
+    logits, fe, av = hb.HeteGAT_multi.inference([X] * len(tile.paths), C, N, True, 0.0, 0.0, graphs, [8], [8, 1],
+                                                params=hp, semantic_mode=mode, dist=tile)
+    total = tile.masked_loss(logits.reshape(-1, C), labels, mask, train)
+    total.backward()
+    tile.all_reduce_grads(hp)
+    tot = tile.all_reduce_sum(total.detach().clone().reshape(1))
+    torch.cuda.synchronize()
+    if s_hi > s_lo:
+        assert_close(logits[0], out_o["logits"][0, s_lo:s_hi], "logits tile")
+        assert_close(fe, out_o["final_embed"][s_lo:s_hi], "final_embed tile")
+        assert_close(av, out_o["att_val"][s_lo:s_hi], "att_val tile")
+    assert_close(tot[0], out_o["total"], "loss")
+    gp = hp.grad_dict()
+    for k, v in grads_o.items():
+        if isinstance(v, list):
+            for i, g in enumerate(v):
+                assert_close(gp[k][i], g, f"d{k}[{i}]")
+        else:
+            assert_close(gp[k], v, f"d{k}")
+
+
+def main_tile():
+    from han_b200.tiles import TileShard
+    base = hd.RowShard.init_process_group()
+    W = base.world
+    for seed, n, mode, P in ((71, 257, "reference", 4), (72, 310, "paper", 4), (73, 96, "reference", 2 if W <= 2 else W // 2)):
+        if (W >= P and W % P) or (W < P and P % W):
+            continue
+        tile = TileShard(base.rank, W, P, base.device)
+        cfg = synth.tiny(seed=seed, n=n, f=36, p=P, deg=6.0)
+        cfg.masks[1][:, 5] = True
+        params = O.init_params(np.random.default_rng(seed + 1), [cfg.F] * cfg.P, cfg.C)
+        run_tile_case(tile, cfg, params, mode)
+    base.barrier()
+    torch.cuda.synchronize()
+    if base.rank == 0:
+        print("DIST_CHECK_OK world=%d partition=tile" % W, flush=True)
+    sys.stdout.flush()
+    os._exit(0)
+
+
 def main():
+    if os.environ.get("HAN_DIST_PARTITION", "row") == "tile":
+        return main_tile()
     shard = hd.RowShard.init_process_group()
     run_dropout_case(shard)
     for seed, n, mode in ((61, 257, "reference"), (62, 400, "paper"), (63, 96, "reference")):

@@ -134,3 +134,78 @@ def test_gloo_world2_exchange_loss_and_grads():
     for p in procs:
         p.join(timeout=60)
     assert all(msg == "ok" for _, msg in res), res
+
+
+# ---- (meta-path x row-block) tile sharding: han_b200/tiles.py ------------------------------------------
+def test_tile_layout_covers_every_tile_and_every_row_once():
+    from han_b200.tiles import tile_layout, tile_rows
+    for W, P, N in ((8, 4, 2_000_000), (4, 4, 3025), (2, 4, 97), (8, 2, 736_389), (2, 2, 10), (1, 3, 7)):
+        owners = {}
+        sem = []
+        for r in range(W):
+            Hn, h, Wz, member, paths = tile_layout(r, W, P)
+            (a_lo, a_hi), (s_lo, s_hi), n_hpad, n_sub = tile_rows(N, Hn, h, Wz, member)
+            assert Hn * Wz == W and len(paths) * Wz == P and a_lo <= s_lo <= s_hi <= a_hi
+            for p in paths:
+                assert (p, h) not in owners
+                owners[(p, h)] = (a_lo, a_hi)
+            sem.append((s_lo, s_hi))
+        assert len(owners) == P * Hn
+        for p in range(P):                               # the row blocks of one meta-path tile [0, N)
+            spans = sorted(owners[(p, h)] for h in range(Hn))
+            assert spans[0][0] == 0 and spans[-1][1] == N and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert sum(hi - lo for lo, hi in sem) == N and len({s for s in sem if s[1] > s[0]}) == sum(1 for s in sem if s[1] > s[0])
+    with pytest.raises(ValueError):
+        tile_layout(0, 3, 4)
+
+
+def _tile_worker(rank, world, port, P, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from han_b200.tiles import TileShard
+    tile = TileShard.init_process_group(P)
+    try:
+        N, D = 23, 6
+        g = torch.Generator().manual_seed(11)
+        Z_full = torch.randn(N, P, D, generator=g)
+        Wt = torch.randn(N, P, D, generator=g)
+        tile.bind([], N)
+        (a_lo, a_hi), (s_lo, s_hi) = tile.attn_rows, tile.sem_rows
+        Z_mine = Z_full[a_lo:a_hi][:, tile.paths, :].clone().requires_grad_(True)
+        out = tile.exchange_Z(Z_mine)
+        assert out.shape == (s_hi - s_lo, P, D) and torch.equal(out, Z_full[s_lo:s_hi])
+        (out * Wt[s_lo:s_hi]).sum().backward()
+        assert torch.equal(Z_mine.grad, Wt[a_lo:a_hi][:, tile.paths, :])
+        # gradients of variables this rank never touched count as zero in the all-reduce
+        lin_a, lin_b = torch.nn.Linear(3, 2), torch.nn.Linear(3, 2)
+        with torch.no_grad():
+            for p_ in list(lin_a.parameters()) + list(lin_b.parameters()):
+                p_.fill_(0.5)
+        mod = torch.nn.ModuleList([lin_a, lin_b])
+        (lin_a if rank % 2 == 0 else lin_b)(torch.ones(1, 3)).sum().backward()
+        tile.all_reduce_grads(mod)
+        n_even = (world + 1) // 2
+        assert torch.allclose(lin_a.weight.grad, torch.full((2, 3), float(n_even)))
+        assert torch.allclose(lin_b.weight.grad, torch.full((2, 3), float(world - n_even)))
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        if td.is_initialized():
+            td.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,P", [(2, 4), (2, 2), (4, 2)])
+def test_gloo_tile_exchange_of_meta_path_embeddings(world, P):
+    """world 2 / P 4: two meta-paths per rank, one row block.  world 4 / P 2: Hn = 2 row blocks per meta-path,
+    the Z exchange runs inside the two ranks that share a row block (sub-groups)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + (os.getpid() % 150) + 7 * world + P
+    procs = [ctx.Process(target=_tile_worker, args=(r, world, port, P, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(msg == "ok" for _, msg in res), res

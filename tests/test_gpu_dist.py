@@ -25,3 +25,17 @@ def test_sharded_step_matches_oracle(comm):
            os.path.join(ROOT, "tests", "dist_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_tile_sharded_step_matches_oracle():
+    """(meta-path x row-block) tile sharding (han_b200/tiles.py): 2 ranks own two / one whole meta-paths each;
+    4 ranks additionally split a meta-path into two row blocks (the T / R exchange runs inside that pair)."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else 4
+    env = dict(os.environ, HAN_DIST_PARTITION="tile")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29539", os.path.join(ROOT, "tests", "dist_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
