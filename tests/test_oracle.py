@@ -195,3 +195,64 @@ def test_oracle_reproduces_golden(name):
             assert np.array_equal(a, b), k
         else:
             assert np.allclose(a, b, rtol=1e-12, atol=1e-14), k
+
+
+# ---- the widened rows: restatements pinned by closed forms / compositions -----------
+def test_const_1_head_is_the_neighbour_mean():
+    """utils/layers.py:49-81: logits = the 0/1 adjacency -> after the -1e9 mask every neighbour weighs 1/deg."""
+    cfg = synth.tiny(seed=21, n=40, f=12, p=1, deg=5.0)
+    rng = np.random.default_rng(22)
+    hp = {"W": torch.from_numpy(rng.normal(size=(cfg.F, 4))), "bias": torch.from_numpy(rng.normal(size=4))}
+    X = torch.from_numpy(cfg.X).double()[None]
+    bias = torch.from_numpy(O.adj_to_bias(cfg.adjs()[0], [cfg.N], 1))
+    out = O.attn_head_const_1(X, 4, bias, O.identity, hp)
+    m = torch.from_numpy(cfg.masks[0]).double()
+    ref = (m / m.sum(1, keepdim=True)) @ (X[0] @ hp["W"]) + hp["bias"]
+    assert torch.allclose(out[0], ref, rtol=1e-12, atol=1e-12)
+
+
+def test_residual_is_a_dead_store_when_widths_agree_and_a_conv1d_otherwise():
+    """utils/layers.py:38-42."""
+    cfg = synth.tiny(seed=23, n=30, f=4, p=1, deg=4.0)
+    rng = np.random.default_rng(24)
+    t = lambda *s: torch.from_numpy(rng.normal(size=s))
+    X = torch.from_numpy(cfg.X).double()[None]
+    bias = torch.from_numpy(O.adj_to_bias(cfg.adjs()[0], [cfg.N], 1))
+    hp = {"W": t(4, 4), "a1": t(4), "b1": t(), "a2": t(4), "b2": t(), "bias": t(4)}
+    assert torch.equal(O.attn_head(X, 4, bias, O.elu, hp, residual=True), O.attn_head(X, 4, bias, O.elu, hp))
+    hp2 = {"W": t(4, 6), "a1": t(6), "b1": t(), "a2": t(6), "b2": t(), "bias": t(6), "W_res": t(4, 6), "b_res": t(6)}
+    plain = O.attn_head(X, 6, bias, O.identity, hp2)
+    res = O.attn_head(X, 6, bias, O.identity, hp2, residual=True)
+    assert torch.allclose(res - plain, X @ hp2["W_res"] + hp2["b_res"], rtol=1e-12, atol=1e-12)
+
+
+def test_stacked_layers_compose_attn_heads():
+    """models/gat.py:48-57: layer 2 of meta-path p reads the concatenated heads of layer 1 of the SAME meta-path."""
+    cfg = synth.tiny(seed=25, n=36, f=10, p=2, deg=5.0)
+    params = O.init_params(np.random.default_rng(26), [cfg.F] * 2, cfg.C, hid=4, heads=2, mp_att_size=8, deep=[(3, 4)])
+    X = torch.from_numpy(cfg.X).double()[None]
+    biases = [torch.from_numpy(O.adj_to_bias(a, [cfg.N], 1)) for a in cfg.adjs()]
+    _, fe, av = O.HeteGAT_multi_inference([X, X], cfg.C, cfg.N, False, 0.0, 0.0, biases, [4, 4], [2, 3, 1], params,
+                                          mp_att_size=8)
+    embeds = []
+    for p in range(2):
+        h1 = torch.cat([O.attn_head(X, 4, biases[p], O.elu, O.head_params(params, p, k)) for k in range(2)], -1)
+        h2 = torch.cat([O.attn_head(h1, 4, biases[p], O.elu, O.head_params(params, p, k, layer=1)) for k in range(3)], -1)
+        embeds.append(h2[0].unsqueeze(1))
+    fe2, av2 = O.SimpleAttLayer(torch.cat(embeds, 1), 8, params, return_alphas=True)
+    assert fe.shape == (cfg.N, 12) and torch.equal(fe, fe2) and torch.equal(av, av2)
+
+
+def test_gat_inference_averages_identity_output_heads():
+    """models/gat.py:25-30."""
+    cfg = synth.tiny(seed=27, n=32, f=9, p=1, c=5, deg=5.0)
+    params = O.init_gat_params(np.random.default_rng(28), cfg.F, cfg.C, [4], [2, 3])
+    X = torch.from_numpy(cfg.X).double()[None]
+    bias = torch.from_numpy(O.adj_to_bias(cfg.adjs()[0], [cfg.N], 1))
+    logits = O.GAT_inference(X, cfg.C, cfg.N, False, 0.0, 0.0, bias, [4], [2, 3], params)
+    lay, out = params["hidden"][0], params["out"]
+    hd = lambda l, k, H: {"W": l["W"][:, k * H:(k + 1) * H], "a1": l["a1"][k], "b1": l["b1"][k], "a2": l["a2"][k],
+                          "b2": l["b2"][k], "bias": l["bias"][k * H:(k + 1) * H]}
+    h1 = torch.cat([O.attn_head(X, 4, bias, O.elu, hd(lay, k, 4)) for k in range(2)], -1)
+    ref = sum(O.attn_head(h1, cfg.C, bias, O.identity, hd(out, k, cfg.C)) for k in range(3)) / 3
+    assert logits.shape == (1, cfg.N, cfg.C) and torch.allclose(logits, ref, rtol=1e-12, atol=1e-12)
