@@ -1,0 +1,398 @@
+// K-C on 5th-generation tensor cores (EXPERIMENTAL, opt-in: HAN_SEM_TC=1; the shipped path is the
+// mma.sync kernel in semantic.cu).  Semantic attention forward, utils/layers.py:152-159, for the shipped
+// shape D = 64, A = 128:
+//
+//   v = tanh(Z w + b)   s = v . u   beta = softmax_P(s) per node   out[n] = sum_p beta[n,p] Z[n,p]
+//
+// Why: the warp-level MMA path issues one m16n8k8 per ~2.2 cycles per SM, so the three TF32 passes of
+// Z w cost ~1.5 ms of tensor-pipe time on the 2M-node config (profiles/r1_ncu_summary.md section 2c);
+// tcgen05 does the same 128 x 128 x 64 tile in 24 instructions (~0.8 us).
+//
+// One PERSISTENT CTA per SM walks tiles of 128 (node, meta-path) rows (whole nodes per tile):
+//   warp 0      TMA producer: w^T hi/lo once (64 KB, SWIZZLE_128B, stays resident), then one Z tile per
+//               step into a 2-deep ring (2 K-blocks of 32 floats each)
+//   warp 1      TMEM allocator (256 columns = two 128-column accumulators) + single-thread
+//               tcgen05.mma.kind::tf32 issuer, 3xTF32 (lo*hi + hi*lo + hi*hi)
+//   warps 2-5   split the landed Z tile into hi / lo in place (generic proxy -> fence.proxy.async), and, one
+//               tile behind, the epilogue: tcgen05.ld one accumulator row per thread, tanh, dot with u,
+//               v written for the backward, per-node softmax over P through shared memory, and the
+//               weighted sum from the Z tile still sitting in the ring (Z = hi + lo exactly).
+// The epilogue of tile i runs under the MMAs of tile i+1 (second accumulator) and the TMA of tile i+2.
+#include <cuda.h>
+
+#include "han_common.cuh"
+
+namespace han {
+
+constexpr int ST_BM = 128;                     // rows per tile
+constexpr int ST_D = 64, ST_A = 128;
+constexpr int ST_BK = 32;                      // fp32 K elements per 128-byte swizzle span
+constexpr int ST_THREADS = 192;
+constexpr uint32_t ST_KB_BYTES = ST_BM * ST_BK * 4;          // one K-block of a 128-row operand: 16 KB
+constexpr uint32_t ST_W_BYTES = 2 * 2 * ST_KB_BYTES;         // w^T: hi | lo, 2 K-blocks each: 64 KB
+constexpr uint32_t ST_STAGE_BYTES = 2 * 2 * ST_KB_BYTES;     // Z tile: hi (2 K-blocks) | lo (2 K-blocks): 64 KB
+constexpr uint32_t ST_SMEM_BYTES = 1024 + ST_W_BYTES + 2 * ST_STAGE_BYTES + 4 * (2 * ST_A + 2 * ST_BM) + 256;
+constexpr uint32_t kStSpinLimit = 1u << 28;
+
+__device__ __forceinline__ uint32_t st_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void st_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void st_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && ++spins > kStSpinLimit) __trap();   // a protocol bug becomes an error, not a hang
+  }
+}
+__device__ __forceinline__ void st_tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void st_umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void st_umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t st_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// byte offset of float column c (0..31) of row r inside one K-block tile in the SWIZZLE_128B layout
+__device__ __forceinline__ uint32_t st_sw128(int r, int c) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 2) ^ (r & 7)) << 4)) + (c & 3) * 4);
+}
+__device__ __forceinline__ void st_bar_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// w [D][A] -> w^T hi / lo [A][D] (K-major operand B)
+__global__ void st_wt_split_kernel(const float* __restrict__ w, float* __restrict__ wt_hi, float* __restrict__ wt_lo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ST_A * ST_D) return;
+  const int a = idx / ST_D, d = idx % ST_D;
+  const float x = w[d * ST_A + a];
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  wt_hi[idx] = hi;
+  wt_lo[idx] = x - hi;
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 1)
+semantic_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmWhi,
+                       const __grid_constant__ CUtensorMap tmWlo, int64_t n, int P, const float* __restrict__ b,
+                       const float* __restrict__ u, int mode, float* __restrict__ out, float* __restrict__ beta,
+                       float* __restrict__ vsave, float* __restrict__ scores) {
+  constexpr int D = ST_D, A = ST_A;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (st_smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - st_smem_u32(smem_raw));
+  // [w^T hi kb0 | hi kb1 | lo kb0 | lo kb1] [stage 0: Z hi kb0 | hi kb1 | lo kb0 | lo kb1] [stage 1 ...] [b|u|ss|bts] [bars]
+  const uint32_t w_base = base;
+  const uint32_t st_base = base + ST_W_BYTES;
+  float* par = reinterpret_cast<float*>(gen + ST_W_BYTES + 2 * ST_STAGE_BYTES);   // b[128] | u[128]
+  float* ss = par + 2 * A;                                                        // [128] scores of the tile
+  float* bts = ss + ST_BM;                                                        // [128] beta of the tile
+  const uint32_t bars = base + ST_W_BYTES + 2 * ST_STAGE_BYTES + 4 * (2 * A + 2 * ST_BM);
+  const uint32_t w_full = bars, full0 = bars + 8, xform0 = bars + 24, mma0 = bars + 40, free0 = bars + 56;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bars + 80 - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nodes_per_tile = ST_BM / P;
+  const int rows_per_tile = nodes_per_tile * P;
+  const int64_t total_rows = n * P;
+  const int64_t n_tiles = ceil_div64(n, nodes_per_tile);
+  const int64_t my_tiles = (n_tiles > (int64_t)blockIdx.x) ? ceil_div64(n_tiles - blockIdx.x, gridDim.x) : 0;
+
+  for (int i = threadIdx.x; i < A; i += ST_THREADS) {
+    par[i] = b[i];
+    par[A + i] = u[i];
+  }
+  if (threadIdx.x == 0) {
+    st_mbar_init(w_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      st_mbar_init(full0 + 8 * s, 1);
+      st_mbar_init(xform0 + 8 * s, 128);
+      st_mbar_init(mma0 + 8 * s, 1);
+      st_mbar_init(free0 + 8 * s, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(st_smem_u32(tmem_slot)),
+                 "n"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0 && my_tiles > 0) {
+      st_mbar_expect_tx(w_full, ST_W_BYTES);
+      for (int kb = 0; kb < 2; ++kb) {
+        st_tma_load_2d(w_base + kb * ST_KB_BYTES, &tmWhi, kb * ST_BK, 0, w_full);
+        st_tma_load_2d(w_base + (2 + kb) * ST_KB_BYTES, &tmWlo, kb * ST_BK, 0, w_full);
+      }
+      for (int64_t i = 0; i < my_tiles; ++i) {
+        const int s = (int)(i & 1);
+        const uint32_t ph = (uint32_t)((i >> 1) & 1);
+        st_mbar_wait(free0 + 8 * s, ph ^ 1);       // the epilogue two tiles back released this slot
+        const int64_t tile = blockIdx.x + i * gridDim.x;
+        const int row0 = (int)(tile * rows_per_tile);
+        const uint32_t dst = st_base + s * ST_STAGE_BYTES;
+        st_mbar_expect_tx(full0 + 8 * s, 2 * ST_KB_BYTES);
+        st_tma_load_2d(dst, &tmZ, 0, row0, full0 + 8 * s);
+        st_tma_load_2d(dst + ST_KB_BYTES, &tmZ, ST_BK, row0, full0 + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0 && my_tiles > 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(A >> 3) << 17) | ((uint32_t)(ST_BM >> 4) << 24);
+      st_mbar_wait(w_full, 0);
+      for (int64_t i = 0; i < my_tiles; ++i) {
+        const int s = (int)(i & 1);
+        const uint32_t ph = (uint32_t)((i >> 1) & 1);
+        st_mbar_wait(xform0 + 8 * s, ph);           // hi / lo of this tile are in place (and, transitively,
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");   //  accumulator s was drained)
+        const uint32_t zs = st_base + s * ST_STAGE_BYTES;
+        const uint32_t acc = tmem_base + (uint32_t)(s * A);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t a_hi = st_desc(zs + kb * ST_KB_BYTES), a_lo = st_desc(zs + (2 + kb) * ST_KB_BYTES);
+          const uint64_t b_hi = st_desc(w_base + kb * ST_KB_BYTES), b_lo = st_desc(w_base + (2 + kb) * ST_KB_BYTES);
+#pragma unroll
+          for (int k = 0; k < ST_BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            st_umma_tf32(acc, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+            st_umma_tf32(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+            st_umma_tf32(acc, a_hi + adv, b_hi + adv, idesc, 1u);
+          }
+        }
+        st_umma_commit(mma0 + 8 * s);
+      }
+    }
+  } else {
+    // ===== warps 2-5: split Z hi/lo (tile i+1), epilogue (tile i) =====
+    const int t = threadIdx.x - 64;   // 0..127 = row of the tile = TMEM lane
+    const int q = warp & 3;           // TMEM lane quarter this warp may read
+    auto split_tile = [&](int64_t i) {
+      const int s = (int)(i & 1);
+      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      st_mbar_wait(full0 + 8 * s, ph);
+      uint4* hi = reinterpret_cast<uint4*>(gen + ST_W_BYTES + s * ST_STAGE_BYTES);
+      uint4* lo = reinterpret_cast<uint4*>(gen + ST_W_BYTES + s * ST_STAGE_BYTES + 2 * ST_KB_BYTES);
+#pragma unroll
+      for (int j = 0; j < (int)(2 * ST_KB_BYTES / 16 / 128); ++j) {   // 16 x 16 B per thread, layout-agnostic
+        const int idx = t + 128 * j;
+        const uint4 x = hi[idx];
+        uint4 h, l;
+        h.x = x.x & 0xFFFFE000u; l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
+        h.y = x.y & 0xFFFFE000u; l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
+        h.z = x.z & 0xFFFFE000u; l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
+        h.w = x.w & 0xFFFFE000u; l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
+        hi[idx] = h;
+        lo[idx] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      st_mbar_arrive(xform0 + 8 * s);
+    };
+    if (my_tiles > 0) split_tile(0);
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      if (i + 1 < my_tiles) split_tile(i + 1);
+      const int s = (int)(i & 1);
+      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      const int64_t tile = blockIdx.x + i * gridDim.x;
+      const int64_t node0 = tile * nodes_per_tile;
+      const int64_t row0 = node0 * P;
+      const int rows_here = (int)min((int64_t)rows_per_tile, total_rows - row0);
+      st_mbar_wait(mma0 + 8 * s, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // ---- v = tanh(acc + b), s = v . u ; thread = row ----
+      const int r = q * 32 + lane;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * A);
+      float part = 0.f;
+      float* vrow = (vsave != nullptr && r < rows_here) ? vsave + (row0 + r) * A : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < A; c0 += 32) {
+        uint32_t acc[32];
+        st_tmem_ld32(lane_addr + c0, acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          float4 v;
+          v.x = tanhf(__uint_as_float(acc[c]) + par[c0 + c]);
+          v.y = tanhf(__uint_as_float(acc[c + 1]) + par[c0 + c + 1]);
+          v.z = tanhf(__uint_as_float(acc[c + 2]) + par[c0 + c + 2]);
+          v.w = tanhf(__uint_as_float(acc[c + 3]) + par[c0 + c + 3]);
+          part = fmaf(v.x, par[A + c0 + c], part);
+          part = fmaf(v.y, par[A + c0 + c + 1], part);
+          part = fmaf(v.z, par[A + c0 + c + 2], part);
+          part = fmaf(v.w, par[A + c0 + c + 3], part);
+          if (vrow != nullptr) *reinterpret_cast<float4*>(vrow + c0 + c) = v;
+        }
+      }
+      ss[r] = part;
+      if (scores != nullptr && r < rows_here) scores[row0 + r] = part;
+      st_bar_epi();
+      if (mode == HAN_SEM_REFERENCE) {
+        // per-node softmax over the P meta-paths (utils/layers.py:156): thread = row
+        float bt = 0.f;
+        if (r < rows_here) {
+          const int nl = r / P;
+          float mx = -INFINITY;
+          for (int p = 0; p < P; ++p) mx = fmaxf(mx, ss[nl * P + p]);
+          float sum = 0.f;
+          for (int p = 0; p < P; ++p) sum += expf(ss[nl * P + p] - mx);
+          bt = expf(ss[r] - mx) / sum;
+          beta[row0 + r] = bt;
+        }
+        bts[r] = bt;
+        st_bar_epi();
+        // out[n] = sum_p beta[n,p] Z[n,p] (:159) from the ring: Z = hi + lo exactly
+        const uint8_t* zhi = gen + ST_W_BYTES + s * ST_STAGE_BYTES;
+        const uint8_t* zlo = zhi + 2 * ST_KB_BYTES;
+        const int nodes_here = rows_here / P;
+        for (int item = t; item < nodes_here * (D / 4); item += 128) {
+          const int nl = item / (D / 4), c4 = item % (D / 4);
+          const int kb = c4 >> 3, cc = (c4 & 7) * 4;     // K-block, float column inside it
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int p = 0; p < P; ++p) {
+            const int rr = nl * P + p;
+            const uint32_t off = kb * ST_KB_BYTES + st_sw128(rr, cc);
+            const float4 h = *reinterpret_cast<const float4*>(zhi + off);
+            const float4 l = *reinterpret_cast<const float4*>(zlo + off);
+            const float bp = bts[rr];
+            o.x = fmaf(bp, h.x + l.x, o.x);
+            o.y = fmaf(bp, h.y + l.y, o.y);
+            o.z = fmaf(bp, h.z + l.z, o.z);
+            o.w = fmaf(bp, h.w + l.w, o.w);
+          }
+          *reinterpret_cast<float4*>(out + (node0 + nl) * D + 4 * c4) = o;
+        }
+      }
+      // this thread is done with accumulator s (tcgen05.ld completed above) and with ring slot s
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      st_mbar_arrive(free0 + 8 * s);
+      st_bar_epi();      // ss / bts are reused by the next tile
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+  }
+}
+
+typedef CUresult (*StEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int st_make_map(CUtensorMap* m, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_rows) {
+  static StEncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<StEncodeTiledFn>(p);
+  }
+  if (!fn) return fail_arg("han_semantic_fwd_tc", "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {ST_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_error, sizeof(g_last_error), "han_semantic_fwd_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return -2;
+  }
+  return 0;
+}
+
+}  // namespace han
+
+using namespace han;
+
+extern "C" {
+
+size_t han_semantic_tc_workspace_bytes(void) { return (size_t)2 * ST_A * ST_D * sizeof(float); }
+
+int han_semantic_fwd_tc(const float* Z, int64_t n, int P, int D, int A, const float* w, const float* b,
+                        const float* u, int mode, float* out, float* beta, float* vsave, float* scores, void* ws,
+                        size_t ws_bytes, han_stream_t stream) {
+  HAN_REQUIRE(Z && w && b && u && ws, "null pointer");
+  HAN_REQUIRE(D == ST_D && A == ST_A, "the tensor-core semantic forward is built for D = 64, A = 128");
+  HAN_REQUIRE(n > 0 && P > 0 && P <= 64 && n * P < ((int64_t)1 << 31), "n > 0, 1 <= P <= 64, n*P < 2^31");
+  HAN_REQUIRE(mode == HAN_SEM_REFERENCE || mode == HAN_SEM_PAPER, "mode");
+  HAN_REQUIRE(mode == HAN_SEM_PAPER || (out && beta), "reference mode needs out and beta");
+  HAN_REQUIRE(mode == HAN_SEM_REFERENCE || scores, "paper mode needs scores");
+  HAN_REQUIRE(ws_bytes >= han_semantic_tc_workspace_bytes(), "workspace too small");
+  HAN_REQUIRE(((uintptr_t)Z % 16 == 0) && ((uintptr_t)ws % 16 == 0) && ((uintptr_t)vsave % 16 == 0) &&
+              ((uintptr_t)out % 16 == 0), "16-byte alignment");
+  cudaStream_t st = as_stream(stream);
+  float* wt_hi = reinterpret_cast<float*>(ws);
+  float* wt_lo = wt_hi + ST_A * ST_D;
+  st_wt_split_kernel<<<(ST_A * ST_D + 255) / 256, 256, 0, st>>>(w, wt_hi, wt_lo);
+  CUtensorMap tmZ, tmWhi, tmWlo;
+  int rc = st_make_map(&tmZ, Z, ST_D, (uint64_t)(n * P), ST_D, ST_BM);
+  if (rc) return rc;
+  rc = st_make_map(&tmWhi, wt_hi, ST_D, ST_A, ST_D, ST_A);
+  if (rc) return rc;
+  rc = st_make_map(&tmWlo, wt_lo, ST_D, ST_A, ST_D, ST_A);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(semantic_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES);
+    attr = true;
+  }
+  const int64_t n_tiles = ceil_div64(n, ST_BM / P);
+  const unsigned grid = (unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+  semantic_fwd_tc_kernel<<<grid, ST_THREADS, ST_SMEM_BYTES, st>>>(tmZ, tmWhi, tmWlo, n, P, b, u, mode, out, beta, vsave,
+                                                                 scores);
+  return check_launch(__func__);
+}
+
+}  // extern "C"

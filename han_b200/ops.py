@@ -27,6 +27,8 @@ L2_BLOCKS = int(_os.environ.get("HAN_L2_BLOCKS", "0"))
 # accumulated inside the by-source pass with 16-byte vector reductions that resolve in L2 (no per-edge dl array,
 # no by-destination pass): ~2 % faster on the 2M config, summation order not fixed run to run.
 DETERMINISTIC = _os.environ.get("HAN_DF1_RED", "0") != "1"
+# EXPERIMENTAL: semantic forward on tcgen05 (semantic_tc.cu); off until validated on hardware
+SEM_TC = _os.environ.get("HAN_SEM_TC", "0") == "1"
 
 
 def _empty(shape, device, dtype=torch.float32):
@@ -350,14 +352,21 @@ class SemanticAttentionFn(torch.autograd.Function):
             out = _empty((n, D), dev)
             beta = _empty((n, P), dev)
             vsave = _empty((n * P, A), dev)
+            def fwd(out_, beta_, scores_):
+                if SEM_TC and (D, A) == (64, 128) and P <= 64:
+                    ws_bytes = query("han_semantic_tc_workspace_bytes")
+                    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                    call("han_semantic_fwd_tc", ptr(Z), n, P, D, A, ptr(w), ptr(b), ptr(u), mode, ptr(out_), ptr(beta_),
+                         ptr(vsave), ptr(scores_), ptr(ws), ws_bytes, stream_ptr())
+                else:
+                    call("han_semantic_fwd", ptr(Z), n, P, D, A, ptr(w), ptr(b), ptr(u), mode, ptr(out_), ptr(beta_),
+                         ptr(vsave), ptr(scores_), stream_ptr())
             if mode == _lib.SEM_REFERENCE:
-                call("han_semantic_fwd", ptr(Z), n, P, D, A, ptr(w), ptr(b), ptr(u), mode, ptr(out),
-                     ptr(beta), ptr(vsave), None, stream_ptr())
+                fwd(out, beta, None)
                 beta_vec = None
             else:
                 scores = _empty((n, P), dev)
-                call("han_semantic_fwd", ptr(Z), n, P, D, A, ptr(w), ptr(b), ptr(u), mode, None, None,
-                     ptr(vsave), ptr(scores), stream_ptr())
+                fwd(None, None, scores)
                 ssum = scores.sum(0, dtype=torch.float64)      # P scalars: reduce over nodes in fp64
                 n_total = n
                 if dist is not None:

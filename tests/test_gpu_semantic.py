@@ -62,3 +62,16 @@ def test_time_major_and_no_alphas():
     a = hb.layers.SimpleAttLayer(Z, 128, time_major=True, params=sp)
     b, _ = hb.layers.SimpleAttLayer(Z.transpose(0, 1).contiguous(), 128, return_alphas=True, params=sp)
     assert torch.equal(a, b)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("HAN_SEM_TC", "0") != "1",
+                    reason="experimental tcgen05 semantic forward (semantic_tc.cu): opt-in, run with HAN_SEM_TC=1")
+@pytest.mark.parametrize("mode", ["reference", "paper"])
+@pytest.mark.parametrize("n,P", [(300, 2), (257, 3), (40000, 4), (65, 1), (5000, 5)])
+def test_semantic_forward_on_tcgen05_matches_oracle(mode, n, P):
+    """HAN_SEM_TC=1 routes the (64, 128) forward through han_semantic_fwd_tc (persistent CTAs, TMA ring,
+    double-buffered TMEM); the backward stays the mma.sync kernel and consumes the v it saved.  Several tiles
+    per CTA (n*P / 128 > 148), partial last tiles, P that does not divide 128."""
+    from han_b200 import ops
+    assert ops.SEM_TC
+    _run(n, P, 64, 128, mode, seed=n + 11 * P)
