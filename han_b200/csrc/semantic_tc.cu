@@ -1,7 +1,7 @@
 // K-C on 5th-generation tensor cores (EXPERIMENTAL, opt-in: HAN_SEM_TC=1; the shipped path is the
 // mma.sync kernel in semantic.cu).  Status: parity-green on B200 (tests/test_gpu_semantic.py), 2.60 ms vs
-// 2.78 ms on the 2M-node config -- the four epilogue warps (tanh + scattered v stores) are the bound now.  Semantic attention forward, utils/layers.py:152-159, for the shipped
-// shape D = 64, A = 128:
+// 2.78 ms on the 2M-node config -- the four epilogue warps (tanh + scattered v stores) are the bound now.
+// Semantic attention forward, utils/layers.py:152-159, for the shipped shape D = 64, A = 128:
 //
 //   v = tanh(Z w + b)   s = v . u   beta = softmax_P(s) per node   out[n] = sum_p beta[n,p] Z[n,p]
 //
