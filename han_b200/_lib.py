@@ -70,7 +70,7 @@ _SIGNATURES = {
     "han_semantic_bwd_workspace_bytes": (SZ, [I, I, I]),
     "han_semantic_bwd": (c_int, [P, P, P, P, I64, I, I, I, P, P, I, P, P, P, P, P, P, SZ, P]),
     "han_semantic_tc_workspace_bytes": (SZ, []),
-    "han_semantic_fwd_tc": (c_int, [P, I64, I, I, I, P, P, P, I, P, P, P, P, P, SZ, P]),
+    "han_semantic_fwd_tc": (c_int, [P, I64, I, I, I, P, P, P, I, P, P, P, P, P, SZ, I, P]),
     "han_adam_l2_step": (c_int, [P, P, P, P, I64, P, FL, FL, FL, FL, FL, P]),
     "han_project_dx": (c_int, [P, I64, I, I, P, I64, I64, P, I64, I, P, FL, I, I64, P]),
 }

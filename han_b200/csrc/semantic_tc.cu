@@ -28,11 +28,12 @@ namespace han {
 constexpr int ST_BM = 128;                     // rows per tile
 constexpr int ST_D = 64, ST_A = 128;
 constexpr int ST_BK = 32;                      // fp32 K elements per 128-byte swizzle span
-constexpr int ST_THREADS = 192;
+constexpr int ST_MAX_EG = 4;                   // epilogue groups: 4 warps each (one per TMEM lane quarter), splitting the columns
 constexpr uint32_t ST_KB_BYTES = ST_BM * ST_BK * 4;          // one K-block of a 128-row operand: 16 KB
 constexpr uint32_t ST_W_BYTES = 2 * 2 * ST_KB_BYTES;         // w^T: hi | lo, 2 K-blocks each: 64 KB
 constexpr uint32_t ST_STAGE_BYTES = 2 * 2 * ST_KB_BYTES;     // Z tile: hi (2 K-blocks) | lo (2 K-blocks): 64 KB
-constexpr uint32_t ST_SMEM_BYTES = 1024 + ST_W_BYTES + 2 * ST_STAGE_BYTES + 4 * (2 * ST_A + 2 * ST_BM) + 256;
+constexpr int ST_PAR_FLOATS = 2 * ST_A + ST_MAX_EG * ST_BM + ST_BM;          // b | u | partial scores [EG][128] | beta [128]
+constexpr uint32_t ST_SMEM_BYTES = 1024 + ST_W_BYTES + 2 * ST_STAGE_BYTES + 4 * ST_PAR_FLOATS + 256;
 constexpr uint32_t kStSpinLimit = 1u << 28;
 
 __device__ __forceinline__ uint32_t st_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -101,7 +102,8 @@ __device__ __forceinline__ uint64_t st_desc(uint32_t smem_addr) {
 __device__ __forceinline__ uint32_t st_sw128(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 2) ^ (r & 7)) << 4)) + (c & 3) * 4);
 }
-__device__ __forceinline__ void st_bar_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int NT>
+__device__ __forceinline__ void st_bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
 // w [D][A] -> w^T hi / lo [A][D] (K-major operand B)
 __global__ void st_wt_split_kernel(const float* __restrict__ w, float* __restrict__ wt_hi, float* __restrict__ wt_lo) {
@@ -114,7 +116,11 @@ __global__ void st_wt_split_kernel(const float* __restrict__ w, float* __restric
   wt_lo[idx] = x - hi;
 }
 
-__global__ void __launch_bounds__(ST_THREADS, 1)
+// EG = 1 is the configuration validated on hardware (four epilogue warps, each thread a whole row of 128
+// columns); EG = 2 / 4 give every row to 2 / 4 threads of different warp groups (64 / 32 columns each) so that
+// 2 / 4 epilogue warps per scheduler hide each other's tanh and store latencies.
+template <int EG>
+__global__ void __launch_bounds__(64 + 128 * EG, 1)
 semantic_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmWhi,
                        const __grid_constant__ CUtensorMap tmWlo, int64_t n, int P, const float* __restrict__ b,
                        const float* __restrict__ u, int mode, float* __restrict__ out, float* __restrict__ beta,
@@ -127,9 +133,10 @@ semantic_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
   const uint32_t w_base = base;
   const uint32_t st_base = base + ST_W_BYTES;
   float* par = reinterpret_cast<float*>(gen + ST_W_BYTES + 2 * ST_STAGE_BYTES);   // b[128] | u[128]
-  float* ss = par + 2 * A;                                                        // [128] scores of the tile
-  float* bts = ss + ST_BM;                                                        // [128] beta of the tile
-  const uint32_t bars = base + ST_W_BYTES + 2 * ST_STAGE_BYTES + 4 * (2 * A + 2 * ST_BM);
+  float* ss = par + 2 * A;                                                        // [EG][128] partial scores of the tile
+  float* bts = ss + ST_MAX_EG * ST_BM;                                            // [128] beta of the tile
+  const uint32_t bars = base + ST_W_BYTES + 2 * ST_STAGE_BYTES + 4 * ST_PAR_FLOATS;
+  constexpr int NEPI = 128 * EG;                                                  // splitter / epilogue threads
   const uint32_t w_full = bars, full0 = bars + 8, xform0 = bars + 24, mma0 = bars + 40, free0 = bars + 56;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bars + 80 - base));
 
@@ -140,7 +147,7 @@ semantic_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
   const int64_t n_tiles = ceil_div64(n, nodes_per_tile);
   const int64_t my_tiles = (n_tiles > (int64_t)blockIdx.x) ? ceil_div64(n_tiles - blockIdx.x, gridDim.x) : 0;
 
-  for (int i = threadIdx.x; i < A; i += ST_THREADS) {
+  for (int i = threadIdx.x; i < A; i += 64 + NEPI) {
     par[i] = b[i];
     par[A + i] = u[i];
   }
@@ -148,9 +155,9 @@ semantic_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
     st_mbar_init(w_full, 1);
     for (int s = 0; s < 2; ++s) {
       st_mbar_init(full0 + 8 * s, 1);
-      st_mbar_init(xform0 + 8 * s, 128);
+      st_mbar_init(xform0 + 8 * s, NEPI);
       st_mbar_init(mma0 + 8 * s, 1);
-      st_mbar_init(free0 + 8 * s, 128);
+      st_mbar_init(free0 + 8 * s, NEPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -213,9 +220,10 @@ semantic_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
       }
     }
   } else {
-    // ===== warps 2-5: split Z hi/lo (tile i+1), epilogue (tile i) =====
-    const int t = threadIdx.x - 64;   // 0..127 = row of the tile = TMEM lane
-    const int q = warp & 3;           // TMEM lane quarter this warp may read
+    // ===== warps 2..: split Z hi/lo (tile i+1), epilogue (tile i) =====
+    const int t = threadIdx.x - 64;   // 0 .. NEPI-1
+    const int grp = t >> 7;           // column group of this thread's warp group
+    const int q = warp & 3;           // TMEM lane quarter this warp may read (warp id % 4)
     auto split_tile = [&](int64_t i) {
       const int s = (int)(i & 1);
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
@@ -223,8 +231,8 @@ semantic_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
       uint4* hi = reinterpret_cast<uint4*>(gen + ST_W_BYTES + s * ST_STAGE_BYTES);
       uint4* lo = reinterpret_cast<uint4*>(gen + ST_W_BYTES + s * ST_STAGE_BYTES + 2 * ST_KB_BYTES);
 #pragma unroll
-      for (int j = 0; j < (int)(2 * ST_KB_BYTES / 16 / 128); ++j) {   // 16 x 16 B per thread, layout-agnostic
-        const int idx = t + 128 * j;
+      for (int j = 0; j < (int)(2 * ST_KB_BYTES / 16 / NEPI); ++j) {   // 16 / EG x 16 B per thread, layout-agnostic
+        const int idx = t + NEPI * j;
         const uint4 x = hi[idx];
         uint4 h, l;
         h.x = x.x & 0xFFFFE000u; l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
@@ -254,7 +262,7 @@ semantic_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
       float part = 0.f;
       float* vrow = (vsave != nullptr && r < rows_here) ? vsave + (row0 + r) * A : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < A; c0 += 32) {
+      for (int c0 = grp * (A / EG); c0 < (grp + 1) * (A / EG); c0 += 32) {
         uint32_t acc[32];
         st_tmem_ld32(lane_addr + c0, acc);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -272,28 +280,36 @@ semantic_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
           if (vrow != nullptr) *reinterpret_cast<float4*>(vrow + c0 + c) = v;
         }
       }
-      ss[r] = part;
-      if (scores != nullptr && r < rows_here) scores[row0 + r] = part;
-      st_bar_epi();
+      ss[grp * ST_BM + r] = part;
+      st_bar_epi<NEPI>();
+      auto score_of = [&](int row) {      // column groups summed in a fixed order
+        float sc = ss[row];
+#pragma unroll
+        for (int g = 1; g < EG; ++g) sc += ss[g * ST_BM + row];
+        return sc;
+      };
+      if (grp == 0 && scores != nullptr && r < rows_here) scores[row0 + r] = score_of(r);
       if (mode == HAN_SEM_REFERENCE) {
-        // per-node softmax over the P meta-paths (utils/layers.py:156): thread = row
-        float bt = 0.f;
-        if (r < rows_here) {
-          const int nl = r / P;
-          float mx = -INFINITY;
-          for (int p = 0; p < P; ++p) mx = fmaxf(mx, ss[nl * P + p]);
-          float sum = 0.f;
-          for (int p = 0; p < P; ++p) sum += expf(ss[nl * P + p] - mx);
-          bt = expf(ss[r] - mx) / sum;
-          beta[row0 + r] = bt;
+        // per-node softmax over the P meta-paths (utils/layers.py:156): thread = row (group 0 only)
+        if (grp == 0) {
+          float bt = 0.f;
+          if (r < rows_here) {
+            const int nl = r / P;
+            float mx = -INFINITY;
+            for (int p = 0; p < P; ++p) mx = fmaxf(mx, score_of(nl * P + p));
+            float sum = 0.f;
+            for (int p = 0; p < P; ++p) sum += expf(score_of(nl * P + p) - mx);
+            bt = expf(score_of(r) - mx) / sum;
+            beta[row0 + r] = bt;
+          }
+          bts[r] = bt;
         }
-        bts[r] = bt;
-        st_bar_epi();
+        st_bar_epi<NEPI>();
         // out[n] = sum_p beta[n,p] Z[n,p] (:159) from the ring: Z = hi + lo exactly
         const uint8_t* zhi = gen + ST_W_BYTES + s * ST_STAGE_BYTES;
         const uint8_t* zlo = zhi + 2 * ST_KB_BYTES;
         const int nodes_here = rows_here / P;
-        for (int item = t; item < nodes_here * (D / 4); item += 128) {
+        for (int item = t; item < nodes_here * (D / 4); item += NEPI) {
           const int nl = item / (D / 4), c4 = item % (D / 4);
           const int kb = c4 >> 3, cc = (c4 & 7) * 4;     // K-block, float column inside it
           float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -314,7 +330,7 @@ semantic_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
       // this thread is done with accumulator s (tcgen05.ld completed above) and with ring slot s
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       st_mbar_arrive(free0 + 8 * s);
-      st_bar_epi();      // ss / bts are reused by the next tile
+      st_bar_epi<NEPI>();      // ss / bts are reused by the next tile
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -363,7 +379,8 @@ size_t han_semantic_tc_workspace_bytes(void) { return (size_t)2 * ST_A * ST_D * 
 
 int han_semantic_fwd_tc(const float* Z, int64_t n, int P, int D, int A, const float* w, const float* b,
                         const float* u, int mode, float* out, float* beta, float* vsave, float* scores, void* ws,
-                        size_t ws_bytes, han_stream_t stream) {
+                        size_t ws_bytes, int epilogue_groups, han_stream_t stream) {
+  HAN_REQUIRE(epilogue_groups == 1 || epilogue_groups == 2 || epilogue_groups == 4, "epilogue_groups in {1, 2, 4}");
   HAN_REQUIRE(Z && w && b && u && ws, "null pointer");
   HAN_REQUIRE(D == ST_D && A == ST_A, "the tensor-core semantic forward is built for D = 64, A = 128");
   HAN_REQUIRE(n > 0 && P > 0 && P <= 64 && n * P < ((int64_t)1 << 31), "n > 0, 1 <= P <= 64, n*P < 2^31");
@@ -386,13 +403,22 @@ int han_semantic_fwd_tc(const float* Z, int64_t n, int P, int D, int A, const fl
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(semantic_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES);
+    cudaFuncSetAttribute(semantic_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES);
+    cudaFuncSetAttribute(semantic_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES);
+    cudaFuncSetAttribute(semantic_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES);
     attr = true;
   }
   const int64_t n_tiles = ceil_div64(n, ST_BM / P);
   const unsigned grid = (unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
-  semantic_fwd_tc_kernel<<<grid, ST_THREADS, ST_SMEM_BYTES, st>>>(tmZ, tmWhi, tmWlo, n, P, b, u, mode, out, beta, vsave,
-                                                                 scores);
+  if (epilogue_groups == 1)
+    semantic_fwd_tc_kernel<1><<<grid, 64 + 128, ST_SMEM_BYTES, st>>>(tmZ, tmWhi, tmWlo, n, P, b, u, mode, out, beta,
+                                                                   vsave, scores);
+  else if (epilogue_groups == 2)
+    semantic_fwd_tc_kernel<2><<<grid, 64 + 256, ST_SMEM_BYTES, st>>>(tmZ, tmWhi, tmWlo, n, P, b, u, mode, out, beta,
+                                                                   vsave, scores);
+  else
+    semantic_fwd_tc_kernel<4><<<grid, 64 + 512, ST_SMEM_BYTES, st>>>(tmZ, tmWhi, tmWlo, n, P, b, u, mode, out, beta,
+                                                                   vsave, scores);
   return check_launch(__func__);
 }
 

@@ -29,7 +29,7 @@ L2_BLOCKS = int(_os.environ.get("HAN_L2_BLOCKS", "0"))
 DETERMINISTIC = _os.environ.get("HAN_DF1_RED", "0") != "1"
 # EXPERIMENTAL: semantic forward on tcgen05 (semantic_tc.cu): parity-green, 7 % faster than the mma.sync kernel
 # (epilogue-bound); off by default until its epilogue is widened
-SEM_TC = _os.environ.get("HAN_SEM_TC", "0") == "1"
+SEM_TC = int(_os.environ.get("HAN_SEM_TC", "0") or 0)      # 0 off | 1, 2, 4 = epilogue groups (1 is the validated one)
 
 
 def _empty(shape, device, dtype=torch.float32):
@@ -358,7 +358,7 @@ class SemanticAttentionFn(torch.autograd.Function):
                     ws_bytes = query("han_semantic_tc_workspace_bytes")
                     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                     call("han_semantic_fwd_tc", ptr(Z), n, P, D, A, ptr(w), ptr(b), ptr(u), mode, ptr(out_), ptr(beta_),
-                         ptr(vsave), ptr(scores_), ptr(ws), ws_bytes, stream_ptr())
+                         ptr(vsave), ptr(scores_), ptr(ws), ws_bytes, int(SEM_TC), stream_ptr())
                 else:
                     call("han_semantic_fwd", ptr(Z), n, P, D, A, ptr(w), ptr(b), ptr(u), mode, ptr(out_), ptr(beta_),
                          ptr(vsave), ptr(scores_), stream_ptr())

@@ -272,11 +272,13 @@ int han_semantic_fwd(const float* Z, int64_t n, int P, int D, int A, const float
  * config -- epilogue-bound, hence not the default): the same forward for D = 64, A = 128 on
  * tcgen05 tensor cores -- persistent CTAs, w^T resident in shared memory, TMA ring for Z, 3xTF32 accumulation in
  * double-buffered TMEM, epilogue of tile i under the MMAs of tile i+1 (han_b200/csrc/semantic_tc.cu).
- * ws: han_semantic_tc_workspace_bytes() bytes (the transposed hi/lo split of w). */
+ * ws: han_semantic_tc_workspace_bytes() bytes (the transposed hi/lo split of w).  epilogue_groups: 1 (the
+ * validated configuration: 4 epilogue warps) or 2 / 4 (8 / 16 epilogue warps sharing each row's columns; written
+ * after the GPU budget of round 1 ran out, to be validated). */
 size_t han_semantic_tc_workspace_bytes(void);
 int han_semantic_fwd_tc(const float* Z, int64_t n, int P, int D, int A, const float* w, const float* b,
                         const float* u, int mode, float* out, float* beta, float* vsave, float* scores, void* ws,
-                        size_t ws_bytes, han_stream_t stream);
+                        size_t ws_bytes, int epilogue_groups, han_stream_t stream);
 /* out[n] = sum_p beta_vec[p] Z[n,p]; beta (nullable) [n][P] receives the broadcast (han.pdf Eq. 9). */
 int han_semantic_combine(const float* Z, int64_t n, int P, int D, const float* beta_vec, float* out,
                          float* beta, han_stream_t stream);
