@@ -36,6 +36,33 @@ def _as_device_tensor(a, device, dtype=None) -> torch.Tensor:
 SPLIT_ROW_EDGES = int(os.environ.get("HAN_SPLIT_ROW_EDGES", "4096"))
 
 
+def split_layout(indptr: torch.Tensor, S: int):
+    """Index arithmetic of ``MetaPathGraph.split_view`` (any device): cut every row of the CSR ``indptr`` with
+    more than S edges into ceil(deg/S) segments of at most S edges.  Returns
+    (indptr_v int64[n_v+1], vptr int64[n+1], vmap int32[n_v][2] = (real row, partial slot or -1),
+    heavy_rows int32[n_h], heavy_ptr int32[n_h+1], n_slots)."""
+    dev = indptr.device
+    n = indptr.numel() - 1
+    deg = indptr[1:] - indptr[:-1]
+    nseg = torch.clamp((deg + (S - 1)) // S, min=1)
+    vptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    vptr[1:] = torch.cumsum(nseg, 0)
+    vrow = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), nseg)
+    n_v = int(vrow.numel())
+    seg = torch.arange(n_v, device=dev, dtype=torch.int64) - vptr[vrow]
+    indptr_v = torch.empty(n_v + 1, dtype=torch.int64, device=dev)
+    indptr_v[:-1] = indptr[vrow] + seg * S
+    indptr_v[-1] = indptr[-1]
+    heavy = nseg > 1
+    hv_v = heavy[vrow]
+    slot = torch.cumsum(hv_v.to(torch.int64), 0) - 1
+    vmap = torch.stack([vrow, torch.where(hv_v, slot, torch.full_like(slot, -1))], 1).to(torch.int32).contiguous()
+    heavy_rows = torch.nonzero(heavy).reshape(-1).to(torch.int32)
+    heavy_ptr = torch.zeros(heavy_rows.numel() + 1, dtype=torch.int32, device=dev)
+    heavy_ptr[1:] = torch.cumsum(nseg[heavy], 0).to(torch.int32)
+    return indptr_v, vptr, vmap, heavy_rows, heavy_ptr, int(hv_v.sum().item())
+
+
 @dataclass
 class SplitView:
     indptr_v: torch.Tensor      # int64 [n_v+1]: the CSR offsets with the cut points inserted
@@ -248,27 +275,13 @@ class MetaPathGraph:
             if self.nnz > 0 and int(deg.max().item()) > S:
                 dev, n = self.device, self.n_rows
                 with torch.cuda.device(dev):
-                    nseg = torch.clamp((deg + (S - 1)) // S, min=1)
-                    vptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-                    vptr[1:] = torch.cumsum(nseg, 0)
-                    vrow = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), nseg)
-                    n_v = int(vrow.numel())
-                    seg = torch.arange(n_v, device=dev, dtype=torch.int64) - vptr[vrow]
-                    indptr_v = torch.empty(n_v + 1, dtype=torch.int64, device=dev)
-                    indptr_v[:-1] = self.indptr[vrow] + seg * S
-                    indptr_v[-1] = self.nnz
-                    heavy = nseg > 1
-                    hv_v = heavy[vrow]
-                    slot = torch.cumsum(hv_v.to(torch.int64), 0) - 1
-                    vmap = torch.stack([vrow, torch.where(hv_v, slot, torch.full_like(slot, -1))], 1).to(torch.int32).contiguous()
-                    heavy_rows = torch.nonzero(heavy).reshape(-1).to(torch.int32)
-                    heavy_ptr = torch.zeros(heavy_rows.numel() + 1, dtype=torch.int32, device=dev)
-                    heavy_ptr[1:] = torch.cumsum(nseg[heavy], 0).to(torch.int32)
+                    indptr_v, vptr, vmap, heavy_rows, heavy_ptr, n_slots = split_layout(self.indptr, S)
+                    n_v = int(indptr_v.numel()) - 1
                     n_chunks = int(query("han_csr_num_chunks", self.nnz))
                     cr = torch.empty(n_chunks + 1, dtype=torch.int32, device=dev)
                     call("han_csr_chunk_rows", ptr(indptr_v), n_v, self.nnz, ptr(cr), stream_ptr())
                 self._split = SplitView(indptr_v, vptr, vmap, heavy_rows, heavy_ptr, cr, n_chunks, n_v,
-                                        int(heavy_rows.numel()), int(hv_v.sum().item()))
+                                        int(heavy_rows.numel()), n_slots)
         return self._split
 
     def source_blocks(self, n_blocks: int):

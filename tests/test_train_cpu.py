@@ -45,3 +45,34 @@ def test_knn_and_kmeans_protocol_on_separable_embeddings(capsys):
     assert nmi > 0.8 and ari > 0.8
     out = capsys.readouterr().out
     assert "KNN(3avg, split:0.2, k=5)" in out and "NMI (2 avg)" in out
+
+
+def test_split_layout_cuts_heavy_rows_exactly():
+    """Index arithmetic of MetaPathGraph.split_view (heavy-row splitting) on CPU tensors:
+    empty rows, rows of exactly S / k*S / k*S+1 edges, no heavy row at all."""
+    import torch
+    from han_b200.graph import split_layout
+    rng = np.random.default_rng(0)
+    for S, degs in ((4, [0, 1, 4, 5, 8, 9, 0, 3, 17, 4]), (16, list(rng.integers(0, 100, size=200))), (8, [3, 2, 1]),
+                    (1, [2, 0, 3])):
+        deg = np.asarray(degs, dtype=np.int64)
+        indptr = np.concatenate([[0], np.cumsum(deg)])
+        iv, vptr, vmap, hrows, hptr, n_slots = split_layout(torch.from_numpy(indptr), S)
+        iv, vptr, vmap, hrows, hptr = (t.numpy() for t in (iv, vptr, vmap, hrows, hptr))
+        nseg = np.maximum(1, -(-deg // S))
+        # every real offset survives, segments are at most S long, lengths per row add up
+        assert iv[0] == 0 and iv[-1] == indptr[-1] and (np.diff(iv) <= S).all() and (np.diff(iv) >= 0).all()
+        assert np.array_equal(vptr, np.concatenate([[0], np.cumsum(nseg)]))
+        assert np.array_equal(iv[vptr[:-1]], indptr[:-1])
+        for r in range(len(deg)):
+            segs = np.diff(iv[vptr[r]:vptr[r + 1] + 1])
+            assert segs.sum() == deg[r] and (vmap[vptr[r]:vptr[r + 1], 0] == r).all()
+            if nseg[r] > 1:
+                assert (segs[:-1] == S).all() and 1 <= segs[-1] <= S
+        # cut rows own consecutive partial slots in row order; whole rows own none
+        heavy = np.nonzero(nseg > 1)[0]
+        assert np.array_equal(hrows, heavy) and n_slots == nseg[heavy].sum() == hptr[-1]
+        assert np.array_equal(hptr, np.concatenate([[0], np.cumsum(nseg[heavy])]))
+        slots = vmap[:, 1]
+        assert (slots[np.isin(vmap[:, 0], heavy)] == np.arange(n_slots)).all()
+        assert (slots[~np.isin(vmap[:, 0], heavy)] == -1).all()
