@@ -27,6 +27,11 @@ L2_BLOCKS = int(_os.environ.get("HAN_L2_BLOCKS", "0"))
 # accumulated inside the by-source pass with 16-byte vector reductions that resolve in L2 (no per-edge dl array,
 # no by-destination pass): ~2 % faster on the 2M config, summation order not fixed run to run.
 DETERMINISTIC = _os.environ.get("HAN_DF1_RED", "0") != "1"
+# EXPERIMENTAL (written after round 1's GPU budget ran out, to be validated): when a meta-path is split over a PAIR
+# of ranks (tile sharding, NCCL exchange), run the forward on the edges whose source is local while the partner's
+# node-table rows are still in flight, then on the rest, and merge the partial softmax states (the kernels of the
+# heavy-row path).  Hides the pair's T exchange (~0.55 ms of a 15.1 ms step at 8 GPUs).
+LOCAL_FIRST = _os.environ.get("HAN_TILE_LOCAL_FIRST", "0") == "1"
 # EXPERIMENTAL: semantic forward on tcgen05 (semantic_tc.cu): parity-green, 7 % faster than the mma.sync kernel
 # (epilogue-bound); off by default until its epilogue is widened
 SEM_TC = int(_os.environ.get("HAN_SEM_TC", "0") or 0)      # 0 off | 1, 2, 4 = epilogue groups (1 is the validated one)
@@ -161,7 +166,26 @@ class NodeAttentionFn(torch.autograd.Function):
                     # dense-path semantics of an all -1e9 row: uniform 1/N over all nodes
                     colmean = T_src[g][:, :D].mean(0).contiguous()
                 sv = graph.split_view() if CHUNKED else None
-                if CHUNKED and L2_BLOCKS > 1 and sv is None and dist is None and not graph.has_empty_rows():
+                if (CHUNKED and LOCAL_FIRST and tabs is None and dist is not None and dist.world == 2 and sv is None
+                        and not graph.has_empty_rows()):
+                    import ctypes
+                    subs, vmaps, all_rows, all_ptr = graph.source_blocks(2)     # block b = sources owned by rank b
+                    part = _empty((n * 2, K, H + 2), dev)
+                    me = dist.rank
+                    lo_src = dist.row_range(dist.n_total)[0]
+                    # local table addressed by GLOBAL source id: row j of the full table is local row j - lo
+                    T_local = ctypes.c_void_p(T[g].data_ptr() - lo_src * TS * 4)
+                    for b, table in ((me, T_local), (1 - me, None)):
+                        if table is None:
+                            table = ptr(T_src[g])          # waits for the partner's rows only now
+                        cr, n_chunks = subs[b].chunks()
+                        call("han_attn_fwd_chunked_split", ptr(subs[b].indptr), ptr(subs[b].indices), ptr(cr), n_chunks,
+                             n, table, ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D, ptr(V[g]),
+                             None, ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), row0, ptr(vmaps[b]),
+                             ptr(part), None, None, 0, stream_ptr(), kernels=1)
+                    call("han_attn_fwd_merge", ptr(all_rows), ptr(all_ptr), n, ptr(part), ptr(R[g]), ptr(bias[g]), K, H,
+                         plan.act, ptr(Z[:, g, :]), G * D, ptr(V[g]), stream_ptr())
+                elif CHUNKED and L2_BLOCKS > 1 and sv is None and dist is None and not graph.has_empty_rows():
                     B = L2_BLOCKS
                     subs, vmaps, all_rows, all_ptr = graph.source_blocks(B)
                     part = _empty((n * B, K, H + 2), dev)
