@@ -427,7 +427,8 @@ def run_e2e(args, wl, hp, train, dist, dev, step):
                 x_ready.record(copy_s)
                 mark("X on device", copy_s)
             if dist:
-                main.wait_stream(copy_s)
+                for g in graphs:
+                    g.wait_ready()          # the graphs have landed; the feature matrix may still be on PCIe
                 if hasattr(dist, "reset"):
                     dist.reset()
                 else:
