@@ -155,6 +155,53 @@ class BaseGAttN:
         mask = mask / mask.mean()
         return (correct * mask).mean()
 
+    # ---- the remaining helpers of the reference class (metric / loss glue outside the hot path; stock ops) ----
+    @staticmethod
+    def loss(logits, labels, nb_classes, class_weights):
+        """models/base_gattn.py:5-10: class-weighted sparse softmax cross-entropy, mean over samples.
+        logits (M,C); labels (M,) integer classes; class_weights (C,)."""
+        labels = labels.long()
+        w = torch.as_tensor(class_weights, dtype=logits.dtype, device=logits.device)[labels]      # one_hot . weights
+        xent = torch.nn.functional.cross_entropy(logits, labels, reduction="none")
+        return (xent * w).mean()
+
+    @staticmethod
+    def preshape(logits, labels, nb_classes):
+        """models/base_gattn.py:26-32."""
+        return logits.reshape(-1, nb_classes), labels.reshape(-1)
+
+    @staticmethod
+    def confmat(logits, labels):
+        """models/base_gattn.py:34-36: confusion matrix, rows = true class, columns = predicted class."""
+        preds = logits.argmax(1)
+        labels = labels.long()
+        n = int(max(int(preds.max()), int(labels.max())) + 1) if labels.numel() else 0
+        return torch.bincount(labels * n + preds, minlength=n * n).reshape(n, n)
+
+    @staticmethod
+    def masked_sigmoid_cross_entropy(logits, labels, mask):
+        """models/base_gattn.py:52-62 (multi-label nodes): per-node mean of the element-wise sigmoid
+        cross-entropy, then the same mask normalisation as the softmax variant."""
+        labels = labels.to(logits.dtype)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, labels, reduction="none").mean(1)
+        mask = mask.to(logits.dtype)
+        mask = mask / mask.mean()
+        return (loss * mask).mean()
+
+    @staticmethod
+    def micro_f1(logits, labels, mask):
+        """models/base_gattn.py:75-101: micro-averaged F1 of round(sigmoid(logits)) over the masked nodes,
+        counted in integers."""
+        predicted = torch.round(torch.sigmoid(logits)).to(torch.int64)
+        labels = labels.to(torch.int64)
+        mask = mask.to(torch.int64).unsqueeze(-1)
+        tp = torch.count_nonzero(predicted * labels * mask)
+        fp = torch.count_nonzero(predicted * (labels - 1) * mask)
+        fn = torch.count_nonzero((predicted - 1) * labels * mask)
+        precision = tp / (tp + fp)
+        recall = tp / (tp + fn)
+        return (2 * precision * recall / (precision + recall)).to(torch.float32)
+
     @staticmethod
     def training(params, lr, l2_coef) -> TrainOp:
         """models/base_gattn.py:12-24.  TF's version takes the loss tensor of a static graph; in eager

@@ -76,3 +76,32 @@ def test_split_layout_cuts_heavy_rows_exactly():
         slots = vmap[:, 1]
         assert (slots[np.isin(vmap[:, 0], heavy)] == np.arange(n_slots)).all()
         assert (slots[~np.isin(vmap[:, 0], heavy)] == -1).all()
+
+
+def test_base_gattn_metric_helpers_match_their_definitions():
+    """models/base_gattn.py:5-10,26-36,52-62,75-101 restated with stock torch ops: checked against numpy / sklearn."""
+    import torch
+    from sklearn.metrics import confusion_matrix, f1_score
+    from han_b200.base_gattn import BaseGAttN
+    rng = np.random.default_rng(3)
+    M, C = 60, 4
+    logits = torch.from_numpy(rng.normal(size=(M, C)))
+    y = torch.from_numpy(rng.integers(0, C, size=M))
+    cw = np.array([1.0, 2.0, 0.5, 3.0])
+    lse = np.log(np.exp(logits.numpy()).sum(1))
+    xent = lse - logits.numpy()[np.arange(M), y.numpy()]
+    assert np.isclose(float(BaseGAttN.loss(logits, y, C, cw)), (xent * cw[y.numpy()]).mean())
+    lg, lb = BaseGAttN.preshape(logits.reshape(1, M, C), y.reshape(1, M), C)
+    assert lg.shape == (M, C) and lb.shape == (M,)
+    cm = BaseGAttN.confmat(logits, y).numpy()
+    assert np.array_equal(cm, confusion_matrix(y.numpy(), logits.numpy().argmax(1), labels=list(range(cm.shape[0]))))
+    # multi-label helpers
+    Y = torch.from_numpy((rng.random((M, C)) < 0.4).astype(np.int64))
+    mask = torch.from_numpy((rng.random(M) < 0.5).astype(np.float32))
+    x = logits.numpy()
+    bce = (np.maximum(x, 0) - x * Y.numpy() + np.log1p(np.exp(-np.abs(x)))).mean(1)
+    m = mask.numpy() / mask.numpy().mean()
+    assert np.isclose(float(BaseGAttN.masked_sigmoid_cross_entropy(logits, Y, mask)), (bce * m).mean())
+    sel = mask.numpy() > 0
+    pred = (1 / (1 + np.exp(-x)) > 0.5).astype(int)
+    assert np.isclose(float(BaseGAttN.micro_f1(logits, Y, mask)), f1_score(Y.numpy()[sel], pred[sel], average="micro"), atol=1e-6)
