@@ -1,12 +1,18 @@
 """CPU oracle for the HAN attention hot path.  TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED: the reference (CG-Labs/HAN, TF1) ships no tests, no golden
-vectors and no seeds, and TensorFlow 1.x cannot be installed in this image, so
-this restatement cannot be checked against reference-produced outputs.  It is
-pinned instead by (a) following the reference line by line (citations below),
-(b) closed-form known-answer cases (tests/test_oracle.py), (c) fp64
-``torch.autograd.gradcheck`` of every function, and (d) the dense path and the
-independent edge-list twin agreeing to ~1e-15.
+PINNED TO THE REFERENCE'S OWN SOURCE.  The reference (CG-Labs/HAN, TF1) ships no tests, golden vectors or
+seeds, and TensorFlow 1.x cannot be installed in this image; what CAN run here is the reference's code itself:
+``utils/process.py`` as shipped (pure numpy) and ``utils/layers.py`` / ``models/gat.py`` /
+``models/base_gattn.py`` UNMODIFIED through a small TF1 API shim (``oracle/refrun/tf1_shim.py``: each tf.* op
+they call, with its documented semantics, on torch-CPU tensors).  ``oracle/refrun/make_ref_golden.py`` executes
+them on seeded inputs and commits the results as ``tests/golden/ref_*.npz``; ``tests/test_oracle_ref.py``
+asserts every function below reproduces those fixtures to <= 1e-12 in fp64 (adj_to_bias bit for bit):
+outputs, loss, every gradient, the variables after one ``training()`` step, attention coefficients, the three
+dropout sites given the same keep masks, TF1 variable names in creation order.  What stays un-pinned is the
+arithmetic INSIDE each TF primitive (Eigen's summation order vs torch's) -- bounded by the fp32-vs-fp64
+fixture pair at <= 2e-6 -- and ``mode="paper"`` of the semantic layer, which the reference does not implement
+(han.pdf Eq. 7-9 only).  Further pins: closed-form known answers, fp64 ``gradcheck``, dense path == edge-list
+twin to ~1e-15 (tests/test_oracle.py).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 ``--impl reference`` leg may import this module.  Nothing under ``han_b200/``
@@ -135,40 +141,64 @@ def attn_head(seq: torch.Tensor, out_sz: int, bias_mat: torch.Tensor, activation
     ``a1`` (H,), ``b1`` () [:23], ``a2`` (H,), ``b2`` () [:24], ``bias`` (H,) [:35].
     """
     assert hp["W"].shape[1] == out_sz
-    if masks is not None:
-        # test hook: the three tf.nn.dropout calls with GIVEN 0/1 keep masks (x: (N,F), coef: (N,N),
-        # s: (N,H)) instead of fresh random ones, so a CUDA run with the same masks can be compared exactly
-        seq = seq * masks["x"].to(seq.dtype) / (1.0 - in_drop)             # :18-19
-        seq_fts = _conv1d_k1(seq, hp["W"], None)                           # :20
-        f_1 = _conv1d_k1(seq_fts, hp["a1"].reshape(-1, 1), hp["b1"])       # :23
-        f_2 = _conv1d_k1(seq_fts, hp["a2"].reshape(-1, 1), hp["b2"])       # :24
-        logits = f_1 + f_2.transpose(1, 2)                                 # :26
-        coefs = torch.softmax(F.leaky_relu(logits, LEAKY_SLOPE) + bias_mat, dim=-1)  # :27
-        coefs = coefs * masks["coef"].to(seq.dtype) / (1.0 - coef_drop)    # :29-30
-        seq_fts = seq_fts * masks["s"].to(seq.dtype) / (1.0 - in_drop)     # :31-32
-        ret = torch.matmul(coefs, seq_fts) + hp["bias"]                    # :34-35
-        return (activation(ret), coefs) if return_coef else activation(ret)
+
+    def drop(x, rate, which):
+        # ``masks`` is a test hook: the three tf.nn.dropout calls take GIVEN 0/1 keep masks (x: (N,F),
+        # coef: (N,N), s: (N,H)) instead of fresh random ones, so a CUDA run (or the reference itself, run
+        # through the TF1 shim with the same masks) can be compared exactly
+        if masks is not None:
+            return x * masks[which].to(x.dtype) / (1.0 - rate)
+        return _dropout(x, 1.0 - rate, gen)
     if in_drop != 0.0:                                                     # :18-19
-        seq = _dropout(seq, 1.0 - in_drop, gen)
+        seq = drop(seq, in_drop, "x")
     seq_fts = _conv1d_k1(seq, hp["W"], None)                               # :20  (1,N,H)
     f_1 = _conv1d_k1(seq_fts, hp["a1"].reshape(-1, 1), hp["b1"])           # :23  (1,N,1)
     f_2 = _conv1d_k1(seq_fts, hp["a2"].reshape(-1, 1), hp["b2"])           # :24  (1,N,1)
     logits = f_1 + f_2.transpose(1, 2)                                     # :26  (1,N,N)
     coefs = torch.softmax(F.leaky_relu(logits, LEAKY_SLOPE) + bias_mat, dim=-1)  # :27
     if coef_drop != 0.0:                                                   # :29-30
-        coefs = _dropout(coefs, 1.0 - coef_drop, gen)
+        coefs = drop(coefs, coef_drop, "coef")
     if in_drop != 0.0:                                                     # :31-32
-        seq_fts = _dropout(seq_fts, 1.0 - in_drop, gen)
+        seq_fts = drop(seq_fts, in_drop, "s")
     vals = torch.matmul(coefs, seq_fts)                                    # :34
     ret = vals + hp["bias"]                                                # :35
     if residual:                                                           # :38-42
         if seq.shape[-1] != ret.shape[-1]:
-            ret = ret + _conv1d_k1(seq, hp["W_res"], hp.get("b_res"))      # :40
+            ret = ret + _conv1d_k1(seq, hp["W_res"], hp.get("b_res"))      # :40  (reads the DROPPED seq of :19)
         else:
             seq_fts = ret + seq                                            # :42 (dead store)
     if return_coef:                                                        # :43-44
         return activation(ret), coefs
     return activation(ret)                                                 # :46
+
+
+def sp_attn_head(seq: torch.Tensor, out_sz: int, adj_rows: np.ndarray, adj_cols: np.ndarray, adj_vals: torch.Tensor,
+                 activation: Callable, nb_nodes: int, hp: Dict[str, torch.Tensor], residual: bool = False) -> torch.Tensor:
+    """Restates ``sp_attn_head`` (utils/layers.py:85-127), dropout off, on the stored entries
+    (row, col, value) of the batch-1 ``tf.SparseTensor`` adjacency.
+
+    :95-96 ``logits = sparse_add(adj * f_1, adj * f_2^T)``: stored value w_ij scales BOTH score terms,
+    ``l_ij = w_ij f1_i + w_ij f2_j``; :97-99 leaky_relu on the stored values; :100 ``tf.sparse_softmax`` =
+    softmax over each row's STORED entries (an explicit zero still takes part); :113-115 sparse @ dense.
+    """
+    assert hp["W"].shape[1] == out_sz
+    seq_fts = _conv1d_k1(seq, hp["W"], None)                               # :90   (1,N,H)
+    f_1 = _conv1d_k1(seq_fts, hp["a1"].reshape(-1, 1), hp["b1"])[0, :, 0]  # :93
+    f_2 = _conv1d_k1(seq_fts, hp["a2"].reshape(-1, 1), hp["b2"])[0, :, 0]  # :94
+    rows = torch.from_numpy(np.asarray(adj_rows, dtype=np.int64))
+    cols = torch.from_numpy(np.asarray(adj_cols, dtype=np.int64))
+    w = adj_vals.to(seq.dtype)
+    e = F.leaky_relu(w * f_1[rows] + w * f_2[cols], LEAKY_SLOPE)           # :95-99
+    m = torch.full((nb_nodes,), -math.inf, dtype=seq.dtype).scatter_reduce(0, rows, e.detach(), reduce="amax")
+    ex = torch.exp(e - m[rows])                                            # :100
+    den = torch.zeros(nb_nodes, dtype=seq.dtype).index_add(0, rows, ex)
+    coefs = ex / den[rows]
+    S = seq_fts[0]                                                         # :112 squeeze
+    vals = torch.zeros_like(S).index_add(0, rows, coefs.unsqueeze(1) * S[cols])   # :113
+    ret = vals.unsqueeze(0) + hp["bias"]                                   # :114-116
+    if residual and seq.shape[-1] != ret.shape[-1]:                        # :119-121
+        ret = ret + _conv1d_k1(seq, hp["W_res"], hp.get("b_res"))
+    return activation(ret)                                                 # :127
 
 
 def attn_head_const_1(seq: torch.Tensor, out_sz: int, bias_mat: torch.Tensor, activation: Callable,
