@@ -43,24 +43,21 @@ _SIGNATURES = {
     "han_project_bwd": (c_int, [P, I64, I64, I64, P, I, I, P, P, SZ, I, P]),
     "han_project_bwd_tc_workspace_bytes": (SZ, [I64, I64, I]),
     "han_project_bwd_tc": (c_int, [P, I64, I64, I64, P, I, P, P, SZ, I, P]),
-    "han_attn_fwd": (c_int, [P, P, I64, P, P, P, I, I, I, P, I64, P, P, P]),
-    "han_attn_coefs": (c_int, [P, P, I64, P, P, I, I, P, P]),
+    "han_attn_coefs": (c_int, [P, P, I64, P, P, I, I, P, P, P]),
     "han_csr_chunk_edges": (c_int64, [I64]),
     "han_csr_num_chunks": (c_int64, [I64]),
     "han_csr_chunk_rows": (c_int, [P, I64, I64, P, P]),
-    "han_attn_fwd_chunked": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, FL, I, I64, P]),
-    "han_attn_bwd_src_chunked": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P, P, FL, I, I64, P]),
-    "han_attn_fwd_chunked_split": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, FL, I, I64,
+    "han_attn_fwd_chunked": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, FL, I, I64, P]),
+    "han_attn_bwd_src_chunked": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P, P, P, FL, I, I64, P]),
+    "han_attn_fwd_chunked_split": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, FL, I, I64,
                                            P, P, P, P, I, P]),
-    "han_attn_fwd_merge": (c_int, [P, P, I64, P, P, P, I, I, I, P, I64, P, P]),
-    "han_attn_bwd_src_chunked_split": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P, P, FL, I, I64,
+    "han_attn_bwd_src_chunked_split": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P, P, P, FL, I, I64,
                                                P, P, P, P, I, P]),
     "han_project_fwd_drop": (c_int, [P, I64, I64, I64, P, I64, I, I, I, P, P, P, P, P, P, P, P, FL, I, I64, P]),
     "han_project_bwd_drop_workspace_bytes": (SZ, [I64, I64, I]),
     "han_project_bwd_drop": (c_int, [P, I64, I64, I64, P, I, I, I, P, I64, P, SZ, P, FL, I, I64, P]),
     "han_reduce_blocks": (c_int, []),
     "han_attn_bwd_prep": (c_int, [P, I64, P, I64, P, P, I64, I, I, I, P, P, I64, P]),
-    "han_attn_bwd_src": (c_int, [P, P, P, I64, P, P, I, I, P, P, P, P]),
     "han_attn_bwd_dst": (c_int, [P, I64, I64, P, I, P, P]),
     "han_attn_bwd_finish": (c_int, [P, I64, I, I, P, P, P, P, P, P, P, P, FL, I, I64, P]),
     "han_reduce_partials": (c_int, [P, I, I64, P, P]),
@@ -118,12 +115,12 @@ def stream_ptr():
 # kernels launched by one call of each entry point (for bench.py's `gpu_launches` count)
 KERNELS_PER_CALL = {
     "han_dense_row_counts": 1, "han_scan_counts": 3, "han_dense_fill_indices": 1, "han_csr_transpose": 7,
-    "han_csr_sort_rows": 2, "han_project_fwd": None, "han_project_bwd": 2, "han_attn_fwd": 1,
-    "han_attn_coefs": 1, "han_attn_bwd_prep": 1, "han_attn_bwd_src": 1,
+    "han_csr_sort_rows": 2, "han_project_fwd": None, "han_project_bwd": 2,
+    "han_attn_coefs": 1, "han_attn_bwd_prep": 1,
     "han_csr_chunk_rows": 1, "han_attn_fwd_chunked": 1, "han_attn_bwd_src_chunked": 1, "han_attn_bwd_dst": 1,
     "han_attn_bwd_finish": 1, "han_reduce_partials": 1, "han_semantic_fwd": 1, "han_semantic_combine": 1,
     "han_semantic_bwd": 2, "han_adam_l2_step": 1, "han_project_dx": 1,
-    "han_attn_fwd_chunked_split": 2, "han_attn_bwd_src_chunked_split": 2, "han_attn_fwd_merge": 1, "han_semantic_fwd_tc": 2,
+    "han_attn_fwd_chunked_split": 2, "han_attn_bwd_src_chunked_split": 2, "han_semantic_fwd_tc": 2,
 }
 
 

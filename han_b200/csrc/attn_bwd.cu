@@ -7,12 +7,12 @@
 //   dS_j   = sum_i alpha_ij dV_i ;  df2_j = sum_i dl_ij   (by source  : transposed structure)
 //   df1_i  = sum_j dl_ij                                  (by destination: CSR order)
 //
-// Design: ONE gather pass, by source.  Everything an edge needs from its destination row lives in
-// one contiguous row record R_i = [dV | f1 | m | rinv | delta] (384 B for K=H=8), so the by-source
+// Design: ONE gather pass, by source (attn_stream.cu).  Everything an edge needs from its destination row
+// lives in one contiguous row record R_i = [dV | f1 | lse | delta] (352 B for K=H=8), so the by-source
 // kernel gathers exactly one record per edge, keeps S_j / f2_j in registers, and emits dl_ij (32 B)
 // to the edge's CSR slot; df1 is then a streaming segmented sum.  No atomics anywhere, so the
-// backward is deterministic.  Algorithmic bytes: 4+4+384+32 per edge by source, 32 per edge by
-// destination, vs 292+328+64 for a two-gather formulation.
+// backward is deterministic.  This file holds the row-local kernels around that pass: prep (dV, delta ->
+// records), the by-destination df1 sums, finish (dS_tot, parameter-gradient partials).
 #include "han_common.cuh"
 #include "han_rng.cuh"
 
@@ -92,99 +92,6 @@ attn_bwd_prep_kernel(const float* __restrict__ dout, int64_t dout_stride, const 
     float s = 0.f;
     for (int r = 0; r < ROWS; ++r) s += red[r * D + c];
     dbias_partial[(int64_t)blockIdx.x * D + c] = s;
-  }
-}
-
-// ---- by-source gather pass ---------------------------------------------------------------------
-template <int K, int H, int UNROLL>
-__global__ void __launch_bounds__(256)
-attn_bwd_src_kernel(const int64_t* __restrict__ t_indptr, const int32_t* __restrict__ t_indices,
-                    const int32_t* __restrict__ perm, int64_t n_src, const float* __restrict__ Tsrc,
-                    const float* __restrict__ R, float* __restrict__ dS_agg, float* __restrict__ df2,
-                    float* __restrict__ dl_edge) {
-  constexpr int D = K * H;
-  constexpr int TS = ((D + K + 3) / 4) * 4;
-  constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
-  constexpr int SLOTS = 32 / K;
-  constexpr int HV = H / 4;
-  const int lane = threadIdx.x & 31;
-  const int head = lane % K, slot = lane / K;
-  const int64_t src = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (src >= n_src) return;
-
-  const int64_t start = t_indptr[src], end = t_indptr[src + 1];
-  float sj[H];
-#pragma unroll
-  for (int q = 0; q < HV; ++q) {
-    const float4 s4 = ldg4(Tsrc + src * TS + head * H + 4 * q);
-    sj[4 * q] = s4.x; sj[4 * q + 1] = s4.y; sj[4 * q + 2] = s4.z; sj[4 * q + 3] = s4.w;
-  }
-  const float f2 = __ldg(Tsrc + src * TS + D + head);
-  float acc[H];
-#pragma unroll
-  for (int h = 0; h < H; ++h) acc[h] = 0.f;
-  float df2acc = 0.f;
-
-  for (int64_t base = start; base < end; base += 32) {
-    const int cnt = (int)min((int64_t)32, end - base);
-    const int my_row = (lane < cnt) ? ldg_stream_i32(t_indices + base + lane) : 0;
-    const int my_perm = (lane < cnt) ? ldg_stream_i32(perm + base + lane) : 0;
-    for (int t = 0; t < cnt; t += SLOTS * UNROLL) {
-      float4 g[UNROLL][HV];
-      float f1[UNROLL], mm[UNROLL], de[UNROLL];
-      int pe[UNROLL];
-      bool ok[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int ei = t + u * SLOTS + slot;
-        const int i = __shfl_sync(0xffffffffu, my_row, ei & 31);
-        pe[u] = __shfl_sync(0xffffffffu, my_perm, ei & 31);
-        ok[u] = ei < cnt;
-        if (ok[u]) {
-          const float* rp = R + (int64_t)i * RS;
-#pragma unroll
-          for (int q = 0; q < HV; ++q) g[u][q] = ldg4(rp + head * H + 4 * q);
-          f1[u] = __ldg(rp + D + head);
-          mm[u] = __ldg(rp + D + K + head);
-          de[u] = __ldg(rp + D + 2 * K + head);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        if (ok[u]) {
-          const float lg = f1[u] + f2;
-          const float a = __expf(leaky(lg) - mm[u]);
-          float da = 0.f;
-#pragma unroll
-          for (int q = 0; q < HV; ++q) {
-            da = fmaf(g[u][q].x, sj[4 * q], da);
-            da = fmaf(g[u][q].y, sj[4 * q + 1], da);
-            da = fmaf(g[u][q].z, sj[4 * q + 2], da);
-            da = fmaf(g[u][q].w, sj[4 * q + 3], da);
-            acc[4 * q] = fmaf(a, g[u][q].x, acc[4 * q]);
-            acc[4 * q + 1] = fmaf(a, g[u][q].y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(a, g[u][q].z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(a, g[u][q].w, acc[4 * q + 3]);
-          }
-          const float dl = a * (da - de[u]) * (lg > 0.f ? 1.f : kLeakySlope);
-          df2acc += dl;
-          dl_edge[(int64_t)pe[u] * K + head] = dl;
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int off = K; off < 32; off <<= 1) {
-    df2acc += __shfl_xor_sync(0xffffffffu, df2acc, off);
-#pragma unroll
-    for (int h = 0; h < H; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], off);
-  }
-  if (slot == 0) {
-    df2[src * K + head] = df2acc;
-#pragma unroll
-    for (int q = 0; q < HV; ++q)
-      *reinterpret_cast<float4*>(dS_agg + src * D + head * H + 4 * q) =
-          make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
   }
 }
 
@@ -352,24 +259,6 @@ int han_attn_bwd_prep(const float* dout, int64_t dout_stride, const float* out, 
   if (K == k && H == h) {                                                                              \
     attn_bwd_prep_kernel<k, h><<<kReduceBlocks, 256, 0, as_stream(stream)>>>(                          \
         dout, dout_stride, out, out_stride, vsave, R, n_dst, act, dbias_partial, R_mc, r_row0);        \
-    return check_launch(__func__);                                                                     \
-  }
-  HAN_FOR_SHAPES(X)
-#undef X
-  return fail_arg(__func__, "unsupported (K,H)");
-}
-
-int han_attn_bwd_src(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
-                     int64_t n_src, const float* Tsrc, const float* R, int K, int H, float* dS_agg,
-                     float* df2, float* dl_edge, han_stream_t stream) {
-  HAN_REQUIRE(t_indptr && Tsrc && R && dS_agg && df2 && dl_edge, "null pointer");
-  HAN_REQUIRE(n_src > 0, "n_src > 0 required");
-  unsigned grid = (unsigned)ceil_div64(n_src, 8);
-#define X(k, h)                                                                                        \
-  if (K == k && H == h) {                                                                              \
-    constexpr int U = (k >= 8) ? 4 : (k >= 4 ? 2 : 1);                                                 \
-    attn_bwd_src_kernel<k, h, U><<<grid, 256, 0, as_stream(stream)>>>(                                 \
-        t_indptr, t_indices, perm, n_src, Tsrc, R, dS_agg, df2, dl_edge);                              \
     return check_launch(__func__);                                                                     \
   }
   HAN_FOR_SHAPES(X)

@@ -1,6 +1,6 @@
 // Chunked edge-stream versions of the two gather kernels (K-B forward, K-D by-source backward).
 //
-// Why: the warp-per-row kernels in attn_fwd.cu / attn_bwd.cu hold every gathered row in registers,
+// Why: a warp-per-row kernel (round 1's first version, removed) holds every gathered row in registers,
 // so registers cap both occupancy and the number of rows in flight (ncu on B200: 35% / 21% warps
 // active, 67% / 35% DRAM utilisation).  Here a warp owns a contiguous CHUNK of the CSR edge stream
 // (whole rows, ~chunk_edges edges, boundaries precomputed per graph by han_csr_chunk_rows) and
@@ -75,7 +75,8 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
                         const int32_t* __restrict__ chunk_rows, int64_t n_chunks,
                         const float* __restrict__ T, float* __restrict__ R, const float* __restrict__ bias,
                         int act, float* __restrict__ out, int64_t out_stride, float* __restrict__ vsave,
-                        const float* __restrict__ colmean, DropCoef dc, SplitRows sp) {
+                        const float* __restrict__ colmean, const float* __restrict__ ew,
+                        const float* __restrict__ resid, int64_t resid_stride, DropCoef dc, SplitRows sp) {
   constexpr int D = K * H;
   constexpr int TS = ((D + K + 3) / 4) * 4;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
@@ -89,6 +90,9 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
   const int head = lane % K, slot = lane / K;
   float* ring = smem + (size_t)w * STAGES * kBatch * TS;
   int* col_s = reinterpret_cast<int*>(smem + (size_t)kStreamWarps * STAGES * kBatch * TS) + w * STAGES * kBatch;
+  // sp_attn_head (utils/layers.py:95-96): stored adjacency value w_ij scales the logit; staged like the columns.
+  // The region exists only when ew != nullptr (the launcher sizes the dynamic shared memory accordingly).
+  float* w_s = reinterpret_cast<float*>(col_s - w * STAGES * kBatch + kStreamWarps * STAGES * kBatch) + w * STAGES * kBatch;
   // attention-coefficient dropout (utils/layers.py:29-30): mask bit from (seed, dst, src, head)
   const uint32_t cseed = dc.thr ? stream_seed(*dc.seed_ptr, 3u, dc.metapath, (uint32_t)head) : 0u;
 
@@ -101,6 +105,7 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
 
   int q = 0;  // next batch to issue
   int col_pref = (lane < kBatch && e_lo + lane < e_hi) ? ldg_stream_i32(indices + e_lo + lane) : 0;
+  float w_pref = (ew && lane < kBatch && e_lo + lane < e_hi) ? __ldg(ew + e_lo + lane) : 1.f;
   auto issue = [&]() {
     if (q < nb) {
       const int64_t bs = e_lo + (int64_t)q * kBatch;
@@ -114,8 +119,10 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
         if (c < TOT && rec < cnt) cp_async16(dst + rec * TS + off * 4, T + (int64_t)col * TS + off * 4);
       }
       if (lane < kBatch) col_s[(q % STAGES) * kBatch + lane] = col_pref;
+      if (ew && lane < kBatch) w_s[(q % STAGES) * kBatch + lane] = w_pref;
       const int64_t nbs = bs + kBatch;
       col_pref = (lane < kBatch && nbs + lane < e_hi) ? ldg_stream_i32(indices + nbs + lane) : 0;
+      if (ew) w_pref = (lane < kBatch && nbs + lane < e_hi) ? __ldg(ew + nbs + lane) : 1.f;
     }
     cp_async_commit();
     ++q;
@@ -189,6 +196,10 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
         *reinterpret_cast<float4*>(vp + 4 * qv) = a;
         const float4 b = ldg4(bias + head * H + 4 * qv);
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        if (resid) {   // residual branch, utils/layers.py:38-40: ret + conv1d(seq, H, 1), then the activation
+          const float4 r4 = ldg4_stream(resid + (int64_t)rr * resid_stride + head * H + 4 * qv);
+          a.x += r4.x; a.y += r4.y; a.z += r4.z; a.w += r4.w;
+        }
         if (act == HAN_ACT_ELU) {
           a.x = a.x > 0.f ? a.x : expm1f(a.x);
           a.y = a.y > 0.f ? a.y : expm1f(a.y);
@@ -225,6 +236,7 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
     __syncwarp();
     const float* buf = ring + (size_t)(b % STAGES) * kBatch * TS;
     const int* cbuf = col_s + (b % STAGES) * kBatch;
+    const float* wbuf = w_s + (b % STAGES) * kBatch;
     const int64_t bs = e_lo + (int64_t)b * kBatch;
     const int64_t be = min(e_hi, bs + kBatch);
     while (pos < be) {
@@ -233,7 +245,9 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
         const int64_t ei = g + slot;
         if (ei < seg_end) {
           const float* rp = buf + (int)(ei - bs) * TS;
-          const float e = leaky(f1v + rp[D + head]);
+          float lg = f1v + rp[D + head];
+          if (ew) lg *= wbuf[(int)(ei - bs)];
+          const float e = leaky(lg);
           const float mnew = fmaxf(m, e);
           const float sc = __expf(m - mnew);   // m = -inf -> 0
           const float p = __expf(e - mnew);
@@ -278,7 +292,8 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
                             const int32_t* __restrict__ perm, const int32_t* __restrict__ chunk_rows,
                             int64_t n_chunks, const float* __restrict__ Tsrc, const float* __restrict__ R,
                             float* __restrict__ dS_agg, float* __restrict__ df2,
-                            float* __restrict__ dl_edge, float* __restrict__ df1_red, DropCoef dc, SplitRows sp) {
+                            float* __restrict__ dl_edge, float* __restrict__ df1_red,
+                            const float* __restrict__ ew_t, DropCoef dc, SplitRows sp) {
   constexpr int D = K * H;
   constexpr int TS = ((D + K + 3) / 4) * 4;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
@@ -293,6 +308,8 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
   float* ring = smem + (size_t)w * STAGES * kBatch * RS;
   int* perm_s = reinterpret_cast<int*>(smem + (size_t)kStreamWarps * STAGES * kBatch * RS) + w * STAGES * kBatch;
   int* row_s = perm_s + kStreamWarps * STAGES * kBatch;
+  // edge weights in transposed-edge order (sp_attn_head); region present only when ew_t != nullptr
+  float* w_s = reinterpret_cast<float*>(row_s - w * STAGES * kBatch + kStreamWarps * STAGES * kBatch) + w * STAGES * kBatch;
   const uint32_t cseed = dc.thr ? stream_seed(*dc.seed_ptr, 3u, dc.metapath, (uint32_t)head) : 0u;
 
   const int64_t chunk = (int64_t)blockIdx.x * kStreamWarps + w;
@@ -304,9 +321,11 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
 
   int q = 0;
   int row_pref = 0, perm_pref = 0;
+  float w_pref = 1.f;
   if (lane < kBatch && e_lo + lane < e_hi) {
     row_pref = ldg_stream_i32(t_indices + e_lo + lane);
     perm_pref = ldg_stream_i32(perm + e_lo + lane);
+    if (ew_t) w_pref = __ldg(ew_t + e_lo + lane);
   }
   auto issue = [&]() {
     if (q < nb) {
@@ -324,11 +343,13 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
       if (lane < kBatch) {
         perm_s[st * kBatch + lane] = perm_pref;
         row_s[st * kBatch + lane] = row_pref;
+        if (ew_t) w_s[st * kBatch + lane] = w_pref;
       }
       const int64_t nbs = bs + kBatch;
       if (lane < kBatch && nbs + lane < e_hi) {
         row_pref = ldg_stream_i32(t_indices + nbs + lane);
         perm_pref = ldg_stream_i32(perm + nbs + lane);
+        if (ew_t) w_pref = __ldg(ew_t + nbs + lane);
       }
     }
     cp_async_commit();
@@ -412,6 +433,7 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
     const float* buf = ring + (size_t)st * kBatch * RS;
     const int* pbuf = perm_s + st * kBatch;
     const int* rbuf = row_s + st * kBatch;
+    const float* wbuf = w_s + st * kBatch;
     const int64_t bs = e_lo + (int64_t)b * kBatch;
     const int64_t be = min(e_hi, bs + kBatch);
     while (pos < be) {
@@ -424,7 +446,8 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
         if (ei < seg_end) {
           const int rec = (int)(ei - bs);
           const float* rp = buf + rec * RS;
-          const float lg = rp[D + head] + f2;
+          const float wt = ew_t ? wbuf[rec] : 1.f;     // l_ij = w_ij (f1_i + f2_j): d l / d f1 = d l / d f2 = w_ij
+          const float lg = (rp[D + head] + f2) * wt;
           const float a = __expf(leaky(lg) - rp[D + K + head]);
           // coefficient dropout: alpha~ = alpha * m / keep feeds the aggregate; d alpha = d alpha~ * m / keep
           float mk = 1.f;
@@ -444,7 +467,7 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
             acc[4 * qv + 2] = fmaf(am, g4.z, acc[4 * qv + 2]);
             acc[4 * qv + 3] = fmaf(am, g4.w, acc[4 * qv + 3]);
           }
-          dl = a * (da * mk - rp[D + 2 * K + head]) * (lg > 0.f ? 1.f : kLeakySlope);
+          dl = a * (da * mk - rp[D + 2 * K + head]) * (lg > 0.f ? 1.f : kLeakySlope) * wt;
           df2acc += dl;
           if constexpr (RED) drow = rbuf[rec];
           else dl_edge[(int64_t)pbuf[rec] * K + head] = dl;
@@ -487,7 +510,8 @@ template <int K, int H>
 __global__ void __launch_bounds__(128)
 attn_fwd_merge_kernel(const int32_t* __restrict__ heavy_rows, const int32_t* __restrict__ heavy_ptr, int n_heavy,
                       const float* __restrict__ part, float* __restrict__ R, const float* __restrict__ bias, int act,
-                      float* __restrict__ out, int64_t out_stride, float* __restrict__ vsave) {
+                      float* __restrict__ out, int64_t out_stride, float* __restrict__ vsave,
+                      const float* __restrict__ resid, int64_t resid_stride) {
   constexpr int D = K * H;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
   constexpr int SLOTS = 32 / K;
@@ -533,7 +557,8 @@ attn_fwd_merge_kernel(const int32_t* __restrict__ heavy_rows, const int32_t* __r
     for (int h = 0; h < H; ++h) {
       const float a = acc[h] * rinv;
       vp[h] = a;
-      const float z = a + bias[head * H + h];
+      float z = a + bias[head * H + h];
+      if (resid) z += resid[(int64_t)rr * resid_stride + head * H + h];
       op[h] = (act == HAN_ACT_ELU && z <= 0.f) ? expm1f(z) : z;
     }
   }
@@ -592,6 +617,8 @@ struct StreamCfg {
   static constexpr int BWD_STAGES = 3;
   static constexpr size_t fwd_smem = (size_t)kStreamWarps * FWD_STAGES * kBatch * (TS * 4 + 4);
   static constexpr size_t bwd_smem = (size_t)kStreamWarps * BWD_STAGES * kBatch * (RS * 4 + 8);
+  static constexpr size_t fwd_w_smem = (size_t)kStreamWarps * FWD_STAGES * kBatch * 4;   // + staged edge weights
+  static constexpr size_t bwd_w_smem = (size_t)kStreamWarps * BWD_STAGES * kBatch * 4;
 };
 
 struct HeavyRows {   // the cut rows of a virtual-row view (all null / 0: no splitting)
@@ -604,20 +631,18 @@ template <int K, int H, bool SPLIT>
 static int launch_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
                               int64_t n_chunks, const float* T, float* R, const float* bias, int act,
                               float* out, int64_t out_stride, float* vsave, const float* colmean,
-                              DropCoef dc, SplitRows sp, HeavyRows hv, cudaStream_t st) {
+                              const float* ew, const float* resid, int64_t resid_stride, DropCoef dc, SplitRows sp,
+                              HeavyRows hv, cudaStream_t st) {
   using C = StreamCfg<K, H>;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(attn_fwd_chunked_kernel<K, H, C::FWD_STAGES, SPLIT>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::fwd_smem);
-    attr = true;
-  }
+  HAN_SMEM_ATTR_ONCE((attn_fwd_chunked_kernel<K, H, C::FWD_STAGES, SPLIT>), C::fwd_smem + C::fwd_w_smem);
   unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
-  attn_fwd_chunked_kernel<K, H, C::FWD_STAGES, SPLIT><<<grid, kStreamWarps * 32, C::fwd_smem, st>>>(
-      indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, dc, sp);
+  const size_t smem = C::fwd_smem + (ew ? C::fwd_w_smem : 0);
+  attn_fwd_chunked_kernel<K, H, C::FWD_STAGES, SPLIT><<<grid, kStreamWarps * 32, smem, st>>>(
+      indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, ew, resid, resid_stride, dc,
+      sp);
   if (SPLIT && hv.n > 0)
     attn_fwd_merge_kernel<K, H><<<(unsigned)ceil_div64(hv.n, 4), 128, 0, st>>>(hv.rows, hv.ptr, hv.n, sp.part, R, bias, act,
-                                                                            out, out_stride, vsave);
+                                                                            out, out_stride, vsave, resid, resid_stride);
   return check_launch("han_attn_fwd_chunked");
 }
 
@@ -625,23 +650,18 @@ template <int K, int H, bool SPLIT>
 static int launch_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
                                   const int32_t* chunk_rows, int64_t n_chunks, const float* Tsrc,
                                   const float* R, float* dS_agg, float* df2, float* dl_edge, float* df1_red,
-                                  DropCoef dc, SplitRows sp, HeavyRows hv, cudaStream_t st) {
+                                  const float* ew_t, DropCoef dc, SplitRows sp, HeavyRows hv, cudaStream_t st) {
   using C = StreamCfg<K, H>;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, false>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bwd_smem);
-    cudaFuncSetAttribute(attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, true>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bwd_smem);
-    attr = true;
-  }
+  HAN_SMEM_ATTR_ONCE((attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, false>), C::bwd_smem + C::bwd_w_smem);
+  HAN_SMEM_ATTR_ONCE((attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, true>), C::bwd_smem + C::bwd_w_smem);
   unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
+  const size_t smem = C::bwd_smem + (ew_t ? C::bwd_w_smem : 0);
   if (df1_red != nullptr)
-    attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, true><<<grid, kStreamWarps * 32, C::bwd_smem, st>>>(
-        t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, dc, sp);
+    attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, true><<<grid, kStreamWarps * 32, smem, st>>>(
+        t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, ew_t, dc, sp);
   else
-    attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, false><<<grid, kStreamWarps * 32, C::bwd_smem, st>>>(
-        t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, dc, sp);
+    attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, false><<<grid, kStreamWarps * 32, smem, st>>>(
+        t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, ew_t, dc, sp);
   if (SPLIT && hv.n > 0)
     attn_bwd_src_merge_kernel<K, H><<<(unsigned)ceil_div64(hv.n, 4), 128, 0, st>>>(hv.rows, hv.ptr, hv.n, sp.part, dS_agg, df2);
   return check_launch("han_attn_bwd_src_chunked");
@@ -680,8 +700,9 @@ int han_csr_chunk_rows(const int64_t* indptr, int64_t n_rows, int64_t nnz, int32
 int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
                          int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                          int K, int H, int act, float* out, int64_t out_stride, float* vsave,
-                         const float* colmean, const uint32_t* seed_ptr, float coef_keep, int metapath,
-                         int64_t row0, han_stream_t stream) {
+                         const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
+                         const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0, han_stream_t stream) {
+  HAN_REQUIRE(!resid || (resid_stride >= (int64_t)K * H && resid_stride % 4 == 0 && (uintptr_t)resid % 16 == 0), "resid");
   HAN_REQUIRE(indptr && chunk_rows && T && R && bias && out && vsave, "null pointer");
   HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
   const DropCoef dc = make_drop(seed_ptr, coef_keep, metapath, row0);
@@ -692,7 +713,7 @@ int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const in
               ((uintptr_t)bias % 16 == 0), "16-byte alignment");
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_fwd_chunked<k, h, false>(indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, dc, SplitRows{nullptr, nullptr}, HeavyRows{nullptr, nullptr, 0}, as_stream(stream));
+    return launch_fwd_chunked<k, h, false>(indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, edge_w, resid, resid_stride, dc, SplitRows{nullptr, nullptr}, HeavyRows{nullptr, nullptr, 0}, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
@@ -701,8 +722,8 @@ int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const in
 int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
                              const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                              const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                             float* dl_edge, float* df1_red, const uint32_t* seed_ptr, float coef_keep, int metapath,
-                             int64_t row0, han_stream_t stream) {
+                             float* dl_edge, float* df1_red, const float* edge_w_t, const uint32_t* seed_ptr,
+                             float coef_keep, int metapath, int64_t row0, han_stream_t stream) {
   HAN_REQUIRE(t_indptr && chunk_rows && Tsrc && R && dS_agg && df2 && (dl_edge || df1_red), "null pointer");
   HAN_REQUIRE(!df1_red || (uintptr_t)df1_red % 16 == 0, "df1_red must be 16-byte aligned");
   HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
@@ -711,7 +732,7 @@ int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, 
   HAN_REQUIRE(((uintptr_t)R % 16 == 0) && ((uintptr_t)Tsrc % 16 == 0) && ((uintptr_t)dS_agg % 16 == 0), "16-byte alignment");
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_bwd_src_chunked<k, h, false>(t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, dc, SplitRows{nullptr, nullptr}, HeavyRows{nullptr, nullptr, 0}, as_stream(stream));
+    return launch_bwd_src_chunked<k, h, false>(t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, edge_w_t, dc, SplitRows{nullptr, nullptr}, HeavyRows{nullptr, nullptr, 0}, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
@@ -720,9 +741,11 @@ int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, 
 int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, const int32_t* chunk_rows,
                                int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                                int K, int H, int act, float* out, int64_t out_stride, float* vsave,
-                               const float* colmean, const uint32_t* seed_ptr, float coef_keep, int metapath,
-                               int64_t row0, const int32_t* vmap, float* part, const int32_t* heavy_rows,
-                               const int32_t* heavy_ptr, int n_heavy, han_stream_t stream) {
+                               const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
+                               const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0, const int32_t* vmap,
+                               float* part, const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
+                               han_stream_t stream) {
+  HAN_REQUIRE(!resid || (resid_stride >= (int64_t)K * H && resid_stride % 4 == 0 && (uintptr_t)resid % 16 == 0), "resid");
   HAN_REQUIRE(indptr_v && chunk_rows && T && R && bias && out && vsave, "null pointer");
   HAN_REQUIRE(vmap && part && n_heavy >= 0 && (n_heavy == 0 || (heavy_rows && heavy_ptr)), "split view: vmap, part, heavy rows");
   HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
@@ -736,7 +759,7 @@ int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, 
   const HeavyRows hv{heavy_rows, heavy_ptr, n_heavy};
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_fwd_chunked<k, h, true>(indptr_v, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, dc, sp, hv, as_stream(stream));
+    return launch_fwd_chunked<k, h, true>(indptr_v, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, edge_w, resid, resid_stride, dc, sp, hv, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
@@ -745,8 +768,8 @@ int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, 
 int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_indices, const int32_t* perm,
                                    const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                                    const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                                   float* dl_edge, float* df1_red, const uint32_t* seed_ptr, float coef_keep,
-                                   int metapath, int64_t row0, const int32_t* vmap, float* part,
+                                   float* dl_edge, float* df1_red, const float* edge_w_t, const uint32_t* seed_ptr,
+                                   float coef_keep, int metapath, int64_t row0, const int32_t* vmap, float* part,
                                    const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
                                    han_stream_t stream) {
   HAN_REQUIRE(t_indptr_v && chunk_rows && Tsrc && R && dS_agg && df2 && (dl_edge || df1_red), "null pointer");
@@ -761,27 +784,7 @@ int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_i
   const HeavyRows hv{heavy_rows, heavy_ptr, n_heavy};
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_bwd_src_chunked<k, h, true>(t_indptr_v, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, dc, sp, hv, as_stream(stream));
-  HAN_FOR_SHAPES(X)
-#undef X
-  return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
-}
-
-/* The merge step on its own (n_heavy == 0 in the calls above skips it): used when one real row's segments
- * come from SEVERAL launches -- the source-blocked forward, where each launch walks the edges of one block of
- * source nodes (a slab of the node table small enough to stay in L2) and every row is cut at block borders. */
-int han_attn_fwd_merge(const int32_t* heavy_rows, const int32_t* heavy_ptr, int64_t n_heavy, const float* part,
-                       float* R, const float* bias, int K, int H, int act, float* out, int64_t out_stride,
-                       float* vsave, han_stream_t stream) {
-  HAN_REQUIRE(heavy_rows && heavy_ptr && part && R && bias && out && vsave, "null pointer");
-  HAN_REQUIRE(n_heavy > 0 && n_heavy < ((int64_t)1 << 31), "n_heavy");
-  HAN_REQUIRE(act == HAN_ACT_ELU || act == HAN_ACT_IDENTITY, "activation");
-#define X(k, h)                                                                                                  \
-  if (K == k && H == h) {                                                                                        \
-    attn_fwd_merge_kernel<k, h><<<(unsigned)ceil_div64(n_heavy, 4), 128, 0, as_stream(stream)>>>(                \
-        heavy_rows, heavy_ptr, (int)n_heavy, part, R, bias, act, out, out_stride, vsave);                        \
-    return check_launch(__func__);                                                                               \
-  }
+    return launch_bwd_src_chunked<k, h, true>(t_indptr_v, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, edge_w_t, dc, sp, hv, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "han_b200.h"
 
 namespace han {
@@ -33,6 +35,20 @@ inline int check_launch(const char* fn) {
 #define HAN_REQUIRE(cond, what)                  \
   do {                                           \
     if (!(cond)) return han::fail_arg(__func__, what); \
+  } while (0)
+
+// Opt-in to > 48 KB of dynamic shared memory.  The attribute is per DEVICE (context), so remember it per device
+// (bit d of a process-wide word), thread-safe; a process that touches several GPUs sets it on each.
+#define HAN_SMEM_ATTR_ONCE(kernel, bytes)                                                              \
+  do {                                                                                                 \
+    static std::atomic<uint64_t> han_done_{0};                                                         \
+    int han_dev_ = 0;                                                                                  \
+    cudaGetDevice(&han_dev_);                                                                          \
+    const uint64_t han_bit_ = 1ull << (han_dev_ & 63);                                                 \
+    if (!(han_done_.load(std::memory_order_acquire) & han_bit_)) {                                     \
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));         \
+      han_done_.fetch_or(han_bit_, std::memory_order_release);                                         \
+    }                                                                                                  \
   } while (0)
 
 inline cudaStream_t as_stream(han_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }

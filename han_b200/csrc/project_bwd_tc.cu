@@ -276,13 +276,9 @@ int han_project_bwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const 
   HAN_REQUIRE((uintptr_t)ws % 16 == 0, "workspace must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   const int64_t rows_per_split = ceil_div64(ceil_div64(n, splits), BT_BK) * BT_BK;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(project_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM_BYTES);
-    cudaFuncSetAttribute(project_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM_BYTES);
-    cudaFuncSetAttribute(project_bwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM_BYTES);
-    attr = true;
-  }
+  HAN_SMEM_ATTR_ONCE(project_bwd_tc_kernel<1>, BT_SMEM_BYTES);
+  HAN_SMEM_ATTR_ONCE(project_bwd_tc_kernel<2>, BT_SMEM_BYTES);
+  HAN_SMEM_ATTR_ONCE(project_bwd_tc_kernel<3>, BT_SMEM_BYTES);
   dim3 grid((unsigned)ceil_div64(F, BT_BM), (unsigned)splits);
   float* part = reinterpret_cast<float*>(ws);
   if (mode == 1)

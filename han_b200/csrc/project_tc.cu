@@ -377,13 +377,9 @@ int han_project_fwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const 
 
   const int nkb = (int)ceil_div64(F, TC_BK);
   const unsigned grid = (unsigned)ceil_div64(n, TC_BM);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(project_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-    cudaFuncSetAttribute(project_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-    cudaFuncSetAttribute(project_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-    attr = true;
-  }
+  HAN_SMEM_ATTR_ONCE(project_tc_kernel<1>, TC_SMEM_BYTES);
+  HAN_SMEM_ATTR_ONCE(project_tc_kernel<2>, TC_SMEM_BYTES);
+  HAN_SMEM_ATTR_ONCE(project_tc_kernel<3>, TC_SMEM_BYTES);
   if (mode == 1)
     project_tc_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, a2, b2, T, R,
                                                                   T_mc, t_rows, t_row0, r_rows);

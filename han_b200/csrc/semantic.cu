@@ -614,11 +614,7 @@ static int launch_sem_fwd(const float* Z, int64_t n, int P, const float* w, cons
                           float* scores, cudaStream_t st) {
   using C = SemFwdCfg<D, A>;
   size_t smem = C::smem_floats * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(semantic_fwd_kernel<D, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  HAN_SMEM_ATTR_ONCE((semantic_fwd_kernel<D, A>), smem);
   int64_t n_tiles = ceil_div64(n, C::TM / P);
   unsigned grid = (unsigned)(n_tiles < (int64_t)kNumSMs * 2 ? n_tiles : (int64_t)kNumSMs * 2);
   semantic_fwd_kernel<D, A><<<grid, kSemThreads, smem, st>>>(Z, n, P, w, b, u, mode, out, beta, vsave, scores);
@@ -634,11 +630,7 @@ static int launch_sem_bwd(const float* dout, const float* Z, const float* beta, 
   size_t smem = C::smem_floats * sizeof(float);
   if (ws_bytes < (size_t)kSemBwdBlocks * C::part_floats * sizeof(float))
     return fail_arg("han_semantic_bwd", "workspace too small");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(semantic_bwd_kernel<D, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  HAN_SMEM_ATTR_ONCE((semantic_bwd_kernel<D, A>), smem);
   float* part = reinterpret_cast<float*>(ws);
   semantic_bwd_kernel<D, A><<<kSemBwdBlocks, kSemThreads, smem, st>>>(dout, Z, beta, vsave, n, P, w, u,
                                                                     mode, dsbar, dZ, part);

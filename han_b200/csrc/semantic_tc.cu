@@ -401,13 +401,9 @@ int han_semantic_fwd_tc(const float* Z, int64_t n, int P, int D, int A, const fl
   if (rc) return rc;
   rc = st_make_map(&tmWlo, wt_lo, ST_D, ST_A, ST_D, ST_A);
   if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(semantic_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES);
-    cudaFuncSetAttribute(semantic_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES);
-    cudaFuncSetAttribute(semantic_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES);
-    attr = true;
-  }
+  HAN_SMEM_ATTR_ONCE(semantic_fwd_tc_kernel<1>, ST_SMEM_BYTES);
+  HAN_SMEM_ATTR_ONCE(semantic_fwd_tc_kernel<2>, ST_SMEM_BYTES);
+  HAN_SMEM_ATTR_ONCE(semantic_fwd_tc_kernel<4>, ST_SMEM_BYTES);
   const int64_t n_tiles = ceil_div64(n, ST_BM / P);
   const unsigned grid = (unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
   if (epilogue_groups == 1)

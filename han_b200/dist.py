@@ -245,24 +245,20 @@ class RowShard:
         pos[by_dst.perm.long()] = torch.arange(by_dst.nnz, dtype=torch.int32, device=dev)
         return _BackwardEdges(by_src, by_dst.indptr, pos)
 
-    def symmetric_tables(self, G: int, K: int, H: int) -> Optional[SymmetricTables]:
+    def symmetric_tables(self, G: int, K: int, H: int, slot: int = 0) -> Optional[SymmetricTables]:
         """The multicast-mapped tables for this plan shape (allocated and rendezvoused once; a
         collective call, so every rank must ask for the same shapes in the same order), or None when
         NVLS multicast is unavailable / HAN_DIST_COMM=nccl (then NCCL all-gathers are used)."""
         if not self.use_multicast or self.device.type != "cuda":
             return None
-        key = (G, K, H, self.n_pad)
+        # One table set per plan invocation that is alive between a forward and its backward (`slot`: group index
+        # of the first layer, 1000*layer + meta-path for stacked layers): the backward reads T and R straight from
+        # the tables, so two plans of the same shape must never share one.
+        key = (G, K, H, self.n_pad, int(slot))
         if key not in self._tables:
             TS, RS = query("han_table_stride", K, H), query("han_record_stride", K, H)
-            try:
-                self._tables[key] = SymmetricTables(self, G, TS, RS)
-            except Exception as ex:  # noqa: BLE001  (API or fabric without multicast)
-                import warnings
-                warnings.warn(f"han_b200.dist: symmetric-memory exchange unavailable ({type(ex).__name__}: {ex}); "
-                              "using NCCL all-gathers")
-                self.use_multicast = False
-                self.comm = "nccl"
-                return None
+            # No silent downgrade: a system without symmetric memory must be run with HAN_DIST_COMM=nccl explicitly.
+            self._tables[key] = SymmetricTables(self, G, TS, RS)
         return self._tables[key]
 
     # ---- collectives ---------------------------------------------------------------------------
@@ -325,12 +321,12 @@ class RowShard:
             # per-destination partial sums accumulated inside the gather pass (vector reductions in L2)
             df1_part = torch.zeros(n_all, K, dtype=torch.float32, device=dev)
             call("han_attn_bwd_src_chunked", ptr(bs.indptr), ptr(bs.indices), ptr(be.pos_in_dst), ptr(cr), n_chunks,
-                 n_loc, ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), None, ptr(df1_part), ptr(plan.seed),
+                 n_loc, ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), None, ptr(df1_part), None, ptr(plan.seed),
                  1.0 - plan.coef_drop, plan.metapath_id(g), row0, stream_ptr())
         else:
             dl = torch.empty(max(bs.nnz, 1), K, dtype=torch.float32, device=dev)
             call("han_attn_bwd_src_chunked", ptr(bs.indptr), ptr(bs.indices), ptr(be.pos_in_dst), ptr(cr), n_chunks,
-                 n_loc, ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), ptr(dl), None, ptr(plan.seed),
+                 n_loc, ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), ptr(dl), None, None, ptr(plan.seed),
                  1.0 - plan.coef_drop, plan.metapath_id(g), row0, stream_ptr())
             df1_part = torch.empty(n_all, K, dtype=torch.float32, device=dev)
             call("han_attn_bwd_dst", ptr(be.by_dst_indptr), n_all, bs.nnz, ptr(dl), K, ptr(df1_part), stream_ptr())

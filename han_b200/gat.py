@@ -51,31 +51,31 @@ class GAT(BaseGAttN):
         graph = layers.as_graph(bias_mat, x.device)
         if params is None:
             params = variables.GATParams(x.shape[1], nb_classes, hid_units, n_heads, device=x.device, residual=residual)
-        if residual and ffd_drop and any("W_res" in lay for lay in params.hidden):
-            raise NotImplementedError("residual conv1d on a per-head dropped input (layers.py:19,40) is not built")
         seed = None
         if attn_drop or ffd_drop:
-            seed = params.drop_seed
-            seed.add_(1)
+            seed = ops.next_seed(params.drop_seed)                  # this call's own snapshot (fwd + bwd masks)
         act = ops.activation_code(activation)
 
         def layer(h, lay, K, H, act_code, stream_id, mode):
             Hp = next(c for c in (4, 8, 16) if c >= H) if H <= 16 else H
             W, a1, a2, bias = _pad_heads(lay, K, H, Hp)
+            res = None
+            if "W_res" in lay:      # ret + conv1d(seq, H, 1) before the activation (layers.py:38-40), per-head dropped input
+                pad = torch.nn.functional.pad
+                Fin = lay["W_res"].shape[0]
+                W_res = lay["W_res"] if Hp == H else pad(lay["W_res"].view(Fin, K, H), (0, Hp - H)).reshape(Fin, K * Hp)
+                b_res = lay["b_res"] if Hp == H else pad(lay["b_res"].view(K, H), (0, Hp - H)).reshape(K * Hp)
+                res = ops.residual_conv(h, W_res, K, Hp, seed, ffd_drop, stream_id, graph.row_offset)
+                bias = bias + b_res
             plan = ops.NodeAttentionPlan(graphs=[graph], K=K, H=Hp, act=act_code, project_mode=mode, in_drop=ffd_drop,
                                          coef_drop=attn_drop, seed=seed, metapath_ids=[stream_id])
             z = ops.node_attention(plan, h, W, a1.unsqueeze(0), lay["b1"].unsqueeze(0), a2.unsqueeze(0),
-                                   lay["b2"].unsqueeze(0), bias.unsqueeze(0))[:, 0, :]
+                                   lay["b2"].unsqueeze(0), bias.unsqueeze(0), res)[:, 0, :]
             return z if Hp == H else z.view(-1, K, Hp)[:, :, :H].reshape(-1, K * H)
 
         h = x
         for l, (lay, (K, H)) in enumerate(zip(params.hidden, params.layer_dims)):   # :11-23
-            use_res = "W_res" in lay
-            z = layer(h, lay, K, H, _lib.ACT_IDENTITY if use_res else act, l, project_mode if l == 0 else 0)
-            if use_res:
-                z = torch.addmm(lay["b_res"], h, lay["W_res"]) + z
-                z = z if act == _lib.ACT_IDENTITY else torch.nn.functional.elu(z)
-            h = z
+            h = layer(h, lay, K, H, act, l, project_mode if l == 0 else 0)
         K, C = params.out_heads, params.C
         out = layer(h, params.out, K, C, _lib.ACT_IDENTITY, len(params.hidden), 0)     # :25-29
         logits = out.view(-1, K, C).sum(1) / K                                        # :30
@@ -137,9 +137,6 @@ class HeteGAT_multi(BaseGAttN):
             raise ValueError("attn_drop and ffd_drop are probabilities of dropping, in [0, 1)")
         if len(n_heads) < len(hid_units) + 1:
             raise ValueError("n_heads needs one entry per attention layer plus the output-layer entry")
-        if residual and len(hid_units) > 1 and ffd_drop:
-            raise NotImplementedError("residual=True with ffd_drop > 0: the residual conv1d reads each head's own "
-                                      "dropped copy of the input (layers.py:19,40); not built")
         pairs = list(zip(inputs_list, bias_mat_list))                      # :39
         P = len(pairs)
         xs = [layers._squeeze_batch(x) for x, _ in pairs]
@@ -158,17 +155,16 @@ class HeteGAT_multi(BaseGAttN):
         if attn_drop or ffd_drop:
             # training-mode dropout (ex_acm3025.py:185-186 feeds 0.6 / 0.6; 0.0 at evaluation): a fresh mask
             # set per call; the seed word lives on the device so a captured CUDA graph advances it too
-            seed = params.drop_seed
-            seed.add_(1)
+            seed = ops.next_seed(params.drop_seed)                  # this call's own snapshot (fwd + bwd masks)
 
         coef_out = [None] * P
         groups = _group_by_input(xs)
         z_parts = []
-        for grp in groups:
+        for gi, grp in enumerate(groups):
             plan = ops.NodeAttentionPlan(graphs=[graphs[p] for p in grp], K=K, H=H, act=act,
                                          project_mode=project_mode, dist=dist, want_coefs=return_coef,
                                          in_drop=ffd_drop, coef_drop=attn_drop, seed=seed,
-                                         metapath_ids=[gid(p) for p in grp])
+                                         metapath_ids=[gid(p) for p in grp], slot=gi)
             if len(grp) == 1:
                 p = gid(grp[0])
                 W, a1, b1 = params.W[p], params.a1[p].unsqueeze(0), params.b1[p].unsqueeze(0)
@@ -199,16 +195,17 @@ class HeteGAT_multi(BaseGAttN):
             for p in range(P):
                 h_old = multi_embed[:, p, :].contiguous()                   # :49
                 q = gid(p)
-                plan = ops.NodeAttentionPlan(graphs=[graphs[p]], K=Kl, H=Hl,
-                                             act=_lib.ACT_IDENTITY if use_res else act, project_mode=0, dist=dist,
+                sid = l * params.P + q
+                plan = ops.NodeAttentionPlan(graphs=[graphs[p]], K=Kl, H=Hl, act=act, project_mode=0, dist=dist,
                                              want_coefs=return_coef, in_drop=ffd_drop, coef_drop=attn_drop,
-                                             seed=seed, metapath_ids=[l * params.P + q])
+                                             seed=seed, metapath_ids=[sid], slot=1000 * l + p)
+                res, bias_l = None, lay["bias"][q]
+                if use_res:     # ret + conv1d(seq, H, 1) before the activation; every head reads its own dropped input
+                    res = ops.residual_conv(h_old, lay["W_res"][q], Kl, Hl, seed, ffd_drop, sid, graphs[p].row_offset)
+                    bias_l = bias_l + lay["b_res"][q]
                 h = ops.node_attention(plan, h_old, lay["W"][q], lay["a1"][q].unsqueeze(0), lay["b1"][q].unsqueeze(0),
-                                       lay["a2"][q].unsqueeze(0), lay["b2"][q].unsqueeze(0),
-                                       lay["bias"][q].unsqueeze(0))[:, 0, :]
-                if use_res:                                                 # ret + conv1d(seq, H, 1), then the activation
-                    h = torch.addmm(lay["b_res"][q], h_old, lay["W_res"][q]) + h
-                    h = h if act == _lib.ACT_IDENTITY else torch.nn.functional.elu(h)
+                                       lay["a2"][q].unsqueeze(0), lay["b2"][q].unsqueeze(0), bias_l.unsqueeze(0),
+                                       res)[:, 0, :]
                 if return_coef:
                     coef_out[p] = layers.EdgeCoefs(graphs[p], plan.coefs[0])
                 nxt.append(h)

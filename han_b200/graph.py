@@ -100,6 +100,9 @@ class MetaPathGraph:
         # set when the arrays were produced on another stream (host->device staging, transposition on a
         # side stream): consumers call wait_ready() before their first kernel that reads this graph
         self.ready: Optional[torch.cuda.Event] = None
+        # sp_attn_head only (utils/layers.py:95-96): the stored adjacency values w_ij (fp32, CSR order) that scale
+        # the logits, l_ij = w_ij (f1_i + f2_j); None = the 0/1 adjacency every other operator uses
+        self.edge_weight: Optional[torch.Tensor] = None
 
     def wait_ready(self) -> "MetaPathGraph":
         if self.ready is not None:
@@ -284,41 +287,14 @@ class MetaPathGraph:
                                         int(heavy_rows.numel()), n_slots)
         return self._split
 
-    def source_blocks(self, n_blocks: int):
-        """EXPERIMENTAL (HAN_L2_BLOCKS): the edges regrouped by block of SOURCE nodes -- ``n_blocks`` sub-CSRs
-        over the same rows, block b holding the edges whose source lies in [b*N/B, (b+1)*N/B) -- so that one
-        pass gathers from a slab of the node table small enough to stay in L2.  Every row is cut at the block
-        borders; ``vmaps[b]`` sends row r of pass b to partial slot r*B + b.  Built once, cached."""
-        key = ("_blocks", n_blocks)
-        if getattr(self, "_blk", None) is None or self._blk[0] != key:
-            self.wait_ready()
-            dev, n, B = self.device, self.n_rows, int(n_blocks)
-            with torch.cuda.device(dev):
-                deg = self.indptr[1:] - self.indptr[:-1]
-                rows = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), deg)
-                width = -(-self.n_cols // B)
-                blk = (self.indices.to(torch.int64) // width)
-                key2 = blk * n + rows                                   # (block, row): stable order keeps columns ascending
-                order = torch.argsort(key2, stable=True)
-                cols = self.indices[order].contiguous()
-                cnt = torch.bincount(key2, minlength=B * n).reshape(B, n)
-                base = torch.zeros(B + 1, dtype=torch.int64, device=dev)
-                base[1:] = torch.cumsum(cnt.sum(1), 0)
-                base_h = base.tolist()
-                subs, vmaps = [], []
-                ar = torch.arange(n, device=dev, dtype=torch.int32)
-                for b in range(B):
-                    ip = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-                    ip[1:] = torch.cumsum(cnt[b], 0)
-                    sub = MetaPathGraph(ip, cols[base_h[b]:base_h[b + 1]], n, self.n_cols, base_h[b + 1] - base_h[b],
-                                        row_offset=self.row_offset)
-                    sub.chunks()
-                    subs.append(sub)
-                    vmaps.append(torch.stack([ar, ar * B + b], 1).contiguous())
-                all_rows = ar
-                all_ptr = (torch.arange(n + 1, device=dev, dtype=torch.int64) * B).to(torch.int32)
-            self._blk = (key, subs, vmaps, all_rows, all_ptr)
-        return self._blk[1:]
+    def edge_weight_t(self) -> Optional[torch.Tensor]:
+        """The edge weights in transposed-edge order (``edge_weight[perm]``) for the by-source backward pass;
+        None for a 0/1 adjacency.  Built once per graph, cached."""
+        if self.edge_weight is None:
+            return None
+        if getattr(self, "_ew_t", None) is None:
+            self._ew_t = self.edge_weight[self.transpose().perm.long()].contiguous()
+        return self._ew_t
 
     def row_slice(self, lo: int, hi: int) -> "MetaPathGraph":
         """Destination-row shard [lo, hi) (column ids stay global)."""

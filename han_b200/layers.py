@@ -101,27 +101,25 @@ def attn_head(seq, out_sz, bias_mat, activation, in_drop=0.0, coef_drop=0.0, res
     attn_head.last_params = params
     use_res = bool(residual) and x.shape[1] != H                     # :39-40; equal widths: a dead store (:42)
     if use_res:
-        if in_drop:
-            raise NotImplementedError("residual conv1d on the dropped input (layers.py:19,40) is not built")
         if "W_res" not in params:                                    # conv1d(seq, H, 1): glorot kernel, zero bias
             lim = math.sqrt(6.0 / (x.shape[1] + H))
             params["W_res"] = torch.nn.Parameter(torch.empty(x.shape[1], H).uniform_(-lim, lim).to(x.device))
             params["b_res"] = torch.nn.Parameter(torch.zeros(H, device=x.device))
     seed = None
     if in_drop or coef_drop:
-        seed = _drop_seed(x.device)
-        seed.add_(1)
+        seed = ops.next_seed(_drop_seed(x.device))                   # this call's own snapshot (fwd + bwd masks)
     act = ops.activation_code(activation)
-    plan = ops.NodeAttentionPlan(graphs=[graph], K=1, H=H, act=_lib.ACT_IDENTITY if use_res else act,
-                                 want_coefs=bool(return_coef), in_drop=float(in_drop), coef_drop=float(coef_drop),
-                                 seed=seed)
+    plan = ops.NodeAttentionPlan(graphs=[graph], K=1, H=H, act=act, want_coefs=bool(return_coef),
+                                 in_drop=float(in_drop), coef_drop=float(coef_drop), seed=seed)
+    res, bias = None, params["bias"]
+    if use_res:
+        # ret + conv1d(seq, H, 1) before the activation (:40); `seq` there is the DROPPED input of :19, i.e. the
+        # same mask stream as this head's projection.  The conv's bias is folded into the head bias.
+        res = ops.residual_conv(x, params["W_res"], 1, H, seed, float(in_drop), 0, graph.row_offset)
+        bias = bias + params["b_res"]
     Z = ops.node_attention(plan, x, params["W"], params["a1"].reshape(1, 1, H), params["b1"].reshape(1, 1),
-                           params["a2"].reshape(1, 1, H), params["b2"].reshape(1, 1),
-                           params["bias"].reshape(1, H))
+                           params["a2"].reshape(1, 1, H), params["b2"].reshape(1, 1), bias.reshape(1, H), res)
     ret = Z.reshape(1, x.shape[0], H)
-    if use_res:                                                      # ret + conv1d(seq, H, 1), then the activation
-        ret = ret + torch.addmm(params["b_res"], x, params["W_res"]).unsqueeze(0)
-        ret = ret if act == _lib.ACT_IDENTITY else torch.nn.functional.elu(ret)
     if return_coef:
         return ret, EdgeCoefs(graph, plan.coefs[0])
     return ret
@@ -162,27 +160,36 @@ attn_head_const_1.last_params = None
 
 def sp_attn_head(seq, out_sz, adj_mat, activation, nb_nodes, in_drop=0.0, coef_drop=0.0, residual=False, *,
                  params: Optional[Dict[str, torch.Tensor]] = None):
-    """Sparse-adjacency head (utils/layers.py:85-127): logits ``adj_ij * (f1_i + f2_j)`` on the stored
-    entries, ``sparse_softmax`` over each row's entries.  With the 0/1 adjacency the reference's drivers
-    build this is ``attn_head`` exactly, which already works on the edge list; weighted adjacencies
-    (entries != 1 scale the logits) are rejected rather than silently treated as 1.
+    """Sparse-adjacency head (utils/layers.py:85-127): logits ``adj_ij * f1_i + adj_ij * f2_j`` on the STORED
+    entries (:95-96), leaky_relu, ``tf.sparse_softmax`` over each row's stored entries (:100), sparse @ dense
+    (:113).  The stored values w_ij ride along as one extra 4-byte stream per edge through K-B / K-D; with the
+    0/1 adjacency the reference's drivers build, this is ``attn_head`` exactly.
 
-    adj_mat: a ``MetaPathGraph``, or a torch sparse COO/CSR tensor (N,N) whose stored values are all 1."""
+    adj_mat: a torch sparse COO/CSR tensor (N,N) or (1,N,N) -- its stored values are the weights -- or a
+    ``MetaPathGraph`` (optionally carrying ``edge_weight``)."""
     x = _squeeze_batch(seq)
     if isinstance(adj_mat, torch.Tensor) and adj_mat.layout != torch.strided:
         coo = adj_mat.to_sparse_coo().coalesce()
-        vals = coo.values()
-        if vals.numel() and not bool((vals == 1).all()):
-            raise NotImplementedError("sp_attn_head with edge weights != 1 (logits scaled per edge) is not built")
-        idx = coo.indices()
+        idx, vals = coo.indices(), coo.values()
+        if idx.shape[0] == 3:                                        # batch-size-1 SparseTensor, :110-113
+            if int(coo.shape[0]) != 1:
+                raise ValueError("sp_attn_head assumes batch size 1 (utils/layers.py:110-113)")
+            idx = idx[1:]
         n = int(nb_nodes)
         order = torch.argsort(idx[0] * n + idx[1])
         rows, cols = idx[0][order], idx[1][order]
         indptr = torch.zeros(n + 1, dtype=torch.int64, device=rows.device)
         indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
-        adj_mat = MetaPathGraph.from_csr(indptr.to(x.device), cols.to(torch.int32).to(x.device), n_cols=n, device=x.device)
+        graph = MetaPathGraph.from_csr(indptr.to(x.device), cols.to(torch.int32).to(x.device), n_cols=n, device=x.device)
+        w = vals[order].to(torch.float32).to(x.device).contiguous()
+        if w.numel() and not bool((w == 1).all()):
+            graph.edge_weight = w
+        adj_mat = graph
     elif not isinstance(adj_mat, MetaPathGraph):
         raise TypeError("adj_mat: MetaPathGraph or a torch sparse tensor")
+    if adj_mat.has_empty_rows():
+        raise ValueError("sp_attn_head: a row without stored entries has no softmax (the reference's adjacency "
+                         "carries self-loops)")
     return attn_head(seq, out_sz, adj_mat, activation, in_drop=in_drop, coef_drop=coef_drop, residual=residual,
                      params=params)
 

@@ -16,25 +16,15 @@ from .graph import MetaPathGraph
 
 _ACT = {"elu": _lib.ACT_ELU, "identity": _lib.ACT_IDENTITY}
 
-# Gather-kernel flavour: chunked cp.async edge-stream kernels (default) or the warp-per-row
-# register kernels (HAN_ATTN_CHUNKED=0; kept for A/B measurements, identical results).
 import os as _os
-CHUNKED = _os.environ.get("HAN_ATTN_CHUNKED", "1") != "0"
-# EXPERIMENTAL: forward gather in passes over blocks of source nodes whose node-table slab stays in L2
-L2_BLOCKS = int(_os.environ.get("HAN_L2_BLOCKS", "0"))
 # df1 = sum over a destination's edges of dl.  Default (deterministic): dl is written per edge and summed in a
 # fixed order by han_attn_bwd_dst -- bitwise reproducible gradients, no atomics anywhere.  HAN_DF1_RED=1:
 # accumulated inside the by-source pass with 16-byte vector reductions that resolve in L2 (no per-edge dl array,
 # no by-destination pass): ~2 % faster on the 2M config, summation order not fixed run to run.
 DETERMINISTIC = _os.environ.get("HAN_DF1_RED", "0") != "1"
-# EXPERIMENTAL (written after round 1's GPU budget ran out, to be validated): when a meta-path is split over a PAIR
-# of ranks (tile sharding, NCCL exchange), run the forward on the edges whose source is local while the partner's
-# node-table rows are still in flight, then on the rest, and merge the partial softmax states (the kernels of the
-# heavy-row path).  Hides the pair's T exchange (~0.55 ms of a 15.1 ms step at 8 GPUs).
-LOCAL_FIRST = _os.environ.get("HAN_TILE_LOCAL_FIRST", "0") == "1"
-# EXPERIMENTAL: semantic forward on tcgen05 (semantic_tc.cu): parity-green, 7 % faster than the mma.sync kernel
-# (epilogue-bound); off by default until its epilogue is widened
-SEM_TC = int(_os.environ.get("HAN_SEM_TC", "0") or 0)      # 0 off | 1, 2, 4 = epilogue groups (1 is the validated one)
+# Semantic layer on tcgen05 (semantic_tc.cu), D = 64, A = 128: on by default; HAN_SEM_TC=0 selects the
+# mma.sync kernels of semantic.cu (any instantiated (D, A)).
+SEM_TC = _os.environ.get("HAN_SEM_TC", "1") != "0"
 
 
 def _empty(shape, device, dtype=torch.float32):
@@ -58,6 +48,8 @@ class NodeAttentionPlan:
     coef_drop: float = 0.0                 # attn_drop: attention coefficients
     seed: Optional[torch.Tensor] = None    # int32[1] on the device (a captured graph can advance it)
     metapath_ids: Optional[Sequence[int]] = None   # stream ids of the G meta-paths (default 0..G-1)
+    slot: int = 0                          # sharded runs: which symmetric-memory table set this invocation owns --
+                                           # every plan alive between a forward and its backward needs its own
 
     def metapath_id(self, g: int) -> int:
         return int(self.metapath_ids[g]) if self.metapath_ids is not None else g
@@ -82,8 +74,8 @@ class NodeAttentionFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, plan: NodeAttentionPlan, X, W, a1, b1, a2, b2, bias):
-        _lib.require_cuda(X, W, a1, b1, a2, b2, bias)
+    def forward(ctx, plan: NodeAttentionPlan, X, W, a1, b1, a2, b2, bias, res=None):
+        _lib.require_cuda(X, W, a1, b1, a2, b2, bias, res)
         G, K, H, D = plan.G, plan.K, plan.H, plan.D
         if not query("han_attn_shape_supported", K, H):
             raise _lib.HanError(f"(K,H)=({K},{H}) is not instantiated in libhan_sm100.so")
@@ -91,10 +83,14 @@ class NodeAttentionFn(torch.autograd.Function):
         W, a1, b1, a2, b2, bias = (t.contiguous() for t in (W, a1, b1, a2, b2, bias))
         n, F = X.shape
         assert W.shape == (F, G * D) and a1.shape == (G, K, H) and bias.shape == (G, D)
+        if res is not None:
+            # residual term of utils/layers.py:38-40, added before the activation inside K-B's epilogue
+            res = res.contiguous()
+            assert G == 1 and res.shape == (n, D), "res: (n, D), one meta-path per plan"
         dev = X.device
         TS, RS = query("han_table_stride", K, H), query("han_record_stride", K, H)
         dist = plan.dist
-        tabs = dist.symmetric_tables(G, K, H) if dist is not None else None
+        tabs = dist.symmetric_tables(G, K, H, plan.slot) if dist is not None else None
         with torch.cuda.device(dev):
             fused_mc = False
             t_rows = r_rows = 0
@@ -163,69 +159,36 @@ class NodeAttentionFn(torch.autograd.Function):
                 graph.wait_ready()                     # staged on another stream (host-fed graphs)
                 colmean = None
                 if graph.has_empty_rows():
-                    # dense-path semantics of an all -1e9 row: uniform 1/N over all nodes
-                    colmean = T_src[g][:, :D].mean(0).contiguous()
-                sv = graph.split_view() if CHUNKED else None
-                if (CHUNKED and LOCAL_FIRST and tabs is None and dist is not None and dist.world == 2 and sv is None
-                        and not graph.has_empty_rows()):
-                    import ctypes
-                    subs, vmaps, all_rows, all_ptr = graph.source_blocks(2)     # block b = sources owned by rank b
-                    part = _empty((n * 2, K, H + 2), dev)
-                    me = dist.rank
-                    lo_src = dist.row_range(dist.n_total)[0]
-                    # local table addressed by GLOBAL source id: row j of the full table is local row j - lo
-                    T_local = ctypes.c_void_p(T[g].data_ptr() - lo_src * TS * 4)
-                    for b, table in ((me, T_local), (1 - me, None)):
-                        if table is None:
-                            table = ptr(T_src[g])          # waits for the partner's rows only now
-                        cr, n_chunks = subs[b].chunks()
-                        call("han_attn_fwd_chunked_split", ptr(subs[b].indptr), ptr(subs[b].indices), ptr(cr), n_chunks,
-                             n, table, ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D, ptr(V[g]),
-                             None, ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), row0, ptr(vmaps[b]),
-                             ptr(part), None, None, 0, stream_ptr(), kernels=1)
-                    call("han_attn_fwd_merge", ptr(all_rows), ptr(all_ptr), n, ptr(part), ptr(R[g]), ptr(bias[g]), K, H,
-                         plan.act, ptr(Z[:, g, :]), G * D, ptr(V[g]), stream_ptr())
-                elif CHUNKED and L2_BLOCKS > 1 and sv is None and dist is None and not graph.has_empty_rows():
-                    B = L2_BLOCKS
-                    subs, vmaps, all_rows, all_ptr = graph.source_blocks(B)
-                    part = _empty((n * B, K, H + 2), dev)
-                    for b, sub in enumerate(subs):
-                        cr, n_chunks = sub.chunks()
-                        call("han_attn_fwd_chunked_split", ptr(sub.indptr), ptr(sub.indices), ptr(cr), n_chunks, n,
-                             ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D, ptr(V[g]),
-                             None, ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), row0, ptr(vmaps[b]),
-                             ptr(part), None, None, 0, stream_ptr(), kernels=1)
-                    call("han_attn_fwd_merge", ptr(all_rows), ptr(all_ptr), n, ptr(part), ptr(R[g]), ptr(bias[g]), K, H,
-                         plan.act, ptr(Z[:, g, :]), G * D, ptr(V[g]), stream_ptr())
-                elif sv is not None:
+                    # dense-path semantics of an all -1e9 row: uniform 1/N over all N nodes (padded rows of a
+                    # sharded table are zero, so the sum over the table divided by N is the mean over real rows)
+                    n_all_nodes = dist.n_total if dist is not None else T_src[g].shape[0]
+                    colmean = (T_src[g][:, :D].sum(0) / n_all_nodes).contiguous()
+                ew = graph.edge_weight                 # sp_attn_head's stored adjacency values (None: 0/1 adjacency)
+                sv = graph.split_view()
+                if sv is not None:
                     # heavy rows are cut into segments; a merge kernel combines their partial softmax states
                     part = _empty((sv.n_slots, K, H + 2), dev)
                     call("han_attn_fwd_chunked_split", ptr(sv.indptr_v), ptr(graph.indices), ptr(sv.chunk_rows),
                          sv.n_chunks, n, ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]),
-                         G * D, ptr(V[g]), ptr(colmean), ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g),
-                         row0, ptr(sv.vmap), ptr(part), ptr(sv.heavy_rows), ptr(sv.heavy_ptr), sv.n_heavy,
-                         stream_ptr())
-                elif CHUNKED:
+                         G * D, ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, ptr(plan.seed), 1.0 - plan.coef_drop,
+                         plan.metapath_id(g), row0, ptr(sv.vmap), ptr(part), ptr(sv.heavy_rows), ptr(sv.heavy_ptr),
+                         sv.n_heavy, stream_ptr())
+                else:
                     cr, n_chunks = graph.chunks()
                     call("han_attn_fwd_chunked", ptr(graph.indptr), ptr(graph.indices), ptr(cr), n_chunks, n,
                          ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D,
-                         ptr(V[g]), ptr(colmean), ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), row0,
-                         stream_ptr())
-                else:
-                    if plan.coef_drop:
-                        raise _lib.HanError("attention dropout needs the chunked kernels (HAN_ATTN_CHUNKED=1)")
-                    call("han_attn_fwd", ptr(graph.indptr), ptr(graph.indices), n, ptr(T_src[g]), ptr(R[g]),
-                         ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D, ptr(V[g]), ptr(colmean),
-                         stream_ptr())
+                         ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, ptr(plan.seed), 1.0 - plan.coef_drop,
+                         plan.metapath_id(g), row0, stream_ptr())
                 if plan.want_coefs:
                     alpha = _empty((graph.nnz, K), dev)
                     if graph.nnz:
                         call("han_attn_coefs", ptr(graph.indptr), ptr(graph.indices), n, ptr(T_src[g]),
-                             ptr(R[g]), K, H, ptr(alpha), stream_ptr())
+                             ptr(R[g]), K, H, ptr(ew), ptr(alpha), stream_ptr())
                     plan.coefs.append(alpha)
         ctx.plan = plan
         ctx.S_keep = S_keep
         ctx.W = W if ctx.needs_input_grad[1] else None     # only a stacked layer needs W again (for dX)
+        ctx.has_res = res is not None
         ctx.save_for_backward(X, a1, a2, T, R, V, Z)
         ctx.mark_non_differentiable()
         return Z
@@ -248,7 +211,7 @@ class NodeAttentionFn(torch.autograd.Function):
             part_par = _empty((NB, 2 * D + 2 * K), dev)
             dbias = _empty((G, D), dev)
             dpar = _empty((G, 2 * D + 2 * K), dev)
-            tabs = dist.symmetric_tables(G, K, H) if dist is not None else None
+            tabs = dist.symmetric_tables(G, K, H, plan.slot) if dist is not None else None
             lo_row = dist.row_range(dist.n_total)[0] if dist is not None else 0
             fused_mc = tabs is not None and dist.comm == "multicast"
             # 1) row-local prep for every meta-path: dV, delta into the row records; bias gradient
@@ -272,26 +235,24 @@ class NodeAttentionFn(torch.autograd.Function):
             for g, graph in enumerate(plan.graphs):
                 if dist is None:
                     gt = graph.transpose().wait_ready()
-                    red = CHUNKED and not DETERMINISTIC
+                    ew_t = graph.edge_weight_t()        # weights in transposed-edge order (None: 0/1 adjacency)
+                    red = not DETERMINISTIC
                     dl = None if red else _empty((max(graph.nnz, 1), K), dev)
                     df1 = torch.zeros((n, K), dtype=torch.float32, device=dev) if red else _empty((n, K), dev)
                     df1_red = ptr(df1) if red else None
-                    tv = gt.split_view() if CHUNKED else None
+                    tv = gt.split_view()
                     if tv is not None:
                         part = _empty((tv.n_slots, K, H + 2), dev)
                         call("han_attn_bwd_src_chunked_split", ptr(tv.indptr_v), ptr(gt.indices), ptr(gt.perm),
                              ptr(tv.chunk_rows), tv.n_chunks, n, ptr(T[g]), ptr(R[g]), K, H, ptr(dS[g]), ptr(df2),
-                             ptr(dl), df1_red, ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), 0,
+                             ptr(dl), df1_red, ptr(ew_t), ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), 0,
                              ptr(tv.vmap), ptr(part), ptr(tv.heavy_rows), ptr(tv.heavy_ptr), tv.n_heavy, stream_ptr())
-                    elif CHUNKED:
+                    else:
                         cr, n_chunks = gt.chunks()
                         call("han_attn_bwd_src_chunked", ptr(gt.indptr), ptr(gt.indices), ptr(gt.perm), ptr(cr),
-                             n_chunks, n, ptr(T[g]), ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(dl), df1_red,
+                             n_chunks, n, ptr(T[g]), ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(dl), df1_red, ptr(ew_t),
                              ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), 0, stream_ptr())
-                    else:
-                        call("han_attn_bwd_src", ptr(gt.indptr), ptr(gt.indices), ptr(gt.perm), n, ptr(T[g]),
-                             ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(dl), stream_ptr())
-                    sv = graph.split_view() if CHUNKED else None
+                    sv = graph.split_view()
                     if red:
                         pass                                      # df1 is complete
                     elif sv is not None:
@@ -358,7 +319,9 @@ class NodeAttentionFn(torch.autograd.Function):
                     call("han_project_dx", ptr(dS[g]), n, K, H, ptr(W[:, g * D:]), G * D, F, ptr(dX), F, 1 if g else 0,
                          ptr(plan.seed) if plan.in_drop else None, 1.0 - plan.in_drop, plan.metapath_id(g), lo_row,
                          stream_ptr())
-        return None, dX, dW, da1, db1, da2, db2, dbias
+        # d(out)/d(res) = act'(.) = what prep left in the records as dV
+        dres = R[0][:, :D].contiguous() if ctx.has_res and ctx.needs_input_grad[8] else None
+        return None, dX, dW, da1, db1, da2, db2, dbias, dres
 
 
 class SemanticAttentionFn(torch.autograd.Function):
@@ -431,8 +394,82 @@ class SemanticAttentionFn(torch.autograd.Function):
         return dZ, dw, db, du, None, None
 
 
-def node_attention(plan: NodeAttentionPlan, X, W, a1, b1, a2, b2, bias) -> torch.Tensor:
-    return NodeAttentionFn.apply(plan, X, W, a1, b1, a2, b2, bias)
+def node_attention(plan: NodeAttentionPlan, X, W, a1, b1, a2, b2, bias, res=None) -> torch.Tensor:
+    return NodeAttentionFn.apply(plan, X, W, a1, b1, a2, b2, bias, res)
+
+
+class ResidualConvFn(torch.autograd.Function):
+    """The residual branch's ``conv1d(seq, H, 1)`` of K heads at once (utils/layers.py:40), WITHOUT its bias
+    (callers fold b_res into the head bias): out[:, kH:(k+1)H] = seq_k W_res[:, kH:(k+1)H], where in training
+    mode seq_k is head k's OWN dropped copy of the input (:18-19: `seq` is reassigned before :40 reads it) --
+    the same mask stream as the head's projection, regenerated from (seed, meta-path, head, node, feature).
+    Exact-FP32 FFMA kernels: han_project_fwd[_drop] forward, han_project_bwd[_drop] / han_project_dx backward."""
+
+    @staticmethod
+    def forward(ctx, X, W_res, K: int, H: int, seed, in_drop: float, metapath: int, row0: int):
+        _lib.require_cuda(X, W_res)
+        X, W_res = X.contiguous(), W_res.contiguous()
+        n, F = X.shape
+        D = K * H
+        assert W_res.shape == (F, D)
+        dev = X.device
+        TS, RS = query("han_table_stride", K, H), query("han_record_stride", K, H)
+        with torch.cuda.device(dev):
+            T, R = _empty((1, n, TS), dev), _empty((1, n, RS), dev)
+            za, zb = torch.zeros(1, K, H, device=dev), torch.zeros(1, K, device=dev)
+            if in_drop:
+                S = _empty((1, n, D), dev)
+                call("han_project_fwd_drop", ptr(X), n, F, X.stride(0), ptr(W_res), D, 1, K, H, ptr(za), ptr(zb), ptr(za),
+                     ptr(zb), ptr(T), ptr(R), ptr(S), ptr(seed), 1.0 - in_drop, metapath, row0, stream_ptr(), kernels=2)
+                out = S[0]
+            else:
+                call("han_project_fwd", ptr(X), n, F, X.stride(0), ptr(W_res), 1, K, H, ptr(za), ptr(zb), ptr(za), ptr(zb),
+                     ptr(T), ptr(R), 0, stream_ptr())
+                out = T[0][:, :D].contiguous()
+        ctx.save_for_backward(X, W_res)
+        ctx.meta = (K, H, seed, in_drop, metapath, row0)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        X, W_res = ctx.saved_tensors
+        K, H, seed, in_drop, metapath, row0 = ctx.meta
+        n, F = X.shape
+        D = K * H
+        dev = X.device
+        dOut = dOut.contiguous()
+        dX = dW = None
+        with torch.cuda.device(dev):
+            if ctx.needs_input_grad[1]:
+                dW = _empty((F, D), dev)
+                if in_drop:
+                    ws_bytes = query("han_project_bwd_drop_workspace_bytes", n, F, D)
+                    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                    call("han_project_bwd_drop", ptr(X), n, F, X.stride(0), ptr(dOut), 1, K, H, ptr(dW), D, ptr(ws),
+                         ws_bytes, ptr(seed), 1.0 - in_drop, metapath, row0, stream_ptr(), kernels=2)
+                else:
+                    ws_bytes = query("han_project_bwd_workspace_bytes", n, F, 1, D)
+                    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                    call("han_project_bwd", ptr(X), n, F, X.stride(0), ptr(dOut), 1, D, ptr(dW), ptr(ws), ws_bytes, 0,
+                         stream_ptr())
+            if ctx.needs_input_grad[0]:
+                dX = _empty((n, F), dev)
+                call("han_project_dx", ptr(dOut), n, K, H, ptr(W_res), D, F, ptr(dX), F, 0,
+                     ptr(seed) if in_drop else None, 1.0 - in_drop, metapath, row0, stream_ptr())
+        return dX, dW, None, None, None, None, None, None
+
+
+def residual_conv(X, W_res, K: int, H: int, seed=None, in_drop: float = 0.0, metapath: int = 0, row0: int = 0):
+    return ResidualConvFn.apply(X, W_res, K, H, seed, float(in_drop), int(metapath), int(row0))
+
+
+def next_seed(counter: torch.Tensor) -> torch.Tensor:
+    """Advances a device-resident dropout seed word and returns a SNAPSHOT of it for this call's plans.  The
+    kernels dereference the seed at execution time, forward and backward; several forward calls followed by
+    one backward (the reference's own pattern, models/gat.py:42-46) would otherwise regenerate every earlier
+    call's masks from the last seed.  add_ and clone are device ops, so a captured CUDA graph advances too."""
+    counter.add_(1)
+    return counter.clone()
 
 
 def semantic_attention(Z, w, b, u, mode: str = "reference", dist=None):

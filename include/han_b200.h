@@ -126,16 +126,15 @@ int han_project_bwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const 
  * alpha_ij S_j, out_i = act(V_i + bias).  T is indexed by the CSR's column ids; f1 is read from
  * R[:, D:D+K]; lse is written to R[:, D+K:D+2K]; V to vsave [n_dst][D]; out to
  * out + i*out_stride (so K-B writes straight into Z[n][P][D], models/gat.py:46,58,60).
- * colmean (nullable) [D]: value used for rows with no edge at all (dense-path uniform 1/N row). */
-int han_attn_fwd(const int64_t* indptr, const int32_t* indices, int64_t n_dst, const float* T,
-                 float* R, const float* bias, int K, int H, int act, float* out, int64_t out_stride,
-                 float* vsave, const float* colmean, han_stream_t stream);
+ * colmean (nullable) [D]: value used for rows with no edge at all (dense-path uniform 1/N row).
+ * edge_w (nullable) [nnz], CSR order: sp_attn_head's stored adjacency values (utils/layers.py:95-96),
+ * l_ij = w_ij (f1_i + f2_j); NULL = the 0/1 adjacency of attn_head.  Entry points: han_attn_fwd_chunked* below. */
 
 /* Per-edge coefficients alpha [nnz][K] (utils/layers.py:43-44 return_coef), from the saved lse. */
 int han_attn_coefs(const int64_t* indptr, const int32_t* indices, int64_t n_dst, const float* T,
-                   const float* R, int K, int H, float* alpha, han_stream_t stream);
+                   const float* R, int K, int H, const float* edge_w, float* alpha, han_stream_t stream);
 
-/* Chunked edge-stream variants of K-B / the by-source pass of K-D (same results): a warp owns a
+/* Chunked edge-stream kernels of K-B / the by-source pass of K-D: a warp owns a
  * contiguous chunk of whole rows (~han_csr_chunk_edges(nnz) edges, boundaries precomputed once per graph) and pulls the
  * gathered rows through a shared-memory cp.async ring, so bytes in flight do not depend on registers
  * and work is balanced by edges, not rows.  chunk_rows: int32[han_csr_num_chunks(nnz) + 1]. */
@@ -146,13 +145,17 @@ int han_csr_chunk_rows(const int64_t* indptr, int64_t n_rows, int64_t nnz, int32
 int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
                          int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                          int K, int H, int act, float* out, int64_t out_stride, float* vsave,
-                         const float* colmean, const uint32_t* seed_ptr, float coef_keep, int metapath,
-                         int64_t row0, han_stream_t stream);
+                         const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
+                         const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0, han_stream_t stream);
+/* resid (nullable) [n_dst][resid_stride]: the residual term of utils/layers.py:38-40, added before the
+ * activation: out_i = act(V_i + bias + resid_i).  Its gradient is dV (R[:, 0:D] after han_attn_bwd_prep). */
 int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
                              const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                              const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                             float* dl_edge, float* df1_red, const uint32_t* seed_ptr, float coef_keep,
-                             int metapath, int64_t row0, han_stream_t stream);
+                             float* dl_edge, float* df1_red, const float* edge_w_t, const uint32_t* seed_ptr,
+                             float coef_keep, int metapath, int64_t row0, han_stream_t stream);
+/* edge_w_t (nullable) [nnz]: the edge weights in TRANSPOSED-edge order (edge_w[perm[t]]); dl then carries the
+ * factor w_ij (d l_ij / d f1_i = d l_ij / d f2_j = w_ij). */
 /* df1_red (nullable): when given, df1[dst][k] += dl is accumulated right here with 16-byte vector reductions
  * (red.global.add.v4.f32, resolved in L2; the caller zeroes df1 first) instead of writing dl per edge for
  * han_attn_bwd_dst: 64 bytes per edge less memory traffic, at the price of a summation order that is not
@@ -174,12 +177,9 @@ int han_attn_bwd_prep(const float* dout, int64_t dout_stride, const float* out, 
  * record (dV | f1 | lse | delta) of local row i is written to row r_row0 + i of every rank's copy
  * (prep fused with the all-gather of the records); f1 and lse are read from the local R. */
 
-/* by-source pass over the transposed structure: for source rows [0,n_src):
+/* by-source pass over the transposed structure (han_attn_bwd_src_chunked above): for source rows [0,n_src):
  *   dS_agg_j = sum_i alpha_ij dV_i ; df2_j = sum_i dl_ij ; dl_edge[perm[t]][K] = dl_ij
  * where dl_ij = alpha_ij (dV_i.S_j - delta_i) * leaky'(f1_i + f2_j).  Tsrc rows = local sources. */
-int han_attn_bwd_src(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
-                     int64_t n_src, const float* Tsrc, const float* R, int K, int H, float* dS_agg,
-                     float* df2, float* dl_edge, han_stream_t stream);
 
 /* Heavy rows (power-law meta-paths).  The same two passes over a VIRTUAL-row CSR: indptr_v [n_v+1] is the
  * CSR's offsets with cut points inserted so that no row exceeds a fixed number of edges (column array and
@@ -192,20 +192,15 @@ int han_attn_bwd_src(const int64_t* t_indptr, const int32_t* t_indices, const in
 int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, const int32_t* chunk_rows,
                                int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                                int K, int H, int act, float* out, int64_t out_stride, float* vsave,
-                               const float* colmean, const uint32_t* seed_ptr, float coef_keep, int metapath,
-                               int64_t row0, const int32_t* vmap, float* part, const int32_t* heavy_rows,
-                               const int32_t* heavy_ptr, int n_heavy, han_stream_t stream);
-/* The forward merge on its own (pass n_heavy = 0 above to skip the built-in one): for rows whose segments come
- * from several launches (source-blocked forward: one launch per block of source nodes whose node-table slab
- * stays in L2; every row is cut at the block borders). */
-int han_attn_fwd_merge(const int32_t* heavy_rows, const int32_t* heavy_ptr, int64_t n_heavy, const float* part,
-                       float* R, const float* bias, int K, int H, int act, float* out, int64_t out_stride,
-                       float* vsave, han_stream_t stream);
+                               const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
+                               const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0, const int32_t* vmap,
+                               float* part, const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
+                               han_stream_t stream);
 int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_indices, const int32_t* perm,
                                    const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                                    const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                                   float* dl_edge, float* df1_red, const uint32_t* seed_ptr, float coef_keep,
-                                   int metapath, int64_t row0, const int32_t* vmap, float* part,
+                                   float* dl_edge, float* df1_red, const float* edge_w_t, const uint32_t* seed_ptr,
+                                   float coef_keep, int metapath, int64_t row0, const int32_t* vmap, float* part,
                                    const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
                                    han_stream_t stream);
 

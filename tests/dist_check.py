@@ -54,6 +54,53 @@ def run_case(shard, cfg, params, mode):
             assert_close(gp[k], v, f"d{k}")
 
 
+def run_stacked_case(shard):
+    """Several plans alive between forward and backward: stacked layers (hid_units=[8,8], one plan per meta-path
+    and layer) AND a different feature tensor per meta-path (one group each).  Every plan invocation must own its
+    symmetric-memory table set (the backward reads T / R from the tables)."""
+    cfg = synth.tiny(seed=81, n=203, f=24, p=2, deg=6.0)
+    rng = np.random.default_rng(82)
+    params = O.init_params(rng, [cfg.F] * cfg.P, cfg.C, hid=8, heads=4, mp_att_size=32, deep=[(2, 8)], residual=True)
+    X2 = rng.normal(size=cfg.X.shape).astype(np.float32)
+    N, P, C = cfg.N, cfg.P, cfg.C
+    dev = shard.device
+    lo, hi = shard.row_range(N)
+    p64 = O.params_to(params, torch.float64, requires_grad=True)
+    Xs = [torch.from_numpy(cfg.X).double()[None], torch.from_numpy(X2).double()[None]]
+    biases = [torch.from_numpy(O.adj_to_bias(a, [N], 1)) for a in cfg.adjs()]
+    labels64 = torch.from_numpy(cfg.labels).double()
+    mask64 = torch.from_numpy(cfg.train_mask.astype(np.float64))
+    total_o, _, logits_o, fe_o, _ = O.step_loss(Xs, biases, labels64, mask64, p64, C, [8, 8], [4, 2, 1], 0.001, "reference",
+                                               residual=True)
+    total_o.backward()
+    hp = hb.HANParams([cfg.F] * P, C, (8, 8), (4, 2, 1), 32, device=dev, residual=True).load_dict(params)
+    full = [hb.process.adj_to_bias(a, [N]) for a in cfg.adjs()]
+    graphs = [g.row_slice(lo, hi) for g in full]
+    shard._bwd = {}
+    shard.bind(graphs, N)
+    Xl = [torch.from_numpy(cfg.X[lo:hi]).to(dev)[None], torch.from_numpy(X2[lo:hi]).to(dev)[None]]
+    labels = torch.from_numpy(cfg.labels[lo:hi]).to(dev)
+    mask = torch.from_numpy(cfg.train_mask[lo:hi].astype(np.float32)).to(dev)
+    train = hb.BaseGAttN.training(hp, 0.005, 0.001)
+    logits, fe, _ = hb.HeteGAT_multi.inference(Xl, C, N, True, 0.0, 0.0, graphs, [8, 8], [4, 2, 1], residual=True,
+                                               mp_att_size=32, params=hp, dist=shard)
+    total = shard.masked_loss(logits.reshape(-1, C), labels, mask, train)
+    total.backward()
+    shard.all_reduce_grads(hp)
+    tot = shard.all_reduce_sum(total.detach().clone().reshape(1))
+    torch.cuda.synchronize()
+    assert_close(logits[0], logits_o.detach()[0, lo:hi], "stacked: logits shard")
+    assert_close(fe, fe_o.detach()[lo:hi], "stacked: final_embed shard")
+    assert_close(tot[0], total_o.detach(), "stacked: loss")
+    gp = hp.grad_dict()
+    for k in ("W", "a1", "a2", "bias"):
+        for i in range(P):
+            assert_close(gp[k][i], p64[k][i].grad, f"stacked: d{k}[{i}]")
+    for kk, vv in p64["deep"][0].items():
+        for i, t in enumerate(vv):
+            assert_close(gp["deep"][0][kk][i], t.grad, f"stacked: deep.d{kk}[{i}]")
+
+
 def run_dropout_case(shard):
     """Sharded node attention with training-mode dropout: masks are keyed by GLOBAL node ids, so the
     sharded run must equal the whole-graph oracle fed the same masks (numpy replica of han_rng.cuh)."""
@@ -168,6 +215,7 @@ def main():
         return main_tile()
     shard = hd.RowShard.init_process_group()
     run_dropout_case(shard)
+    run_stacked_case(shard)
     for seed, n, mode in ((61, 257, "reference"), (62, 400, "paper"), (63, 96, "reference")):
         cfg = synth.tiny(seed=seed, n=n, f=36, p=3, deg=6.0)
         cfg.masks[1][:, 5] = True                  # one source every node attends to (crosses shards)

@@ -55,15 +55,7 @@ def _product_node_attention(cfg, par, K, H, act_name, upstream, want_coefs=False
 SHAPES = [(8, 8), (4, 8), (1, 8), (8, 4), (2, 8), (8, 16), (16, 4), (1, 4), (4, 16)]
 
 
-@pytest.fixture(params=[True, False], ids=["chunked", "warp_per_row"])
-def flavour(request, monkeypatch):
-    """Both gather-kernel flavours (cp.async edge-stream chunks / warp-per-row registers)."""
-    from han_b200 import ops
-    monkeypatch.setattr(ops, "CHUNKED", request.param)
-    return request.param
-
-
-def test_chunk_boundaries_on_a_larger_graph(flavour):
+def test_chunk_boundaries_on_a_larger_graph():
     """~75 chunks of 2048 edges: rows straddling batch and chunk boundaries, a row longer than a
     whole chunk, runs of empty transposed rows; checked against the fp64 edge-list twin (forward)
     and its autograd (backward)."""
@@ -106,7 +98,7 @@ def test_chunk_boundaries_on_a_larger_graph(flavour):
 
 
 @pytest.mark.parametrize("K,H", SHAPES)
-def test_node_attention_fwd_bwd_parity(K, H, flavour):
+def test_node_attention_fwd_bwd_parity(K, H):
     cfg = synth.tiny(seed=K * 31 + H, n=131, f=37, p=2, deg=7.0)   # N, F not multiples of 32/4
     rng = np.random.default_rng(K * 100 + H)
     par = _rand_params(rng, cfg.F, cfg.P, K, H)
@@ -156,7 +148,7 @@ def test_identity_activation_and_three_metapaths():
         assert_close(gp[k], go[k], "d" + k)
 
 
-def test_degenerate_rows_and_long_rows(flavour):
+def test_degenerate_rows_and_long_rows():
     """single-neighbour rows (alpha == 1 exactly), a full row, a source every node attends to (long
     transposed row), rows longer than one 32-edge chunk, no-self-loop rows."""
     cfg = synth.tiny(seed=9, n=200, f=24, p=2, deg=3.0)
@@ -277,18 +269,6 @@ def test_heavy_rows_cut_into_segments_match_oracle(split, monkeypatch):
     compare_step(out_o, grads_o, out_p, grads_p)
     assert torch.allclose(out_p["logits"], out_u["logits"], rtol=1e-5, atol=1e-6)
     assert torch.allclose(grads_p["W"][0], grads_u["W"][0], rtol=1e-4, atol=1e-7)
-
-
-def test_source_blocked_forward_matches_oracle(monkeypatch):
-    """The experimental L2-blocked forward (HAN_L2_BLOCKS: one pass per block of source nodes, every row cut
-    at the block borders, han_attn_fwd_merge at the end) computes the same step."""
-    from han_b200 import ops
-    cfg = synth.tiny(seed=151, n=210, f=18, p=2, deg=9.0)
-    params = O.init_params(np.random.default_rng(152), [cfg.F] * cfg.P, cfg.C)
-    out_o, grads_o = oracle_step(cfg, params)
-    monkeypatch.setattr(ops, "L2_BLOCKS", 4)
-    out_p, grads_p, _ = product_step(cfg, params)
-    compare_step(out_o, grads_o, out_p, grads_p)
 
 
 def test_vector_reduction_df1_mode_matches_oracle(monkeypatch):

@@ -39,17 +39,3 @@ def test_tile_sharded_step_matches_oracle():
            "--master-addr", "127.0.0.1", "--master-port", "29539", os.path.join(ROOT, "tests", "dist_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
-
-
-@pytest.mark.skipif(os.environ.get("HAN_RUN_EXPERIMENTAL", "0") != "1",
-                    reason="experimental local-first forward (HAN_TILE_LOCAL_FIRST): run with HAN_RUN_EXPERIMENTAL=1")
-def test_local_first_forward_over_a_pair_matches_oracle():
-    """HAN_TILE_LOCAL_FIRST=1 with the NCCL exchange on exactly 2 ranks: forward over local sources first, the
-    partner's sources after the gather, partial states merged.  Same oracle check as the other exchanges."""
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
-    env = dict(os.environ, HAN_DIST_COMM="nccl", HAN_TILE_LOCAL_FIRST="1")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-           "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "dist_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
-    assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -140,3 +140,99 @@ def test_reference_training_call_with_dropout():
         e0 = hb.HeteGAT_multi.inference([X, X], cfg.C, cfg.N, False, 0.0, 0.0, graphs, [8], [8, 1], params=hp)[1]
         e1 = hb.HeteGAT_multi.inference([X, X], cfg.C, cfg.N, False, 0.0, 0.0, graphs, [8], [8, 1], params=hp)[1]
     assert torch.equal(e0, e1)
+
+
+def _head_oracle_with_product_masks(cfg, hp64, seed_value, g, in_drop, coef_drop, residual):
+    n, F, H = cfg.N, cfg.F, hp64["W"].shape[1]
+    masks = {"x": torch.from_numpy(x_mask(seed_value, g, 0, n, F, 1.0 - in_drop)),
+             "coef": torch.from_numpy(coef_mask(seed_value, g, 0, n, n, 1.0 - coef_drop)),
+             "s": torch.from_numpy(s_mask(seed_value, g, n, H, 1.0 - in_drop))}
+    X = torch.from_numpy(cfg.X).double()[None]
+    bias = torch.from_numpy(O.adj_to_bias(cfg.adjs()[0], [n], 1))
+    return O.attn_head(X, H, bias, O.elu, hp64, in_drop=in_drop, coef_drop=coef_drop, residual=residual, masks=masks)
+
+
+@pytest.mark.gpu
+def test_residual_conv_reads_the_dropped_input():
+    """residual=True in training mode (the reference's training configuration with residual, ex_acm3025.py:185-186):
+    the residual conv1d of utils/layers.py:40 reads `seq` AFTER :19 reassigned it to the dropped copy.  Pinned to the
+    reference by tests/golden/ref_attn_head_dropout_residual.npz (oracle == reference given the same masks); here the
+    CUDA path == oracle given the product's masks, forward and every gradient."""
+    import han_b200 as hb
+    from han_b200 import layers
+    cfg = synth.tiny(seed=301, n=80, f=20, p=1, deg=6.0)
+    rng = np.random.default_rng(302)
+    H, F = 8, cfg.F
+    hp = {"W": rng.normal(size=(F, H)) * 0.3, "a1": rng.normal(size=H), "b1": np.float64(0.05), "a2": rng.normal(size=H),
+          "b2": np.float64(-0.03), "bias": rng.normal(0, 0.1, H), "W_res": rng.normal(size=(F, H)) * 0.3,
+          "b_res": rng.normal(0, 0.1, H)}
+    dev = torch.device("cuda")
+    layers._DROP_SEEDS[str(dev)] = torch.tensor([4242], dtype=torch.int32, device=dev)      # attn_head bumps it to 4243
+    pp = {k: torch.nn.Parameter(torch.as_tensor(v).float().to(dev)) for k, v in hp.items()}
+    graph = hb.process.adj_to_bias(cfg.adjs()[0], [cfg.N])
+    up = torch.from_numpy(rng.normal(size=(1, cfg.N, H)))
+    out = hb.layers.attn_head(torch.from_numpy(cfg.X).to(dev)[None], H, graph, hb.layers.elu, in_drop=0.6, coef_drop=0.6,
+                              residual=True, params=pp)
+    (out * up.float().to(dev)).sum().backward()
+    p64 = {k: torch.as_tensor(v).double().clone().requires_grad_(True) for k, v in hp.items()}
+    ref = _head_oracle_with_product_masks(cfg, p64, 4243, 0, 0.6, 0.6, True)
+    (ref * up).sum().backward()
+    assert_close(out, ref.detach(), "out")
+    for k in p64:
+        assert_close(pp[k].grad, p64[k].grad, "d" + k)
+
+
+@pytest.mark.gpu
+def test_several_dropped_calls_then_one_backward_keep_their_own_masks():
+    """The reference's own pattern (models/gat.py:42-46): attn_head is called K times, THEN the graph is
+    differentiated.  Every call must regenerate ITS masks in the backward (a per-call snapshot of the seed word),
+    not those of the last call."""
+    import han_b200 as hb
+    from han_b200 import layers
+    cfg = synth.tiny(seed=311, n=70, f=16, p=1, deg=6.0)
+    rng = np.random.default_rng(312)
+    H, F = 8, cfg.F
+    dev = torch.device("cuda")
+    layers._DROP_SEEDS[str(dev)] = torch.tensor([900], dtype=torch.int32, device=dev)
+    graph = hb.process.adj_to_bias(cfg.adjs()[0], [cfg.N])
+    X = torch.from_numpy(cfg.X).to(dev)[None]
+    hps, pps, outs = [], [], []
+    for c in range(3):
+        hp = {"W": rng.normal(size=(F, H)) * 0.3, "a1": rng.normal(size=H), "b1": np.float64(0.0), "a2": rng.normal(size=H),
+              "b2": np.float64(0.0), "bias": rng.normal(0, 0.1, H)}
+        pp = {k: torch.nn.Parameter(torch.as_tensor(v).float().to(dev)) for k, v in hp.items()}
+        outs.append(hb.layers.attn_head(X, H, graph, hb.layers.elu, in_drop=0.5, coef_drop=0.5, params=pp))
+        hps.append(hp); pps.append(pp)
+    up = torch.from_numpy(rng.normal(size=(1, cfg.N, 3 * H)))
+    (torch.cat(outs, -1) * up.float().to(dev)).sum().backward()          # ONE backward after all forwards
+    for c in range(3):
+        p64 = {k: torch.as_tensor(v).double().clone().requires_grad_(True) for k, v in hps[c].items()}
+        ref = _head_oracle_with_product_masks(cfg, p64, 901 + c, 0, 0.5, 0.5, False)
+        (ref * up[..., c * H:(c + 1) * H]).sum().backward()
+        assert_close(outs[c], ref.detach(), f"out[{c}]")
+        for k in p64:
+            assert_close(pps[c][k].grad, p64[k].grad, f"call {c}: d{k}")
+
+
+@pytest.mark.gpu
+def test_stacked_residual_model_trains_with_dropout():
+    """HeteGAT_multi with hid_units=[8,8], residual=True and the reference's 0.6 / 0.6 dropout feed: runs, gives finite
+    gradients for every variable (incl. W_res / b_res), fresh masks per call."""
+    import han_b200 as hb
+    cfg = synth.tiny(seed=321, n=150, f=24, p=2, deg=7.0, binary=True)
+    dev = torch.device("cuda")
+    hp = hb.HANParams([cfg.F] * 2, cfg.C, (8, 8), (4, 2, 1), 32, device=dev, residual=True,
+                      generator=torch.Generator().manual_seed(5))
+    X = torch.from_numpy(cfg.X).to(dev)[None]
+    graphs = [hb.process.adj_to_bias(a, [cfg.N]) for a in cfg.adjs()]
+    labels = torch.from_numpy(cfg.labels).to(dev)
+    mask = torch.from_numpy(cfg.train_mask.astype(np.float32)).to(dev)
+    embs = []
+    for _ in range(2):
+        logits, emb, _ = hb.HeteGAT_multi.inference([X, X], cfg.C, cfg.N, True, 0.6, 0.6, graphs, [8, 8], [4, 2, 1],
+                                                    residual=True, mp_att_size=32, params=hp)
+        hb.BaseGAttN.masked_softmax_cross_entropy(logits.reshape(-1, cfg.C), labels, mask).backward()
+        embs.append(emb.detach().clone())
+    assert all(q.grad is not None and torch.isfinite(q.grad).all() for q in hp.parameters())
+    assert float(hp.deep[0]["W_res"][0].grad.abs().max()) > 0
+    assert not torch.equal(embs[0], embs[1])

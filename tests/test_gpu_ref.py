@@ -1,0 +1,230 @@
+"""The CUDA path against what the REFERENCE'S OWN SOURCE computed: tests/golden/ref_*.npz were produced by
+executing /root/reference/utils/process.py (as shipped) and utils/layers.py, models/gat.py, models/base_gattn.py
+(unmodified, through oracle/refrun/tf1_shim.py) -- see oracle/refrun/make_ref_golden.py.  Nothing here reads
+/root/reference; every call goes autograd.Function -> ctypes -> C-ABI.  fp32 CUDA vs fp64 reference run:
+max-norm relative error <= 1e-5 per tensor (tests/util.py); CSR indices bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden import make_golden
+from tests.golden.trees import unflatten_tree
+from tests.util import assert_close, product_step
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def _graph(d, i=0):
+    import han_b200 as hb
+    dev = torch.device("cuda")
+    n = len(d[f"indptr{i}"]) - 1
+    return hb.MetaPathGraph.from_csr(torch.from_numpy(d[f"indptr{i}"]).to(dev), torch.from_numpy(d[f"indices{i}"]).to(dev),
+                                     n_cols=n)
+
+
+def test_adj_to_bias_builds_the_reference_mask_bit_exact():
+    """utils/process.py:14-25 executed as shipped -> bias; the device builder must give np.nonzero(bias == 0)
+    from the same adj (and from the reference's bias itself) for nhood 1, 2, 3, weighted / negative entries."""
+    import han_b200 as hb
+    d = load("ref_adj_to_bias")
+    for n in sorted({k.split("/")[0] for k in d.keys()}):
+        adj, sizes, nhood, bias = d[f"{n}/adj"], d[f"{n}/sizes"].tolist(), int(d[f"{n}/nhood"]), d[f"{n}/bias"]
+        if sizes[0] != adj.shape[1]:
+            with pytest.raises(Exception):
+                hb.process.adj_to_bias(adj, sizes, nhood=nhood)       # refused, DESIGN section 7
+            continue
+        for g in range(adj.shape[0]):
+            rows, cols = np.nonzero(bias[g] == 0)
+            graph = hb.process.adj_to_bias(adj[g:g + 1], sizes[g:g + 1], nhood=nhood)
+            ip, ix = graph.to_host()
+            assert np.array_equal(ix, cols.astype(np.int32)), n
+            assert np.array_equal(np.diff(ip), np.bincount(rows, minlength=adj.shape[1])), n
+            g2 = hb.MetaPathGraph.from_dense_bias(bias[g].astype(np.float32), device="cuda")
+            ip2, ix2 = g2.to_host()
+            assert np.array_equal(ip2, ip) and np.array_equal(ix2, ix), n
+
+
+@pytest.mark.parametrize("name", ["ref_han_multi_p2_k8h8", "ref_han_multi_p3_k4h8", "ref_han_multi_degenerate"])
+@pytest.mark.parametrize("project_mode", [0, 1])
+def test_han_multi_step_matches_the_reference_run(name, project_mode):
+    """HeteGAT_multi.inference + masked CE + L2 (ex_acm3025.py:139-152): outputs, loss, every gradient, and the
+    variables after one training() step (L2 + TF1 Adam) against the reference's own run."""
+    import han_b200 as hb
+    cfg, params, d, meta = make_golden.load_case(name)
+    if project_mode and (meta["heads"], meta["hid"]) != (8, 8):
+        pytest.skip("the tcgen05 projection is instantiated for 8 heads x 8 hid")
+    out_p, grads_p, hp = product_step(cfg, params, (meta["hid"],), (meta["heads"], 1), "reference", project_mode=project_mode)
+    for k in ("logits", "final_embed", "att_val", "ce", "total"):
+        assert_close(out_p[k], d[k], k)
+    for k in make_golden.LIST_KEYS:
+        for i, g in enumerate(grads_p[k]):
+            assert_close(g, d[f"g_{k}{i}"], f"d{k}[{i}]")
+    for k in make_golden.VEC_KEYS:
+        assert_close(grads_p[k], d[f"g_{k}"], "d" + k)
+    if project_mode:
+        return
+    # one training() step: the fused L2 + Adam kernel on fresh variables
+    dev = torch.device("cuda")
+    hp2 = hb.HANParams([cfg.F] * cfg.P, cfg.C, (meta["hid"],), (meta["heads"], 1), meta["att"], device=dev).load_dict(params)
+    X = torch.from_numpy(cfg.X).to(dev)[None]
+    graphs = [_graph(d, i) for i in range(cfg.P)]
+    logits, _, _ = hb.HeteGAT_multi.inference([X] * cfg.P, cfg.C, cfg.N, True, 0.0, 0.0, graphs, [meta["hid"]],
+                                              [meta["heads"], 1], mp_att_size=meta["att"], params=hp2)
+    labels = torch.from_numpy(cfg.labels).to(dev)
+    mask = torch.from_numpy(cfg.train_mask.astype(np.float32)).to(dev)
+    loss = hb.BaseGAttN.masked_softmax_cross_entropy(logits.reshape(-1, cfg.C), labels, mask)
+    acc = hb.BaseGAttN.masked_accuracy(logits.reshape(-1, cfg.C), labels, mask)
+    assert abs(float(acc) - float(d["acc"])) < 1e-6
+    hb.BaseGAttN.training(hp2, 0.005, 0.001).run(loss)
+    after = make_golden.unflatten_params(d, "a_", cfg.P)
+    new = hp2.to_dict()
+    # the first Adam step moves every variable by ~lr * sign(g): compare where |g| is not tiny (the sign of a
+    # gradient at fp32 rounding level is not defined)
+    for k in make_golden.LIST_KEYS:
+        for i, t in enumerate(new[k]):
+            g = torch.from_numpy(d[f"g_{k}{i}"])
+            big = g.abs() > 1e-4 * g.abs().max()
+            assert torch.allclose(t.detach().double().cpu()[big], after[k][i][big], atol=2e-5), (k, i)
+    for k in make_golden.VEC_KEYS:
+        g = torch.from_numpy(d[f"g_{k}"])
+        big = g.abs() > 1e-4 * g.abs().max()
+        assert torch.allclose(new[k].detach().double().cpu()[big], after[k][big], atol=2e-5), k
+
+
+def test_stacked_layers_with_residual_match_the_reference_run():
+    """models/gat.py:48-57 + utils/layers.py:38-42: hid_units=[8,8,4], n_heads=[4,2,4,1], residual=True."""
+    from han_b200 import synth
+    d = load("ref_han_multi_stacked_residual")
+    params = unflatten_tree(d, "p")
+    N, F, P, C, heads, hid, att, _ = (int(x) for x in d["meta"])
+    deep = [tuple(int(x) for x in r) for r in d["deep"]]
+    masks = []
+    for i in range(P):
+        m = np.zeros((N, N), dtype=bool)
+        m[np.repeat(np.arange(N), np.diff(d[f"indptr{i}"])), d[f"indices{i}"]] = True
+        masks.append(m)
+    tm = d["train_mask"].astype(bool)
+    cfg = synth.SmallConfig("ref", N, F, C, [f"MP{i}" for i in range(P)], d["X"], masks, d["labels"], tm, ~tm, ~tm)
+    hid_units = (hid,) + tuple(h for (_, h) in deep)
+    n_heads = (heads,) + tuple(k for (k, _) in deep) + (1,)
+    out_p, grads_p, _ = product_step(cfg, params, hid_units, n_heads, residual=True)
+    for k in ("logits", "final_embed", "att_val", "ce", "total"):
+        assert_close(out_p[k], d[k], k)
+    g = unflatten_tree(d, "g")
+    for k, v in g.items():
+        if k == "deep":
+            for l, lay in enumerate(v):
+                for kk, vv in lay.items():
+                    for i, t in enumerate(vv):
+                        assert_close(grads_p["deep"][l][kk][i], t, f"deep[{l}].d{kk}[{i}]")
+        elif isinstance(v, list):
+            for i, t in enumerate(v):
+                assert_close(grads_p[k][i], t, f"d{k}[{i}]")
+        else:
+            assert_close(grads_p[k], v, "d" + k)
+
+
+def test_hetegat_head_averaged_coefficients_match_the_reference_run():
+    import han_b200 as hb
+    cfg, params, d, meta = make_golden.load_case("ref_hetegat_coefs")
+    dev = torch.device("cuda")
+    hp = hb.HANParams([cfg.F] * cfg.P, cfg.C, (meta["hid"],), (meta["heads"], 1), meta["att"], device=dev).load_dict(params)
+    graphs = [_graph(d, i) for i in range(cfg.P)]
+    with torch.no_grad():
+        lp, fp, ap, cl = hb.HeteGAT.inference(torch.from_numpy(cfg.X).to(dev)[None], cfg.C, cfg.N, False, 0.0, 0.0, graphs,
+                                              [meta["hid"]], [meta["heads"], 1], mp_att_size=meta["att"], return_coef=True,
+                                              params=hp)
+    assert_close(lp, d["logits"], "logits"); assert_close(fp, d["final_embed"], "final_embed")
+    assert_close(ap, d["att_val"], "att_val")
+    for p in range(cfg.P):
+        assert_close(cl[p].to_dense()[0], d[f"coef{p}"], f"head-averaged coefs[{p}]")
+
+
+def test_gat_inference_matches_the_reference_run():
+    import han_b200 as hb
+    d = load("ref_gat")
+    N, F, _, C = (int(x) for x in d["meta"])
+    params = unflatten_tree(d, "p")
+    hid_units, n_heads, residual = d["hid_units"].tolist(), d["n_heads"].tolist(), bool(d["residual"])
+    gp = hb.GATParams(F, C, hid_units, n_heads, device="cuda", residual=residual).load_dict(params)
+    lp = hb.GAT.inference(torch.from_numpy(d["X"]).cuda()[None], C, N, False, 0.0, 0.0, _graph(d), hid_units, n_heads,
+                          residual=residual, params=gp)
+    ce = hb.BaseGAttN.masked_softmax_cross_entropy(lp.reshape(-1, C), torch.from_numpy(d["labels"]).cuda(),
+                                                   torch.from_numpy(d["train_mask"].astype(np.float32)).cuda())
+    ce.backward()
+    assert_close(lp, d["logits"], "logits"); assert_close(ce, d["ce"], "ce")
+    g = unflatten_tree(d, "g")
+    grads = gp.grad_dict()
+    for l, lay in enumerate(g["hidden"]):
+        for k, v in lay.items():
+            assert_close(grads["hidden"][l][k], v, f"hidden[{l}].d{k}")
+    for k, v in g["out"].items():
+        assert_close(grads["out"][k], v, f"out.d{k}")
+
+
+def _cuda_head(d, keys):
+    return {k: torch.nn.Parameter(torch.from_numpy(d[f"p/{k}"]).float().cuda()) for k in keys}
+
+
+HEAD_KEYS = ["W", "a1", "b1", "a2", "b2", "bias"]
+
+
+def test_attn_head_with_coefficients_and_residual_matches_the_reference_run():
+    import han_b200 as hb
+    d = load("ref_attn_head")
+    pp = _cuda_head(d, HEAD_KEYS + ["W_res", "b_res"])
+    out, coefs = hb.layers.attn_head(torch.from_numpy(d["X"]).cuda()[None], 8, _graph(d), hb.layers.elu, residual=True,
+                                     return_coef=True, params=pp)
+    (out * torch.from_numpy(d["cot"]).float().cuda()).sum().backward()
+    assert_close(out, d["out"], "out")
+    assert_close(coefs.to_dense(), d["coefs"], "coefs")
+    for k, v in pp.items():
+        assert_close(v.grad, d[f"g/{k}"], "d" + k)
+
+
+def test_attn_head_const_1_matches_the_reference_run():
+    import han_b200 as hb
+    d = load("ref_attn_head_const_1")
+    pp = _cuda_head(d, ["W", "bias", "W_res", "b_res"])
+    out = hb.layers.attn_head_const_1(torch.from_numpy(d["X"]).cuda()[None], 8, _graph(d), hb.layers.elu, residual=True,
+                                      params=pp)
+    (out * torch.from_numpy(d["cot"]).float().cuda()).sum().backward()
+    assert_close(out, d["out"], "out")
+    for k, v in pp.items():
+        assert_close(v.grad, d[f"g/{k}"], "d" + k)
+
+
+@pytest.mark.parametrize("tag", ["binary", "weighted"])
+def test_sp_attn_head_matches_the_reference_run(tag):
+    """utils/layers.py:85-127 on a sparse adjacency whose stored values scale the logits (:95-96)."""
+    import han_b200 as hb
+    d = load("ref_sp_attn_head")
+    pp = _cuda_head(d, HEAD_KEYS)
+    N = d["X"].shape[0]
+    rows = np.repeat(np.arange(N), np.diff(d["indptr0"]))
+    adj = torch.sparse_coo_tensor(torch.from_numpy(np.stack([rows, d["indices0"].astype(np.int64)])),
+                                  torch.from_numpy(d[f"{tag}/values"]).float(), (N, N)).cuda()
+    out = hb.layers.sp_attn_head(torch.from_numpy(d["X"]).cuda()[None], 8, adj, hb.layers.elu, N, params=pp)
+    (out * torch.from_numpy(d[f"{tag}/cot"]).float().cuda()).sum().backward()
+    assert_close(out, d[f"{tag}/out"], "out")
+    for k, v in pp.items():
+        assert_close(v.grad, d[f"{tag}/g/{k}"], "d" + k)
+
+
+def test_semantic_layer_matches_the_reference_run():
+    import han_b200 as hb
+    d = load("ref_semantic")
+    Z = torch.from_numpy(d["Z"]).float().cuda().requires_grad_(True)
+    sp = {k: torch.nn.Parameter(torch.from_numpy(d[f"p/{k}"]).float().cuda()) for k in ("w_omega", "b_omega", "u_omega")}
+    out, al = hb.layers.SimpleAttLayer(Z, 128, time_major=False, return_alphas=True, params=sp)
+    (out * torch.from_numpy(d["cot"]).float().cuda()).sum().backward()
+    assert_close(out, d["out"], "out"); assert_close(al, d["alphas"], "alphas"); assert_close(Z.grad, d["g/Z"], "dZ")
+    for k, v in sp.items():
+        assert_close(v.grad, d[f"g/{k}"], "d" + k)

@@ -64,14 +64,13 @@ def test_time_major_and_no_alphas():
     assert torch.equal(a, b)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("HAN_SEM_TC", "0") not in ("1", "2", "4"),
-                    reason="experimental tcgen05 semantic forward (semantic_tc.cu): opt-in, run with HAN_SEM_TC=1|2|4")
+@pytest.mark.parametrize("tc", [True, False], ids=["tcgen05", "mma_sync"])
 @pytest.mark.parametrize("mode", ["reference", "paper"])
 @pytest.mark.parametrize("n,P", [(300, 2), (257, 3), (40000, 4), (65, 1), (5000, 5)])
-def test_semantic_forward_on_tcgen05_matches_oracle(mode, n, P):
-    """HAN_SEM_TC=1 routes the (64, 128) forward through han_semantic_fwd_tc (persistent CTAs, TMA ring,
-    double-buffered TMEM); the backward stays the mma.sync kernel and consumes the v it saved.  Several tiles
-    per CTA (n*P / 128 > 148), partial last tiles, P that does not divide 128."""
+def test_semantic_64x128_on_both_kernel_families(monkeypatch, tc, mode, n, P):
+    """(D, A) = (64, 128) runs on the tcgen05 kernels of semantic_tc.cu by default (persistent CTAs, TMA ring,
+    TMEM accumulators; forward AND backward) and on the mma.sync kernels of semantic.cu with HAN_SEM_TC=0.
+    Several tiles per CTA (n*P / 128 > 148), partial last tiles, P that does not divide 128."""
     from han_b200 import ops
-    assert ops.SEM_TC
+    monkeypatch.setattr(ops, "SEM_TC", tc)
     _run(n, P, 64, 128, mode, seed=n + 11 * P)
