@@ -166,7 +166,7 @@ def test_residual_conv_reads_the_dropped_input():
     hp = {"W": rng.normal(size=(F, H)) * 0.3, "a1": rng.normal(size=H), "b1": np.float64(0.05), "a2": rng.normal(size=H),
           "b2": np.float64(-0.03), "bias": rng.normal(0, 0.1, H), "W_res": rng.normal(size=(F, H)) * 0.3,
           "b_res": rng.normal(0, 0.1, H)}
-    dev = torch.device("cuda")
+    dev = torch.device("cuda", torch.cuda.current_device())
     layers._DROP_SEEDS[str(dev)] = torch.tensor([4242], dtype=torch.int32, device=dev)      # attn_head bumps it to 4243
     pp = {k: torch.nn.Parameter(torch.as_tensor(v).float().to(dev)) for k, v in hp.items()}
     graph = hb.process.adj_to_bias(cfg.adjs()[0], [cfg.N])
@@ -192,7 +192,7 @@ def test_several_dropped_calls_then_one_backward_keep_their_own_masks():
     cfg = synth.tiny(seed=311, n=70, f=16, p=1, deg=6.0)
     rng = np.random.default_rng(312)
     H, F = 8, cfg.F
-    dev = torch.device("cuda")
+    dev = torch.device("cuda", torch.cuda.current_device())
     layers._DROP_SEEDS[str(dev)] = torch.tensor([900], dtype=torch.int32, device=dev)
     graph = hb.process.adj_to_bias(cfg.adjs()[0], [cfg.N])
     X = torch.from_numpy(cfg.X).to(dev)[None]
