@@ -480,7 +480,7 @@ def secondary_acm(dev):
     return {"workload": WORKLOADS["acm"], "edges": cfg.n_edges(), "gpu_ms_per_step": round(gpu_ms, 4),
             "gpu_value": cfg.n_edges() / (gpu_ms * 1e-3), "cpu_reference_ms_per_step": round(cpu_ms, 2),
             "cpu_reference_value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"],
-            "gpu_over_cpu": round(cpu_ms / gpu_ms, 1), "gpu_loss": float(loss),
+            "gpu_over_cpu": round(cpu_ms / gpu_ms, 1), "gpu_loss": float(loss.detach()),
             "note": "complete reference step on both sides (BASELINE configs[0] shape), device-resident inputs"}
 
 
@@ -598,7 +598,9 @@ def parity_check(args, wl, hp, dist, dev, step, rank, world, rows_per_block=250,
         else:
             errs[f"d{k}"] = rel(grads[k], v.grad)
     worst = max(errs, key=errs.get)
-    return {"max_rel": float(f"{errs[worst]:.3e}"), "worst": worst, "rows": M, "receptive_field_nodes": nU,
+    top = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    return {"max_rel": float(f"{errs[worst]:.3e}"), "worst": worst, "worst6": {k: float(f"{v:.2e}") for k, v in top},
+            "rows": M, "receptive_field_nodes": nU,
             "edges_checked": int(sum(int(c.sum()) for c, _ in csr_rows)), "max_row_degree": int(max(int(c.max()) for c, _ in csr_rows)),
             "tolerance": 1e-5, "ok": bool(errs[worst] <= 1e-5), "tensors": len(errs),
             "against": "fp64 edge-list twin of the reference (oracle, pinned to the reference's own source) on the sample's "

@@ -93,8 +93,12 @@ def test_sp_attn_head_on_a_binary_sparse_adjacency_equals_attn_head():
         o = O.attn_head(X, 8, bias, O.elu, hp)
     assert torch.equal(a, b)
     assert_close(a, o, "sp_attn_head vs dense oracle")
-    with pytest.raises(NotImplementedError):
-        hb.layers.sp_attn_head(Xc, 8, (m.float() * 2.0).to_sparse_coo().cuda(), hb.layers.elu, cfg.N, params=pp)
+    with torch.no_grad():      # stored values != 1 scale the logits (utils/layers.py:95-96): a different result
+        w2 = hb.layers.sp_attn_head(Xc, 8, (m.float() * 2.0).to_sparse_coo().cuda(), hb.layers.elu, cfg.N, params=pp)
+        rows, cols = np.nonzero(cfg.masks[0])
+        ow = O.sp_attn_head(X, 8, rows, cols, torch.full((len(rows),), 2.0, dtype=torch.float64), O.elu, cfg.N, hp)
+    assert not torch.equal(w2, a)
+    assert_close(w2, ow, "sp_attn_head with weights 2 vs oracle")
 
 
 @pytest.mark.parametrize("hid_units,n_heads,residual,classes", [((8,), (4, 1), False, 3), ((8, 8), (2, 2, 2), True, 7)])
