@@ -7,9 +7,15 @@
 // TRANSPOSED straight into the canonical K-major SWIZZLE_128B layout the UMMA descriptors expect
 // (16-byte chunk c of row r lives at chunk position c ^ (r % 8) of its 128-byte row; conflict-free
 // STS.128).  One elected thread issues tcgen05.mma.kind::tf32 (M=128 features x N=G*64 x K=8) with
-// 3xTF32 accumulation into TMEM; the accumulator stays in TMEM over the CTA's whole row range and is
-// written once as a split-K partial; the deterministic second-stage reduce is shared with the FFMA
-// path (project.cu).
+// 3xTF32 accumulation into TMEM.
+//
+// Accumulation accuracy: the tensor core adds into its fp32 accumulator with TRUNCATION, so a chain of L node
+// rows drifts by ~7e-9 * L relative to the sum (measured on B200, tools/dw_accuracy.py: 2e-4 over the 27k rows
+// one CTA owns on the 2M-node graph, against 3e-6 for the FFMA kernel -- outside the 1e-5 contract).  The chain
+// is therefore cut every BT_CHAIN_KB k-blocks (256 rows): two TMEM accumulators alternate, and while the MMAs
+// fill one, four drain warps read the other with tcgen05.ld and add it (fp32, round-to-nearest) into this CTA's
+// split-K partial in global memory (128 KB per CTA, L2-resident).  The deterministic second-stage reduce is
+// shared with the FFMA path (project.cu).
 #include "han_common.cuh"
 
 namespace han {
@@ -19,7 +25,9 @@ constexpr int BT_BK = 32;       // rows of X / dS per stage (MMA K, one 128-byte
 constexpr int BT_STAGES = 2;
 constexpr int BT_MAXN = 256;
 constexpr int BT_PRODUCERS = 256;                 // warps 1-8: every load of a stage is in flight before the first store
-constexpr int BT_THREADS = 32 + BT_PRODUCERS;     // warp 0: MMA issuer + TMEM; warps 1-4 also run the epilogue
+constexpr int BT_DRAINERS = 128;                  // warps 9-12: one per TMEM lane quarter (warp id % 4)
+constexpr int BT_THREADS = 32 + BT_PRODUCERS + BT_DRAINERS;     // warp 0: MMA issuer + TMEM
+constexpr int BT_CHAIN_KB = 8;                    // k-blocks (of 32 node rows) accumulated in TMEM before a drain
 constexpr uint32_t BT_A_BYTES = BT_BM * BT_BK * 4;
 constexpr uint32_t BT_B_BYTES = BT_MAXN * BT_BK * 4;
 constexpr uint32_t BT_STAGE_BYTES = 2 * BT_A_BYTES + 2 * BT_B_BYTES;
@@ -105,7 +113,7 @@ project_bwd_tc_kernel(const float* __restrict__ X, int64_t n, int64_t F, int64_t
   const uint32_t base = (bt_smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - bt_smem_u32(smem_raw));
   const uint32_t bars = base + BT_STAGES * BT_STAGE_BYTES;
-  const uint32_t full0 = bars, empty0 = bars + 16, accum = bars + 32;
+  const uint32_t full0 = bars, empty0 = bars + 16, accfull0 = bars + 32, accfree0 = bars + 48;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + BT_STAGES * BT_STAGE_BYTES + 64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -120,12 +128,15 @@ project_bwd_tc_kernel(const float* __restrict__ X, int64_t n, int64_t F, int64_t
       bt_mbar_init(full0 + 8 * s, BT_PRODUCERS);
       bt_mbar_init(empty0 + 8 * s, 1);
     }
-    bt_mbar_init(accum, 1);
+    for (int a = 0; a < 2; ++a) {
+      bt_mbar_init(accfull0 + 8 * a, 1);
+      bt_mbar_init(accfree0 + 8 * a, BT_DRAINERS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bt_smem_u32(tmem_slot)),
-                 "n"(BT_MAXN)
+                 "n"(2 * BT_MAXN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -141,6 +152,12 @@ project_bwd_tc_kernel(const float* __restrict__ X, int64_t n, int64_t F, int64_t
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % BT_STAGES;
         const uint32_t ph = (kb / BT_STAGES) & 1;
+        const int chain = kb / BT_CHAIN_KB, kc0 = kb % BT_CHAIN_KB;     // chain c accumulates into accumulator c & 1
+        const uint32_t acc = tmem_base + (uint32_t)((chain & 1) * BT_MAXN);
+        if (kc0 == 0 && chain >= 2) {                                   // the drain of chain c-2 released this accumulator
+          bt_mbar_wait(accfree0 + 8 * (chain & 1), (uint32_t)(((chain >> 1) - 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
         bt_mbar_wait(full0 + 8 * s, ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = base + s * BT_STAGE_BYTES;
@@ -149,16 +166,50 @@ project_bwd_tc_kernel(const float* __restrict__ X, int64_t n, int64_t F, int64_t
 #pragma unroll
         for (int k = 0; k < BT_BK / 8; ++k) {
           const uint64_t adv = (uint64_t)((k * 32) >> 4);
-          if (MODE == 1) bt_umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-          if (MODE != 3) bt_umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, (MODE == 1) || (kb | k) != 0);
-          bt_umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (MODE != 3) || (kb | k) != 0);
+          if (MODE == 1) bt_umma_tf32(acc, a_lo + adv, b_hi + adv, idesc, (kc0 | k) != 0);
+          if (MODE != 3) bt_umma_tf32(acc, a_hi + adv, b_lo + adv, idesc, (MODE == 1) || (kc0 | k) != 0);
+          bt_umma_tf32(acc, a_hi + adv, b_hi + adv, idesc, (MODE != 3) || (kc0 | k) != 0);
         }
         bt_umma_commit(empty0 + 8 * s);
+        if (kc0 == BT_CHAIN_KB - 1 || kb == nkb - 1) bt_umma_commit(accfull0 + 8 * (chain & 1));
       }
-      bt_umma_commit(accum);
+    }
+  } else if (warp > 8) {
+    // ===== drain warps 9-12: thread = accumulator row = feature; partial += accumulator of every finished chain =====
+    const int q = warp & 3;
+    const int64_t f = f0 + q * 32 + lane;
+    float* dst = part + ((int64_t)blockIdx.y * F + f) * NC;
+    const int nchains = (nkb + BT_CHAIN_KB - 1) / BT_CHAIN_KB;
+    if (nchains == 0 && f < F)
+      for (int c = 0; c < NC; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int chain = 0; chain < nchains; ++chain) {
+      const int a = chain & 1;
+      bt_mbar_wait(accfull0 + 8 * a, (uint32_t)((chain >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BT_MAXN);
+      for (int c0 = 0; c0 < NC; c0 += 32) {
+        uint32_t v[32];
+        bt_tmem_ld32(lane_addr + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (f < F) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 o = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                                   __uint_as_float(v[4 * c + 3]));
+            float4* dp = reinterpret_cast<float4*>(dst + c0 + 4 * c);
+            if (chain > 0) {
+              const float4 p4 = *dp;
+              o.x += p4.x; o.y += p4.y; o.z += p4.z; o.w += p4.w;
+            }
+            *dp = o;
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      bt_mbar_arrive(accfree0 + 8 * a);
     }
   } else {
-    // ===== producers (warps 1-8), then epilogue (warps 1-4) =====
+    // ===== producers (warps 1-8) =====
     // Per 32-row stage a thread owns half a feature column of X (16 values: feature fa, rows 16*half..) and one
     // column of dS (32 values); all 48 loads are issued before the first transposing store, so a CTA keeps a
     // whole 48 KB stage in flight instead of 4-8 loads per thread.
@@ -203,37 +254,12 @@ project_bwd_tc_kernel(const float* __restrict__ X, int64_t n, int64_t F, int64_t
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core reads
       bt_mbar_arrive(full0 + 8 * s);
     }
-    if (warp > 4) goto done;   // warps 5-8 have no accumulator rows to drain
-    // ---- epilogue: thread = accumulator row = feature ----
-    const int q = warp & 3;
-    const int64_t f = f0 + q * 32 + lane;
-    float* dst = part + ((int64_t)blockIdx.y * F + f) * NC;
-    if (nkb > 0) {
-      bt_mbar_wait(accum, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < NC; c0 += 32) {
-        uint32_t v[32];
-        bt_tmem_ld32(lane_addr + c0, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (f < F) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<float4*>(dst + c0 + 4 * c) =
-                make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
-                            __uint_as_float(v[4 * c + 3]));
-        }
-      }
-    } else if (f < F) {
-      for (int c = 0; c < NC; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
   }
-done:
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BT_MAXN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BT_MAXN) : "memory");
   }
 }
 
