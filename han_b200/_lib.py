@@ -47,9 +47,9 @@ _SIGNATURES = {
     "han_csr_chunk_edges": (c_int64, [I64]),
     "han_csr_num_chunks": (c_int64, [I64]),
     "han_csr_chunk_rows": (c_int, [P, I64, I64, P, P]),
-    "han_attn_fwd_chunked": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, FL, I, I64, P]),
+    "han_attn_fwd_chunked": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, I64, P, FL, I, I64, P]),
     "han_attn_bwd_src_chunked": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P, P, P, FL, I, I64, P]),
-    "han_attn_fwd_chunked_split": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, FL, I, I64,
+    "han_attn_fwd_chunked_split": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, I64, P, FL, I, I64,
                                            P, P, P, P, I, P]),
     "han_attn_bwd_src_chunked_split": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P, P, P, FL, I, I64,
                                                P, P, P, P, I, P]),

@@ -165,7 +165,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(TC_MAXN)
+                 "n"(2 * TC_MAXN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -206,9 +206,14 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
           const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);   // 32 B per K=8 step inside the swizzle span
-          if (MODE == 1) umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-          if (MODE != 3) umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, (MODE == 1) || (kb | k) != 0);
-          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (MODE != 3) || (kb | k) != 0);
+          // Two accumulators: the tensor core adds into its fp32 accumulator with TRUNCATION (~0.5 ulp of the running
+          // sum per instruction, biased), so the large hi*hi terms get a chain of their own (F/8 instructions instead
+          // of 3F/8) and the 2^-11-times-smaller correction terms lo*hi + hi*lo accumulate separately; the epilogue
+          // adds the two in fp32 (measured at the 2M-node scale: parity of the step 1.2e-5 -> see profiles/).
+          const uint32_t corr = tmem_base + TC_MAXN;
+          if (MODE == 1) umma_tf32(corr, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+          if (MODE != 3) umma_tf32(corr, a_hi + adv, b_lo + adv, idesc, (MODE == 1) || (kb | k) != 0);
+          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
         }
         umma_commit(empty0 + 8 * s);   // frees the stage when these MMAs have read it
       }
@@ -251,6 +256,17 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tmem_ld32(lane_addr + g * D, v0);
       tmem_ld32(lane_addr + g * D + 32, v1);
       tmem_ld_wait();
+      if (MODE != 3) {   // + the correction accumulator (lo*hi + hi*lo)
+        uint32_t c[32];
+        tmem_ld32(lane_addr + TC_MAXN + g * D, c);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(__uint_as_float(v0[i]) + __uint_as_float(c[i]));
+        tmem_ld32(lane_addr + TC_MAXN + g * D + 32, c);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v1[i] = __float_as_uint(__uint_as_float(v1[i]) + __uint_as_float(c[i]));
+      }
       if (row < n_rows) {
         const float* pg = par + g * 144;
         float f1[K], f2[K];
@@ -294,7 +310,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_MAXN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TC_MAXN) : "memory");
   }
 }
 

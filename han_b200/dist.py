@@ -77,10 +77,11 @@ class SymmetricTables:
         dev = shard.device
         n_all = shard.world * shard.n_pad
         self.G, self.TS, self.RS, self.n_all = G, TS, RS, n_all
+        grp = shard.group if shard.group is not None else td.group.WORLD     # a sub-group in tile mode
         self.T = symm.empty(G * n_all * TS, dtype=torch.float32, device=dev)
-        self.hT = symm.rendezvous(self.T, td.group.WORLD)
+        self.hT = symm.rendezvous(self.T, grp)
         self.R = symm.empty(G * n_all * RS, dtype=torch.float32, device=dev)
-        self.hR = symm.rendezvous(self.R, td.group.WORLD)
+        self.hR = symm.rendezvous(self.R, grp)
         self.T_mc = int(self.hT.multicast_ptr)
         self.R_mc = int(self.hR.multicast_ptr)
         if shard.comm == "multicast" and (not self.T_mc or not self.R_mc):

@@ -159,12 +159,14 @@ class HeteGAT_multi(BaseGAttN):
 
         coef_out = [None] * P
         groups = _group_by_input(xs)
+        # tile sharding, single attention layer, one group: K-B stores Z straight into the semantic owners' buffers
+        sink = tile.z_sink(K * H) if (tile is not None and len(hid_units) == 1 and len(groups) == 1) else None
         z_parts = []
         for gi, grp in enumerate(groups):
             plan = ops.NodeAttentionPlan(graphs=[graphs[p] for p in grp], K=K, H=H, act=act,
                                          project_mode=project_mode, dist=dist, want_coefs=return_coef,
                                          in_drop=ffd_drop, coef_drop=attn_drop, seed=seed,
-                                         metapath_ids=[gid(p) for p in grp], slot=gi)
+                                         metapath_ids=[gid(p) for p in grp], slot=gi, z_sink=sink)
             if len(grp) == 1:
                 p = gid(grp[0])
                 W, a1, b1 = params.W[p], params.a1[p].unsqueeze(0), params.b1[p].unsqueeze(0)
@@ -213,7 +215,7 @@ class HeteGAT_multi(BaseGAttN):
 
         if tile is not None:
             # (rows of my attention block, my meta-paths, D) -> (my semantic rows, ALL meta-paths, D): one all-to-all
-            multi_embed = tile.exchange_Z(multi_embed.contiguous())
+            multi_embed = tile.exchange_Z(multi_embed.contiguous(), pushed=bool(sink is not None and sink.used))
 
         final_embed, att_val = layers.SimpleAttLayer(                       # :61-63
             multi_embed, mp_att_size, time_major=False, return_alphas=True,

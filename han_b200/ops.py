@@ -48,6 +48,7 @@ class NodeAttentionPlan:
     coef_drop: float = 0.0                 # attn_drop: attention coefficients
     seed: Optional[torch.Tensor] = None    # int32[1] on the device (a captured graph can advance it)
     metapath_ids: Optional[Sequence[int]] = None   # stream ids of the G meta-paths (default 0..G-1)
+    z_sink: Optional[object] = None        # tiles.ZSink: K-B also stores its rows into the owners' semantic inputs
     slot: int = 0                          # sharded runs: which symmetric-memory table set this invocation owns --
                                            # every plan alive between a forward and its backward needs its own
 
@@ -170,14 +171,27 @@ class NodeAttentionFn(torch.autograd.Function):
                     part = _empty((sv.n_slots, K, H + 2), dev)
                     call("han_attn_fwd_chunked_split", ptr(sv.indptr_v), ptr(graph.indices), ptr(sv.chunk_rows),
                          sv.n_chunks, n, ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]),
-                         G * D, ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, ptr(plan.seed), 1.0 - plan.coef_drop,
+                         G * D, ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, None, 0, ptr(plan.seed), 1.0 - plan.coef_drop,
                          plan.metapath_id(g), row0, ptr(sv.vmap), ptr(part), ptr(sv.heavy_rows), ptr(sv.heavy_ptr),
                          sv.n_heavy, stream_ptr())
+                elif plan.z_sink is not None and colmean is None and ew is None:
+                    # tile sharding: one launch per semantic sub-block of this rank's rows; each also stores its rows
+                    # into the owning rank's semantic input over NVLink, so the all-to-all of Z rides on the gather
+                    sink = plan.z_sink
+                    T_g = ptr(T_src[g])
+                    for (r0, r1, member) in sink.blocks(n):
+                        cr, n_chunks = graph.chunks_for_rows(r0, r1)
+                        o2, o2_stride = sink.out2(member, g)
+                        call("han_attn_fwd_chunked", ptr(graph.indptr[r0:]), ptr(graph.indices), ptr(cr), n_chunks, r1 - r0,
+                             T_g, ptr(R[g][r0:]), ptr(bias[g]), K, H, plan.act, ptr(Z[r0:, g, :]), G * D,
+                             ptr(V[g][r0:]), None, None, ptr(res[r0:]) if res is not None else None, D, o2, o2_stride,
+                             ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), row0 + r0, stream_ptr())
+                    sink.used = True
                 else:
                     cr, n_chunks = graph.chunks()
                     call("han_attn_fwd_chunked", ptr(graph.indptr), ptr(graph.indices), ptr(cr), n_chunks, n,
                          ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D,
-                         ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, ptr(plan.seed), 1.0 - plan.coef_drop,
+                         ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, None, 0, ptr(plan.seed), 1.0 - plan.coef_drop,
                          plan.metapath_id(g), row0, stream_ptr())
                 if plan.want_coefs:
                     alpha = _empty((graph.nnz, K), dev)

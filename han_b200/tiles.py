@@ -61,8 +61,109 @@ def tile_rows(N: int, Hn: int, h: int, Wz: int, member: int) -> Tuple[Tuple[int,
     return (a_lo, a_hi), (s_lo, s_hi), n_hpad, n_sub
 
 
+class ZBuffers:
+    """Symmetric-memory landing zones of the two re-sharding steps between node-level attention (meta-path x
+    row-block tiles) and the semantic layer (row sub-blocks, all meta-paths), inside the Wz ranks that share a row block:
+
+      Zrecv  [n_sub][P][D]      this rank's semantic rows, ALL meta-paths: member m's K-B kernels store their meta-paths'
+                                columns of these rows straight into it over NVLink (han_attn_fwd_chunked's `out2`), so the
+                                all-to-all of Z costs no pass of its own and overlaps the rest of the gather;
+      dZrecv [Wz*n_sub][per][D] the gradient of this rank's attention rows for its own meta-paths: every member pushes the
+                                slice of its semantic backward that belongs here (peer-to-peer copies).
+
+    One cross-rank barrier per direction says "everything has landed"."""
+
+    def __init__(self, tile: "TileShard", D: int):
+        import torch.distributed._symmetric_memory as symm
+        dev = tile.device
+        P, Wz, n_sub, per = tile.P, tile.Wz, tile.n_sub, len(tile.paths)
+        grp = tile.z_group if tile.z_group is not None else td.group.WORLD
+        self.D = D
+        self.zr = symm.empty(n_sub * P * D, dtype=torch.float32, device=dev)
+        self.hz = symm.rendezvous(self.zr, grp)
+        self.dz = symm.empty(Wz * n_sub * per * D, dtype=torch.float32, device=dev)
+        self.hd = symm.rendezvous(self.dz, grp)
+        self.zr.zero_()
+        self.dz.zero_()
+        self.Zrecv = self.zr.view(n_sub, P, D)
+        self.dZrecv = self.dz.view(Wz * n_sub, per, D)
+        self.peer_Z = [self.hz.get_buffer(r, (n_sub, P, D), torch.float32) for r in range(Wz)]
+        self.peer_dZ = [self.hd.get_buffer(r, (Wz * n_sub, per, D), torch.float32) for r in range(Wz)]
+
+    def barrier_Z(self):
+        self.hz.barrier(channel=0)
+
+    def barrier_dZ(self):
+        self.hd.barrier(channel=0)
+
+
+class ZSink:
+    """What ops.NodeAttentionFn needs to fuse the Z re-sharding into K-B: the row sub-blocks of this rank's attention
+    rows and, per sub-block and local meta-path, the peer address its output rows also go to."""
+
+    def __init__(self, tile: "TileShard", bufs: ZBuffers):
+        self.tile, self.bufs = tile, bufs
+        self.used = False
+
+    def blocks(self, n_rows: int):
+        """-> [(r0, r1, member)] : rows [r0, r1) of this rank's attention block are member's semantic rows."""
+        t = self.tile
+        out = []
+        for m in range(t.Wz):
+            r0, r1 = min(n_rows, m * t.n_sub), min(n_rows, (m + 1) * t.n_sub)
+            if r1 > r0:
+                out.append((r0, r1, m))
+        return out
+
+    def out2(self, member: int, g: int):
+        """(pointer, row stride in floats) of local meta-path g's columns in member's Zrecv."""
+        import ctypes
+        t, b = self.tile, self.bufs
+        col = (t.member * len(t.paths) + g) * b.D
+        return ctypes.c_void_p(b.peer_Z[member].data_ptr() + col * 4), t.P * b.D
+
+
 class _ZExchange(torch.autograd.Function):
-    """Z (rows of block h, this rank's meta-paths, D)  ->  (this rank's semantic rows, ALL P meta-paths, D)."""
+    """Z (rows of block h, this rank's meta-paths, D)  ->  (this rank's semantic rows, ALL P meta-paths, D).
+
+    Forward: when K-B already stored its rows into the owners' Zrecv (``pushed``), only the barrier remains; otherwise
+    (stacked layers, heavy-row graphs) the slices are pushed here with peer-to-peer copies.  Backward: the slices of dZ
+    go to the ranks that own those meta-paths (peer-to-peer copies into their dZrecv), one barrier."""
+
+    @staticmethod
+    def forward(ctx, Z, tile: "TileShard", pushed: bool):
+        n_h, per, D = Z.shape
+        b = tile.zbuffers(D)
+        if not pushed:
+            for m in range(tile.Wz):
+                r0, r1 = min(n_h, m * tile.n_sub), min(n_h, (m + 1) * tile.n_sub)
+                if r1 > r0:
+                    b.peer_Z[m][:r1 - r0, tile.member * per:(tile.member + 1) * per, :].copy_(Z[r0:r1], non_blocking=True)
+        _lib.trace_mark("Z landed >")
+        b.barrier_Z()
+        _lib.trace_mark("Z landed <")
+        ctx.tile, ctx.n_h, ctx.per = tile, n_h, per
+        n_sem = tile.sem_rows[1] - tile.sem_rows[0]
+        return b.Zrecv[:n_sem]
+
+    @staticmethod
+    def backward(ctx, dOut):
+        tile, n_h, per = ctx.tile, ctx.n_h, ctx.per
+        n_sem, P, D = dOut.shape
+        b = tile.zbuffers(D)
+        me = tile.member
+        _lib.trace_mark("dZ push >")
+        for m in range(tile.Wz):
+            if n_sem:
+                b.peer_dZ[m][me * tile.n_sub:me * tile.n_sub + n_sem].copy_(dOut[:, m * per:(m + 1) * per, :], non_blocking=True)
+        b.barrier_dZ()
+        _lib.trace_mark("dZ push <")
+        return b.dZrecv[:n_h], None, None
+
+
+class _ZExchangeA2A(torch.autograd.Function):
+    """The same re-sharding as ONE ``all_to_all_single`` each way: used with the gloo backend (CPU tests of the layout
+    arithmetic) and with HAN_DIST_COMM=nccl."""
 
     @staticmethod
     def forward(ctx, Z, tile: "TileShard"):
@@ -106,11 +207,18 @@ class TileShard:
             zg = [td.new_group([h * P + p for p in range(P)]) for h in range(self.Hn)]
             ag = [td.new_group([h * P + p for h in range(self.Hn)]) for p in range(P)]
             self.z_group = zg[self.h]
+            # T / R exchange inside the ranks that share a meta-path: symmetric-memory tables on that sub-group with
+            # copy-engine pulls (HAN_DIST_COMM=pull, default) or NCCL all-gathers (HAN_DIST_COMM=nccl)
             self.attn = RowShard(self.h, self.Hn, device, group=ag[self.member])
-            self.attn.comm, self.attn.use_multicast = "nccl", False    # symmetric-memory pull on a sub-group: next step
+            if self.attn.comm == "multicast":
+                self.attn.comm = "pull"
         self.n_total = None
         self.attn_rows = self.sem_rows = (0, 0)
         self.n_hpad = self.n_sub = 0
+        self._zbufs = {}
+        import os
+        # Z / dZ re-sharding through symmetric memory (K-B's fused stores + peer copies), or as an all-to-all collective
+        self.fused_z = device.type == "cuda" and os.environ.get("HAN_DIST_COMM", "pull") != "nccl"
 
     @staticmethod
     def init_process_group(P: int) -> "TileShard":
@@ -138,8 +246,23 @@ class TileShard:
             self.attn._bwd = {}
 
     # ---- the one exchange of the forward / backward ------------------------------------------------
-    def exchange_Z(self, Z: torch.Tensor) -> torch.Tensor:
-        return _ZExchange.apply(Z, self)
+    def zbuffers(self, D: int) -> ZBuffers:
+        """Symmetric landing zones for this graph size (collective: every rank of the row block calls it in step)."""
+        key = (self.n_sub, D)
+        if key not in self._zbufs:
+            self._zbufs[key] = ZBuffers(self, D)
+        return self._zbufs[key]
+
+    def z_sink(self, D: int) -> Optional[ZSink]:
+        """Hand this to the LAST attention layer's plans: their K-B kernels then store every output row into the
+        owner's semantic input as well (the all-to-all fused into the kernel's epilogue).  None when the exchange
+        runs as an NCCL / gloo all-to-all."""
+        return ZSink(self, self.zbuffers(D)) if self.fused_z else None
+
+    def exchange_Z(self, Z: torch.Tensor, pushed: bool = False) -> torch.Tensor:
+        if self.fused_z:
+            return _ZExchange.apply(Z, self, pushed)
+        return _ZExchangeA2A.apply(Z, self)
 
     # ---- collectives over all ranks ------------------------------------------------------------------
     def barrier(self):

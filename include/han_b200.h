@@ -142,11 +142,19 @@ int64_t han_csr_chunk_edges(int64_t nnz);   /* ~nnz/(148*32) clamped to [128, 20
 int64_t han_csr_num_chunks(int64_t nnz);
 int han_csr_chunk_rows(const int64_t* indptr, int64_t n_rows, int64_t nnz, int32_t* chunk_rows,
                        han_stream_t stream);
+/* indptr may point at row r0 of a larger CSR (then n_rows / nnz are those of the sub-range and chunk_rows holds
+ * row numbers relative to r0). */
 int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
                          int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                          int K, int H, int act, float* out, int64_t out_stride, float* vsave,
                          const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
-                         const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0, han_stream_t stream);
+                         float* out2, int64_t out2_stride, const uint32_t* seed_ptr, float coef_keep, int metapath,
+                         int64_t row0, han_stream_t stream);
+/* out2 (nullable) [n_dst][out2_stride]: a SECOND destination of every output row -- in tile-sharded multi-GPU runs
+ * a peer-mapped address inside another GPU's semantic-layer input (symmetric memory): the re-sharding all-to-all
+ * of Z is fused into K-B's epilogue as plain stores over NVLink (models/gat.py:58-60 across GPUs).
+ * Row sub-ranges: indptr / R / out / vsave / resid / out2 may point at row r0 of larger arrays (pass row0 + r0) with a
+ * chunk table built by han_csr_chunk_rows over the same sub-range; indices and T stay whole. */
 /* resid (nullable) [n_dst][resid_stride]: the residual term of utils/layers.py:38-40, added before the
  * activation: out_i = act(V_i + bias + resid_i).  Its gradient is dV (R[:, 0:D] after han_attn_bwd_prep). */
 int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
@@ -193,7 +201,8 @@ int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, 
                                int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                                int K, int H, int act, float* out, int64_t out_stride, float* vsave,
                                const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
-                               const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0, const int32_t* vmap,
+                               float* out2, int64_t out2_stride, const uint32_t* seed_ptr, float coef_keep, int metapath,
+                               int64_t row0, const int32_t* vmap,
                                float* part, const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
                                han_stream_t stream);
 int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_indices, const int32_t* perm,
