@@ -626,7 +626,14 @@ def run_e2e(args, wl, hp, train, dist, dev, step):
             graphs = [hb.MetaPathGraph.from_dense_bias(b.to(dev, non_blocking=True)) for b in hB]
             return step(X, graphs)
     else:
-        hX = wl["X"].cpu().pin_memory()
+        tile = dist if (dist is not None and hasattr(dist, "gather_features") and dist.fused_z) else None
+        if tile is not None:
+            # tile sharding: this rank uploads only its SEMANTIC rows of X (1/W of the matrix); the ranks of a row block
+            # hand their slices to one another over NVLink
+            (a_lo, _), (s_lo, s_hi) = tile.rows(wl["N"])
+            hX = wl["X"][s_lo - a_lo:s_hi - a_lo].cpu().pin_memory()
+        else:
+            hX = wl["X"].cpu().pin_memory()
         hG = [(g.indptr.cpu().pin_memory(), g.indices.cpu().pin_memory()) for g in wl["graphs"]]
         h2d = hX.numel() * 4 + sum(a.numel() * 8 + b.numel() * 4 for a, b in hG)
 
@@ -653,7 +660,10 @@ def run_e2e(args, wl, hp, train, dist, dev, step):
                 graphs.append(hb.MetaPathGraph.from_csr(a, b, n_cols=wl["N"], device=dev, row_offset=wl["lo"], stream=copy_s))
                 mark(f"graph {i} on device", copy_s)
             with torch.cuda.stream(copy_s):
-                X = hX.to(dev, non_blocking=True).unsqueeze(0)
+                if tile is not None:
+                    X = tile.gather_features(hX, copy_s).unsqueeze(0)
+                else:
+                    X = hX.to(dev, non_blocking=True).unsqueeze(0)
                 x_ready = torch.cuda.Event()
                 x_ready.record(copy_s)
                 mark("X on device", copy_s)
@@ -673,7 +683,8 @@ def run_e2e(args, wl, hp, train, dist, dev, step):
             main.wait_event(x_ready)
             out = step(X, graphs)
             mark("step done", main)
-            X.record_stream(main)
+            if tile is None:
+                X.record_stream(main)
             return out
     one()                                   # warm-up (allocator, pinned staging)
     if dist:

@@ -143,6 +143,55 @@ class SymmetricTables:
                     _lib.trace_mark(f"pull g{g} peer{r} done")
         return _Pulled(view, events)
 
+    # ---- "push" exchange: producers hand finished row chunks of their block to every peer right away ----------
+    PUSH_CHUNKS = int(os.environ.get("HAN_PUSH_CHUNKS", "4"))
+    PUSH_MIN_ROWS = int(os.environ.get("HAN_PUSH_MIN_ROWS", "4096"))     # tests lower it to chunk tiny graphs too
+
+    def chunk_bounds(self, n: int):
+        """Row chunks of this rank's block for the chunked producers (multiples of 128 rows: projection tiles)."""
+        c = max(1, min(self.PUSH_CHUNKS, n // self.PUSH_MIN_ROWS))
+        step = -(-(-(-n // c)) // 128) * 128
+        return [(r0, min(n, r0 + step)) for r0 in range(0, n, step)]
+
+    def _push(self, view, peers, g, r0, r1):
+        """Copy rows [r0, r1) (table coordinates) of table g (None: all G) of MY copy into every peer's copy, on the
+        push stream, ordered after the work queued so far on the current stream."""
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        st = self.pull_streams[0]
+        st.wait_event(ev)
+        W = self.shard.world
+        with torch.cuda.stream(st):
+            for k in range(1, W):
+                r = (self.shard.rank + k) % W
+                for gg in (range(self.G) if g is None else (g,)):
+                    peers[r][gg, r0:r1].copy_(view[gg, r0:r1], non_blocking=True)
+        _lib.trace_mark(f"push rows {r0}:{r1} queued")
+
+    def _pushed(self, hdl, view):
+        """All pushes of every rank have landed: one cross-rank barrier on the push stream; the current stream waits."""
+        st = self.pull_streams[0]
+        with torch.cuda.stream(st):
+            hdl.barrier(channel=0)
+            done = torch.cuda.Event()
+            done.record(st)
+        torch.cuda.current_stream().wait_event(done)
+        _lib.trace_mark("pushes landed")
+        return view
+
+    def push_T(self, r0: int, r1: int):
+        self._push(self.Tv, self.peers_T, None, r0, r1)
+
+    def pushed_T(self):
+        return self._pushed(self.hT, self.Tv)
+
+    def push_R(self, g: int, r0: int, r1: int):
+        self._push(self.Rv, self.peers_R, g, r0, r1)
+
+    def pushed_R(self):
+        return self._pushed(self.hR, self.Rv)
+
     def exchange_T(self, fused_multicast: bool):
         if fused_multicast:
             self.fence_T(0)           # producers already wrote every rank's copy (multimem.st)
@@ -178,6 +227,8 @@ class RowShard:
         #   "pull"      (default) symmetric memory + copy-engine peer copies, overlapped with the kernels
         #   "multicast" producers write every rank's copy through the NVLS multicast address (multimem.st)
         #   "nccl"      plain NCCL all-gathers on a high-priority side stream
+        #   "push"      symmetric memory; the producers (projection, backward prep) run in row chunks and copy every
+        #               finished chunk into the peers' tables while the next chunk is computed (tile sharding's default)
         self.comm = os.environ.get("HAN_DIST_COMM", "pull")
         self.use_multicast = self.comm != "nccl"
         self.comm_stream = torch.cuda.Stream(device=device, priority=-1) if device.type == "cuda" else None

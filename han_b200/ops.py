@@ -138,17 +138,28 @@ class NodeAttentionFn(torch.autograd.Function):
                 if X.stride(0) % 4 != 0 or X.data_ptr() % 16 != 0:
                     Xa = torch.zeros(n, (F + 3) // 4 * 4, dtype=X.dtype, device=dev)
                     Xa[:, :F] = X
-                for g0 in range(0, G, 4):
-                    g1 = min(G, g0 + 4)
-                    Wg = W[:, g0 * D:g1 * D].contiguous() if (g0, g1) != (0, G) else W
-                    ws_bytes = query("han_project_tc_workspace_bytes", F, g1 - g0, K, H)
-                    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                    call("han_project_fwd_tc", ptr(Xa), n, F, Xa.stride(0), ptr(Wg), g1 - g0, K, H, ptr(a1[g0]),
-                         ptr(b1[g0]), ptr(a2[g0]), ptr(b2[g0]), None if fused_mc else ptr(T[g0]), ptr(R[g0]),
-                         tabs.T_mc_row(g0, 0) if fused_mc else None, t_rows, lo if fused_mc else 0, r_rows,
-                         plan.project_mode, ptr(ws), ws_bytes, stream_ptr(), kernels=2)
+                # "push" exchange: the projection runs in row chunks and every finished chunk of this rank's table block
+                # is copied into the peers' tables (peer-to-peer, copy engines) while the next chunk is being projected
+                push = tabs is not None and dist.comm == "push"
+                bounds = tabs.chunk_bounds(n) if push else [(0, n)]
+                for (c0, c1) in bounds:
+                    for g0 in range(0, G, 4):
+                        g1 = min(G, g0 + 4)
+                        Wg = W[:, g0 * D:g1 * D].contiguous() if (g0, g1) != (0, G) else W
+                        ws_bytes = query("han_project_tc_workspace_bytes", F, g1 - g0, K, H)
+                        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                        call("han_project_fwd_tc", ptr(Xa[c0:]), c1 - c0, F, Xa.stride(0), ptr(Wg), g1 - g0, K, H, ptr(a1[g0]),
+                             ptr(b1[g0]), ptr(a2[g0]), ptr(b2[g0]), None if fused_mc else ptr(T[g0][c0:]), ptr(R[g0][c0:]),
+                             tabs.T_mc_row(g0, 0) if fused_mc else None, t_rows, (lo + c0) if fused_mc else 0, r_rows,
+                             plan.project_mode, ptr(ws), ws_bytes, stream_ptr(), kernels=2)
+                    if push:
+                        tabs.push_T(lo + c0, lo + c1)
             # sources of every local destination row
-            if tabs is not None:
+            if tabs is not None and dist.comm == "push":
+                if plan.in_drop or plan.project_mode == 0 or (K, H) != (8, 8):
+                    tabs.push_T(lo, lo + n)           # FFMA projection: the whole block at once
+                T_src = tabs.pushed_T()               # cross-rank barrier on the push stream
+            elif tabs is not None:
                 T_src = tabs.exchange_T(fused_mc)     # cross-rank fence (+ copy-engine pulls of the peers' blocks)
             else:
                 T_src = dist.all_gather_rows(T) if dist is not None else T    # NCCL all-gather on a side stream
@@ -229,18 +240,28 @@ class NodeAttentionFn(torch.autograd.Function):
             lo_row = dist.row_range(dist.n_total)[0] if dist is not None else 0
             fused_mc = tabs is not None and dist.comm == "multicast"
             # 1) row-local prep for every meta-path: dV, delta into the row records; bias gradient
+            push = tabs is not None and dist.comm == "push"
+            bounds = tabs.chunk_bounds(n) if push else [(0, n)]
+            if len(bounds) > 1:
+                part_bias = _empty((len(bounds) * NB, D), dev)
             for g, graph in enumerate(plan.graphs):
                 if graph.has_empty_rows():
                     raise _lib.HanError("backward through rows without any edge is not supported "
                                         "(adj_to_bias always inserts self-loops)")
                 # sharded + NVLS: the prep kernel writes the complete record of its rows into every
-                # rank's record table through the multicast address (prep fused with the all-gather)
-                call("han_attn_bwd_prep", ptr(dZ[:, g, :]), G * D, ptr(Z[:, g, :]), G * D, ptr(V[g]),
-                     ptr(R[g]), n, K, H, plan.act, ptr(part_bias),
-                     tabs.R_mc_row(g, 0) if fused_mc else None, lo_row, stream_ptr())
-                call("han_reduce_partials", ptr(part_bias), NB, D, ptr(dbias[g]), stream_ptr())
+                # rank's record table through the multicast address (prep fused with the all-gather);
+                # "push": row chunks, each finished chunk of records is copied to the peers while the next is prepared
+                for ci, (c0, c1) in enumerate(bounds):
+                    call("han_attn_bwd_prep", ptr(dZ[c0:, g, :]), G * D, ptr(Z[c0:, g, :]), G * D, ptr(V[g][c0:]),
+                         ptr(R[g][c0:]), c1 - c0, K, H, plan.act, ptr(part_bias[ci * NB:]),
+                         tabs.R_mc_row(g, 0) if fused_mc else None, lo_row + c0, stream_ptr())
+                    if push:
+                        tabs.push_R(g, lo_row + c0, lo_row + c1)
+                call("han_reduce_partials", ptr(part_bias), len(bounds) * NB, D, ptr(dbias[g]), stream_ptr())
             # sharded: every rank needs the records of ALL destination rows
-            if tabs is not None:
+            if push:
+                R_all = tabs.pushed_R()
+            elif tabs is not None:
                 R_all = tabs.exchange_R(fused_mc)
             else:
                 R_all = dist.gather_records(R) if dist is not None else None   # NCCL, overlaps the passes
