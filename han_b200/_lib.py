@@ -47,9 +47,9 @@ _SIGNATURES = {
     "han_csr_chunk_edges": (c_int64, [I64]),
     "han_csr_num_chunks": (c_int64, [I64]),
     "han_csr_chunk_rows": (c_int, [P, I64, I64, P, P]),
-    "han_attn_fwd_chunked": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, I64, P, FL, I, I64, P]),
+    "han_attn_fwd_chunked": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, I64, I64, P, FL, I, I64, P]),
     "han_attn_bwd_src_chunked": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P, P, P, FL, I, I64, P]),
-    "han_attn_fwd_chunked_split": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, I64, P, FL, I, I64,
+    "han_attn_fwd_chunked_split": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, I64, I64, P, FL, I, I64,
                                            P, P, P, P, I, P]),
     "han_attn_bwd_src_chunked_split": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P, P, P, FL, I, I64,
                                                P, P, P, P, I, P]),
@@ -65,7 +65,7 @@ _SIGNATURES = {
     "han_semantic_fwd": (c_int, [P, I64, I, I, I, P, P, P, I, P, P, P, P, P]),
     "han_semantic_combine": (c_int, [P, I64, I, I, P, P, P, P]),
     "han_semantic_bwd_workspace_bytes": (SZ, [I, I, I]),
-    "han_semantic_bwd": (c_int, [P, P, P, P, I64, I, I, I, P, P, I, P, P, P, P, P, P, SZ, P]),
+    "han_semantic_bwd": (c_int, [P, P, P, P, I64, I, I, I, P, P, I, P, P, P, P, P, P, SZ, P, I64, P]),
     "han_semantic_tc_workspace_bytes": (SZ, []),
     "han_semantic_fwd_tc": (c_int, [P, I64, I, I, I, P, P, P, I, P, P, P, P, P, SZ, I, P]),
     "han_adam_l2_step": (c_int, [P, P, P, P, I64, P, FL, FL, FL, FL, FL, P]),

@@ -76,8 +76,8 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
                         const float* __restrict__ T, float* __restrict__ R, const float* __restrict__ bias,
                         int act, float* __restrict__ out, int64_t out_stride, float* __restrict__ vsave,
                         const float* __restrict__ colmean, const float* __restrict__ ew,
-                        const float* __restrict__ resid, int64_t resid_stride, float* __restrict__ out2,
-                        int64_t out2_stride, DropCoef dc, SplitRows sp) {
+                        const float* __restrict__ resid, int64_t resid_stride, float* const* __restrict__ out2_tab,
+                        int64_t out2_block_rows, int64_t out2_stride, DropCoef dc, SplitRows sp) {
   constexpr int D = K * H;
   constexpr int TS = ((D + K + 3) / 4) * 4;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
@@ -209,8 +209,13 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
         }
         *reinterpret_cast<float4*>(op + 4 * qv) = a;
         // second destination of the same row: a peer GPU's semantic-layer input over NVLink (tile sharding) -- the
-        // all-to-all of Z is this store, fire-and-forget, overlapped with the rest of the gather
-        if (out2) *reinterpret_cast<float4*>(out2 + (int64_t)rr * out2_stride + head * H + 4 * qv) = a;
+        // all-to-all of Z is this store, fire-and-forget, overlapped with the rest of the gather.  Rows
+        // [m * out2_block_rows, (m+1) * out2_block_rows) belong to the rank whose buffer is out2_tab[m].
+        if (out2_tab) {
+          const int64_t m = rr / out2_block_rows;
+          float* o2 = out2_tab[m] + ((int64_t)rr - m * out2_block_rows) * out2_stride + head * H + 4 * qv;
+          *reinterpret_cast<float4*>(o2) = a;
+        }
       }
     }
   };
@@ -515,7 +520,8 @@ __global__ void __launch_bounds__(128)
 attn_fwd_merge_kernel(const int32_t* __restrict__ heavy_rows, const int32_t* __restrict__ heavy_ptr, int n_heavy,
                       const float* __restrict__ part, float* __restrict__ R, const float* __restrict__ bias, int act,
                       float* __restrict__ out, int64_t out_stride, float* __restrict__ vsave,
-                      const float* __restrict__ resid, int64_t resid_stride, float* __restrict__ out2, int64_t out2_stride) {
+                      const float* __restrict__ resid, int64_t resid_stride, float* const* __restrict__ out2_tab,
+                      int64_t out2_block_rows, int64_t out2_stride) {
   constexpr int D = K * H;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
   constexpr int SLOTS = 32 / K;
@@ -565,7 +571,10 @@ attn_fwd_merge_kernel(const int32_t* __restrict__ heavy_rows, const int32_t* __r
       if (resid) z += resid[(int64_t)rr * resid_stride + head * H + h];
       const float o = (act == HAN_ACT_ELU && z <= 0.f) ? expm1f(z) : z;
       op[h] = o;
-      if (out2) out2[(int64_t)rr * out2_stride + head * H + h] = o;
+      if (out2_tab) {
+        const int64_t m = rr / out2_block_rows;
+        out2_tab[m][((int64_t)rr - m * out2_block_rows) * out2_stride + head * H + h] = o;
+      }
     }
   }
 }
@@ -637,19 +646,20 @@ template <int K, int H, bool SPLIT>
 static int launch_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
                               int64_t n_chunks, const float* T, float* R, const float* bias, int act,
                               float* out, int64_t out_stride, float* vsave, const float* colmean,
-                              const float* ew, const float* resid, int64_t resid_stride, float* out2, int64_t out2_stride,
-                              DropCoef dc, SplitRows sp, HeavyRows hv, cudaStream_t st) {
+                              const float* ew, const float* resid, int64_t resid_stride, float* const* out2_tab,
+                              int64_t out2_block_rows, int64_t out2_stride, DropCoef dc, SplitRows sp, HeavyRows hv,
+                              cudaStream_t st) {
   using C = StreamCfg<K, H>;
   HAN_SMEM_ATTR_ONCE((attn_fwd_chunked_kernel<K, H, C::FWD_STAGES, SPLIT>), C::fwd_smem + C::fwd_w_smem);
   unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
   const size_t smem = C::fwd_smem + (ew ? C::fwd_w_smem : 0);
   attn_fwd_chunked_kernel<K, H, C::FWD_STAGES, SPLIT><<<grid, kStreamWarps * 32, smem, st>>>(
-      indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, ew, resid, resid_stride, out2,
-      out2_stride, dc, sp);
+      indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, ew, resid, resid_stride, out2_tab,
+      out2_block_rows, out2_stride, dc, sp);
   if (SPLIT && hv.n > 0)
     attn_fwd_merge_kernel<K, H><<<(unsigned)ceil_div64(hv.n, 4), 128, 0, st>>>(hv.rows, hv.ptr, hv.n, sp.part, R, bias, act,
-                                                                            out, out_stride, vsave, resid, resid_stride, out2,
-                                                                            out2_stride);
+                                                                            out, out_stride, vsave, resid, resid_stride, out2_tab,
+                                                                            out2_block_rows, out2_stride);
   return check_launch("han_attn_fwd_chunked");
 }
 
@@ -708,9 +718,9 @@ int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const in
                          int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                          int K, int H, int act, float* out, int64_t out_stride, float* vsave,
                          const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
-                         float* out2, int64_t out2_stride, const uint32_t* seed_ptr, float coef_keep, int metapath,
-                         int64_t row0, han_stream_t stream) {
-  HAN_REQUIRE(!out2 || (out2_stride >= (int64_t)K * H && out2_stride % 4 == 0 && (uintptr_t)out2 % 16 == 0), "out2");
+                         float* const* out2_tab, int64_t out2_block_rows, int64_t out2_stride, const uint32_t* seed_ptr,
+                         float coef_keep, int metapath, int64_t row0, han_stream_t stream) {
+  HAN_REQUIRE(!out2_tab || (out2_stride >= (int64_t)K * H && out2_stride % 4 == 0 && out2_block_rows > 0), "out2");
   HAN_REQUIRE(!resid || (resid_stride >= (int64_t)K * H && resid_stride % 4 == 0 && (uintptr_t)resid % 16 == 0), "resid");
   HAN_REQUIRE(indptr && chunk_rows && T && R && bias && out && vsave, "null pointer");
   HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
@@ -722,7 +732,7 @@ int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const in
               ((uintptr_t)bias % 16 == 0), "16-byte alignment");
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_fwd_chunked<k, h, false>(indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, edge_w, resid, resid_stride, out2, out2_stride, dc, SplitRows{nullptr, nullptr}, HeavyRows{nullptr, nullptr, 0}, as_stream(stream));
+    return launch_fwd_chunked<k, h, false>(indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, edge_w, resid, resid_stride, out2_tab, out2_block_rows, out2_stride, dc, SplitRows{nullptr, nullptr}, HeavyRows{nullptr, nullptr, 0}, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
@@ -751,14 +761,14 @@ int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, 
                                int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                                int K, int H, int act, float* out, int64_t out_stride, float* vsave,
                                const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
-                               float* out2, int64_t out2_stride, const uint32_t* seed_ptr, float coef_keep, int metapath,
-                               int64_t row0, const int32_t* vmap,
+                               float* const* out2_tab, int64_t out2_block_rows, int64_t out2_stride,
+                               const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0, const int32_t* vmap,
                                float* part, const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
                                han_stream_t stream) {
   HAN_REQUIRE(!resid || (resid_stride >= (int64_t)K * H && resid_stride % 4 == 0 && (uintptr_t)resid % 16 == 0), "resid");
   HAN_REQUIRE(indptr_v && chunk_rows && T && R && bias && out && vsave, "null pointer");
   HAN_REQUIRE(vmap && part && n_heavy >= 0 && (n_heavy == 0 || (heavy_rows && heavy_ptr)), "split view: vmap, part, heavy rows");
-  HAN_REQUIRE(!out2 || (out2_stride >= (int64_t)K * H && out2_stride % 4 == 0 && (uintptr_t)out2 % 16 == 0), "out2");
+  HAN_REQUIRE(!out2_tab || (out2_stride >= (int64_t)K * H && out2_stride % 4 == 0 && out2_block_rows > 0), "out2");
   HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
   const DropCoef dc = make_drop(seed_ptr, coef_keep, metapath, row0);
   HAN_REQUIRE(n_dst > 0 && n_chunks > 0, "sizes");
@@ -770,7 +780,7 @@ int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, 
   const HeavyRows hv{heavy_rows, heavy_ptr, n_heavy};
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_fwd_chunked<k, h, true>(indptr_v, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, edge_w, resid, resid_stride, out2, out2_stride, dc, sp, hv, as_stream(stream));
+    return launch_fwd_chunked<k, h, true>(indptr_v, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, edge_w, resid, resid_stride, out2_tab, out2_block_rows, out2_stride, dc, sp, hv, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");

@@ -306,8 +306,17 @@ __global__ void __launch_bounds__(kSemThreads)
 semantic_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ Z,
                     const float* __restrict__ beta, const float* __restrict__ vsave, int64_t n, int P,
                     const float* __restrict__ w, const float* __restrict__ u, int mode,
-                    const float* __restrict__ dsbar, float* __restrict__ dZ, float* __restrict__ part) {
+                    const float* __restrict__ dsbar, float* __restrict__ dZ, float* __restrict__ part,
+                    float* const* __restrict__ dz_tab, int64_t dz_stride) {
   using C = SemBwdCfg<D, A>;
+  // Destination of the dZ row of (node, meta-path p): dZ[node][p][:] locally, or -- tile-sharded multi-GPU runs --
+  // dz_tab[p] + node * dz_stride: a peer-mapped address inside the GPU that owns meta-path p, so the re-sharding
+  // all-to-all of dZ is this kernel's own stores over NVLink.
+  auto dz_row = [&](int64_t row) -> float* {
+    if (dz_tab == nullptr) return dZ + row * D;
+    const int64_t node = row / P;
+    return dz_tab[row - node * P] + node * dz_stride;
+  };
   constexpr int TM = C::TM, ZLD = C::ZLD, VLD = C::VLD, WLD = C::WLD;
   extern __shared__ __align__(16) float smem[];
   float* wT = smem;                  // [A][WLD]   wT[a][d] = w[d][a]
@@ -449,11 +458,12 @@ semantic_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ Z,
           const int r = wm * 16 + gid + 8 * h;
           if (r < rows_here) {
             const float bt = bts[r];
+            float* zrow = dz_row(row0 + r);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
               const int d = wn * (D / 2) + nt * 8 + 2 * tig;
               const float2 gg = *reinterpret_cast<const float2*>(Gs + r * ZLD + d);
-              *reinterpret_cast<float2*>(dZ + (row0 + r) * D + d) =
+              *reinterpret_cast<float2*>(zrow + d) =
                   make_float2(fmaf(bt, gg.x, acc[nt][2 * h]), fmaf(bt, gg.y, acc[nt][2 * h + 1]));
             }
           }
@@ -514,7 +524,7 @@ semantic_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ Z,
             if (r < rows_here) {
               const float bt = bts[r];
               const float4 g = *reinterpret_cast<const float4*>(Gs + r * ZLD + dg * 4);
-              *reinterpret_cast<float4*>(dZ + (row0 + r) * D + dg * 4) =
+              *reinterpret_cast<float4*>(dz_row(row0 + r) + dg * 4) =
                   make_float4(fmaf(bt, g.x, acc[i][0]), fmaf(bt, g.y, acc[i][1]),
                               fmaf(bt, g.z, acc[i][2]), fmaf(bt, g.w, acc[i][3]));
             }
@@ -625,7 +635,7 @@ template <int D, int A>
 static int launch_sem_bwd(const float* dout, const float* Z, const float* beta, const float* vsave,
                           int64_t n, int P, const float* w, const float* u, int mode,
                           const float* dsbar, float* dZ, float* dw, float* db, float* du, void* ws,
-                          size_t ws_bytes, cudaStream_t st) {
+                          size_t ws_bytes, float* const* dz_tab, int64_t dz_stride, cudaStream_t st) {
   using C = SemBwdCfg<D, A>;
   size_t smem = C::smem_floats * sizeof(float);
   if (ws_bytes < (size_t)kSemBwdBlocks * C::part_floats * sizeof(float))
@@ -633,7 +643,7 @@ static int launch_sem_bwd(const float* dout, const float* Z, const float* beta, 
   HAN_SMEM_ATTR_ONCE((semantic_bwd_kernel<D, A>), smem);
   float* part = reinterpret_cast<float*>(ws);
   semantic_bwd_kernel<D, A><<<kSemBwdBlocks, kSemThreads, smem, st>>>(dout, Z, beta, vsave, n, P, w, u,
-                                                                    mode, dsbar, dZ, part);
+                                                                    mode, dsbar, dZ, part, dz_tab, dz_stride);
   int64_t cols = (int64_t)C::part_floats;
   sem_reduce_kernel<<<(unsigned)ceil_div64(cols, 128), 128, 0, st>>>(part, kSemBwdBlocks, cols, dw,
                                                                    (int64_t)D * A, db, du, A);
@@ -689,13 +699,14 @@ size_t han_semantic_bwd_workspace_bytes(int P, int D, int A) {
 int han_semantic_bwd(const float* dout, const float* Z, const float* beta, const float* vsave,
                      int64_t n, int P, int D, int A, const float* w, const float* u, int mode,
                      const float* dsbar, float* dZ, float* dw, float* db, float* du, void* ws,
-                     size_t ws_bytes, han_stream_t stream) {
-  HAN_REQUIRE(dout && Z && beta && vsave && w && u && dZ && dw && db && du && ws, "null pointer");
+                     size_t ws_bytes, float* const* dz_tab, int64_t dz_stride, han_stream_t stream) {
+  HAN_REQUIRE(dout && Z && beta && vsave && w && u && (dZ || dz_tab) && dw && db && du && ws, "null pointer");
+  HAN_REQUIRE(!dz_tab || (dz_stride >= D && dz_stride % 4 == 0), "dz_stride");
   HAN_REQUIRE(n > 0 && P > 0 && P <= 64, "n > 0, 1 <= P <= 64");
   HAN_REQUIRE(mode == HAN_SEM_REFERENCE || dsbar, "paper mode needs dsbar");
 #define X(d, a)         \
   if (D == d && A == a) \
-    return launch_sem_bwd<d, a>(dout, Z, beta, vsave, n, P, w, u, mode, dsbar, dZ, dw, db, du, ws, ws_bytes, as_stream(stream));
+    return launch_sem_bwd<d, a>(dout, Z, beta, vsave, n, P, w, u, mode, dsbar, dZ, dw, db, du, ws, ws_bytes, dz_tab, dz_stride, as_stream(stream));
   HAN_FOR_SEM(X)
 #undef X
   return fail_arg(__func__, "unsupported (D,A); see han_semantic_shape_supported");

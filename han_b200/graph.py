@@ -264,21 +264,6 @@ class MetaPathGraph:
             self._chunks = (cr, n_chunks)
         return self._chunks
 
-    def chunks_for_rows(self, r0: int, r1: int):
-        """Work items for the row sub-range [r0, r1) only (row numbers relative to r0): lets the edge-stream kernels run
-        on a block of rows with all row-indexed pointers shifted to r0.  Cached per range."""
-        cache = self.__dict__.setdefault("_sub_chunks", {})
-        if (r0, r1) not in cache:
-            self.wait_ready()
-            ends = self.indptr[[r0, r1]].tolist()                       # build-time sync, once per graph and range
-            nnz = int(ends[1] - ends[0])
-            n_chunks = int(query("han_csr_num_chunks", nnz))
-            with torch.cuda.device(self.device):
-                cr = torch.empty(n_chunks + 1, dtype=torch.int32, device=self.device)
-                call("han_csr_chunk_rows", ptr(self.indptr[r0:]), r1 - r0, nnz, ptr(cr), stream_ptr())
-            cache[(r0, r1)] = (cr, n_chunks)
-        return cache[(r0, r1)]
-
     def split_view(self):
         """Virtual-row view for graphs with heavy rows (power-law meta-paths): every row with more than
         ``SPLIT_ROW_EDGES`` edges is cut into segments of at most that many, so that no single warp of the

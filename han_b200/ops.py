@@ -176,34 +176,27 @@ class NodeAttentionFn(torch.autograd.Function):
                     n_all_nodes = dist.n_total if dist is not None else T_src[g].shape[0]
                     colmean = (T_src[g][:, :D].sum(0) / n_all_nodes).contiguous()
                 ew = graph.edge_weight                 # sp_attn_head's stored adjacency values (None: 0/1 adjacency)
+                # tile sharding: every output row is also stored into the semantic input of the rank that owns it,
+                # over NVLink -- the all-to-all of Z rides on the gather kernel's epilogue
+                o2_tab, o2_rows, o2_stride = (None, 0, 0)
+                if plan.z_sink is not None:
+                    o2_tab, o2_rows, o2_stride = plan.z_sink.out2(g)
+                    plan.z_sink.used = True
                 sv = graph.split_view()
                 if sv is not None:
                     # heavy rows are cut into segments; a merge kernel combines their partial softmax states
                     part = _empty((sv.n_slots, K, H + 2), dev)
                     call("han_attn_fwd_chunked_split", ptr(sv.indptr_v), ptr(graph.indices), ptr(sv.chunk_rows),
                          sv.n_chunks, n, ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]),
-                         G * D, ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, None, 0, ptr(plan.seed), 1.0 - plan.coef_drop,
-                         plan.metapath_id(g), row0, ptr(sv.vmap), ptr(part), ptr(sv.heavy_rows), ptr(sv.heavy_ptr),
+                         G * D, ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, o2_tab, o2_rows, o2_stride, ptr(plan.seed),
+                         1.0 - plan.coef_drop, plan.metapath_id(g), row0, ptr(sv.vmap), ptr(part), ptr(sv.heavy_rows), ptr(sv.heavy_ptr),
                          sv.n_heavy, stream_ptr())
-                elif plan.z_sink is not None and colmean is None and ew is None:
-                    # tile sharding: one launch per semantic sub-block of this rank's rows; each also stores its rows
-                    # into the owning rank's semantic input over NVLink, so the all-to-all of Z rides on the gather
-                    sink = plan.z_sink
-                    T_g = ptr(T_src[g])
-                    for (r0, r1, member) in sink.blocks(n):
-                        cr, n_chunks = graph.chunks_for_rows(r0, r1)
-                        o2, o2_stride = sink.out2(member, g)
-                        call("han_attn_fwd_chunked", ptr(graph.indptr[r0:]), ptr(graph.indices), ptr(cr), n_chunks, r1 - r0,
-                             T_g, ptr(R[g][r0:]), ptr(bias[g]), K, H, plan.act, ptr(Z[r0:, g, :]), G * D,
-                             ptr(V[g][r0:]), None, None, ptr(res[r0:]) if res is not None else None, D, o2, o2_stride,
-                             ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), row0 + r0, stream_ptr())
-                    sink.used = True
                 else:
                     cr, n_chunks = graph.chunks()
                     call("han_attn_fwd_chunked", ptr(graph.indptr), ptr(graph.indices), ptr(cr), n_chunks, n,
                          ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D,
-                         ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, None, 0, ptr(plan.seed), 1.0 - plan.coef_drop,
-                         plan.metapath_id(g), row0, stream_ptr())
+                         ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, o2_tab, o2_rows, o2_stride, ptr(plan.seed),
+                         1.0 - plan.coef_drop, plan.metapath_id(g), row0, stream_ptr())
                 if plan.want_coefs:
                     alpha = _empty((graph.nnz, K), dev)
                     if graph.nnz:
@@ -420,12 +413,22 @@ class SemanticAttentionFn(torch.autograd.Function):
                     gp = ctx.dist.all_reduce_sum(gp)
                 bv = beta_vec.double()
                 dsbar = (bv * (gp - (bv * gp).sum()) / ctx.n_total).float().contiguous()
-            dZ = _empty((n, P, D), dev)
+            # tile sharding: the kernel stores every dZ row straight into the GPU that owns its meta-path (peer-mapped
+            # symmetric memory); what flows back through autograd is then only a placeholder (tiles._ZExchange.backward
+            # finds the rows already in place and returns them)
+            route = ctx.dist.dz_route(n, P, D) if (hasattr(ctx.dist, "dz_route") and ctx.needs_input_grad[0]) else None
+            if route is not None:
+                dz_tab, dz_stride = route
+                dZ = torch.zeros((), device=dev).expand(n, P, D)
+            else:
+                dz_tab, dz_stride = None, 0
+                dZ = _empty((n, P, D), dev)
             dw, db, du = _empty((D, A), dev), _empty((A,), dev), _empty((A,), dev)
             ws_bytes = query("han_semantic_bwd_workspace_bytes", P, D, A)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             call("han_semantic_bwd", ptr(dout), ptr(Z), ptr(beta), ptr(vsave), n, P, D, A, ptr(w), ptr(u),
-                 ctx.mode, ptr(dsbar), ptr(dZ), ptr(dw), ptr(db), ptr(du), ptr(ws), ws_bytes, stream_ptr())
+                 ctx.mode, ptr(dsbar), None if route is not None else ptr(dZ), ptr(dw), ptr(db), ptr(du), ptr(ws),
+                 ws_bytes, dz_tab, dz_stride, stream_ptr())
         return dZ, dw, db, du, None, None
 
 

@@ -105,22 +105,17 @@ class ZSink:
         self.tile, self.bufs = tile, bufs
         self.used = False
 
-    def blocks(self, n_rows: int):
-        """-> [(r0, r1, member)] : rows [r0, r1) of this rank's attention block are member's semantic rows."""
-        t = self.tile
-        out = []
-        for m in range(t.Wz):
-            r0, r1 = min(n_rows, m * t.n_sub), min(n_rows, (m + 1) * t.n_sub)
-            if r1 > r0:
-                out.append((r0, r1, m))
-        return out
-
-    def out2(self, member: int, g: int):
-        """(pointer, row stride in floats) of local meta-path g's columns in member's Zrecv."""
-        import ctypes
+    def out2(self, g: int):
+        """(device table of base pointers, rows per block, row stride in floats) for local meta-path g: block m of this
+        rank's attention rows (n_sub rows) is member m's semantic rows, and its rows land in member m's Zrecv at local
+        meta-path g's columns."""
         t, b = self.tile, self.bufs
-        col = (t.member * len(t.paths) + g) * b.D
-        return ctypes.c_void_p(b.peer_Z[member].data_ptr() + col * 4), t.P * b.D
+        cache = b.__dict__.setdefault("_out2_tabs", {})
+        if g not in cache:
+            col = (t.member * len(t.paths) + g) * b.D
+            ptrs = [b.peer_Z[m].data_ptr() + col * 4 for m in range(t.Wz)]
+            cache[g] = torch.tensor(ptrs, dtype=torch.int64, device=t.device)
+        return _lib.ptr(cache[g]), t.n_sub, t.P * b.D
 
 
 class _ZExchange(torch.autograd.Function):
@@ -153,9 +148,13 @@ class _ZExchange(torch.autograd.Function):
         b = tile.zbuffers(D)
         me = tile.member
         _lib.trace_mark("dZ push >")
-        for m in range(tile.Wz):
-            if n_sem:
-                b.peer_dZ[m][me * tile.n_sub:me * tile.n_sub + n_sem].copy_(dOut[:, m * per:(m + 1) * per, :], non_blocking=True)
+        if tile._dz_routed:
+            tile._dz_routed = False           # the semantic backward kernel stored its rows into the owners' dZrecv itself
+        else:
+            for m in range(tile.Wz):
+                if n_sem:
+                    b.peer_dZ[m][me * tile.n_sub:me * tile.n_sub + n_sem].copy_(dOut[:, m * per:(m + 1) * per, :],
+                                                                                non_blocking=True)
         b.barrier_dZ()
         _lib.trace_mark("dZ push <")
         return b.dZrecv[:n_h], None, None
@@ -219,6 +218,7 @@ class TileShard:
         self.attn_rows = self.sem_rows = (0, 0)
         self.n_hpad = self.n_sub = 0
         self._zbufs = {}
+        self._dz_routed = False
         import os
         # Z / dZ re-sharding through symmetric memory (K-B's fused stores + peer copies), or as an all-to-all collective
         self.fused_z = device.type == "cuda" and os.environ.get("HAN_DIST_COMM", "pull") != "nccl"
@@ -289,6 +289,20 @@ class TileShard:
                 peers[m][lo:lo + n_sem].copy_(mine, non_blocking=True)
             h.barrier(channel=0)
         return X[:self.attn_rows[1] - self.attn_rows[0]]
+
+    def dz_route(self, n_sem: int, P: int, D: int):
+        """For the semantic backward kernel: (device table of P base pointers, row stride in floats) so that the gradient
+        row of (semantic row i, meta-path p) lands in the owner of p's dZrecv -- or None when the exchange runs as a
+        collective.  Marks the pending exchange as already routed."""
+        if not self.fused_z or P != self.P or n_sem != self.sem_rows[1] - self.sem_rows[0]:
+            return None
+        b = self.zbuffers(D)
+        if not hasattr(b, "_dz_tab"):
+            per = len(self.paths)
+            ptrs = [b.peer_dZ[p // per].data_ptr() + ((self.member * self.n_sub) * per + p % per) * D * 4 for p in range(P)]
+            b._dz_tab = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        self._dz_routed = True
+        return _lib.ptr(b._dz_tab), len(self.paths) * D
 
     def exchange_Z(self, Z: torch.Tensor, pushed: bool = False) -> torch.Tensor:
         if self.fused_z:

@@ -148,13 +148,12 @@ int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const in
                          int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                          int K, int H, int act, float* out, int64_t out_stride, float* vsave,
                          const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
-                         float* out2, int64_t out2_stride, const uint32_t* seed_ptr, float coef_keep, int metapath,
-                         int64_t row0, han_stream_t stream);
-/* out2 (nullable) [n_dst][out2_stride]: a SECOND destination of every output row -- in tile-sharded multi-GPU runs
- * a peer-mapped address inside another GPU's semantic-layer input (symmetric memory): the re-sharding all-to-all
- * of Z is fused into K-B's epilogue as plain stores over NVLink (models/gat.py:58-60 across GPUs).
- * Row sub-ranges: indptr / R / out / vsave / resid / out2 may point at row r0 of larger arrays (pass row0 + r0) with a
- * chunk table built by han_csr_chunk_rows over the same sub-range; indices and T stay whole. */
+                         float* const* out2_tab, int64_t out2_block_rows, int64_t out2_stride, const uint32_t* seed_ptr,
+                         float coef_keep, int metapath, int64_t row0, han_stream_t stream);
+/* out2_tab (nullable): DEVICE array of base pointers, one per block of out2_block_rows destination rows: row i is also
+ * stored to out2_tab[i / out2_block_rows] + (i % out2_block_rows) * out2_stride.  In tile-sharded multi-GPU runs the
+ * pointers are peer-mapped addresses inside the other GPUs' semantic-layer inputs (symmetric memory): the re-sharding
+ * all-to-all of Z is fused into K-B's epilogue as plain stores over NVLink (models/gat.py:58-60 across GPUs). */
 /* resid (nullable) [n_dst][resid_stride]: the residual term of utils/layers.py:38-40, added before the
  * activation: out_i = act(V_i + bias + resid_i).  Its gradient is dV (R[:, 0:D] after han_attn_bwd_prep). */
 int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
@@ -201,8 +200,8 @@ int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, 
                                int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                                int K, int H, int act, float* out, int64_t out_stride, float* vsave,
                                const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
-                               float* out2, int64_t out2_stride, const uint32_t* seed_ptr, float coef_keep, int metapath,
-                               int64_t row0, const int32_t* vmap,
+                               float* const* out2_tab, int64_t out2_block_rows, int64_t out2_stride,
+                               const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0, const int32_t* vmap,
                                float* part, const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
                                han_stream_t stream);
 int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_indices, const int32_t* perm,
@@ -293,7 +292,10 @@ size_t han_semantic_bwd_workspace_bytes(int P, int D, int A);
 int han_semantic_bwd(const float* dout, const float* Z, const float* beta, const float* vsave,
                      int64_t n, int P, int D, int A, const float* w, const float* u, int mode,
                      const float* dsbar, float* dZ, float* dw, float* db, float* du, void* ws,
-                     size_t ws_bytes, han_stream_t stream);
+                     size_t ws_bytes, float* const* dz_tab, int64_t dz_stride, han_stream_t stream);
+/* dz_tab (nullable): DEVICE array of P base pointers; when given, the gradient row of (node, meta-path p) goes to
+ * dz_tab[p] + node * dz_stride instead of dZ[node][p][:] (dZ may then be NULL).  Tile-sharded multi-GPU runs pass
+ * peer-mapped addresses inside the GPUs that own each meta-path, fusing the all-to-all of dZ into this kernel. */
 
 #ifdef __cplusplus
 }
