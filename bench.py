@@ -521,6 +521,8 @@ def parity_check(args, wl, hp, dist, dev, step, rank, world, rows_per_block=250,
     mask = torch.zeros(s_hi - s_lo, dtype=torch.float32, device=dev)
     mask[(local - s_lo).to(dev)] = 1.0
     keep = {}
+    if dist is not None:
+        dist.bind(wl["graphs"], N)        # the host-fed leg re-bound the exchange structures to its own graph handles
     loss = step(wl["X"].unsqueeze(0), wl["graphs"], mask=mask, with_l2=False, keep=keep).detach().reshape(1).clone()
     D = keep["final_embed"].shape[1]
     buf = torch.zeros(M, D + P, dtype=torch.float32, device=dev)

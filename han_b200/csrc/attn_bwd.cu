@@ -219,13 +219,33 @@ attn_bwd_finish_kernel(const float* __restrict__ T, int64_t n, const float* __re
   }
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int nblocks, int64_t cols,
-                                       float* __restrict__ outv) {
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * cols + c];
-  outv[c] = s;
+// outv[c] = sum_b part[b][c], deterministic: 32 columns x 8 row groups per CTA; row group j sums blocks j, j+8, ...
+// with 4 independent accumulators (the loads pipeline instead of one dependent chain of nblocks L2 round trips), the 8
+// group sums are then added in a fixed order.
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ part, int nblocks, int64_t cols, float* __restrict__ outv) {
+  __shared__ float sm[8][33];
+  const int lc = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lc;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < cols) {
+    int b = j;
+    for (; b + 24 < nblocks; b += 32) {
+      s0 += part[(int64_t)b * cols + c];
+      s1 += part[(int64_t)(b + 8) * cols + c];
+      s2 += part[(int64_t)(b + 16) * cols + c];
+      s3 += part[(int64_t)(b + 24) * cols + c];
+    }
+    for (; b < nblocks; b += 8) s0 += part[(int64_t)b * cols + c];
+  }
+  sm[j][lc] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (j == 0 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sm[k][lc];
+    outv[c] = s;
+  }
 }
 
 }  // namespace han
@@ -311,7 +331,7 @@ int han_attn_bwd_finish(const float* T, int64_t n, int K, int H, const float* a1
 int han_reduce_partials(const float* part, int nblocks, int64_t cols, float* outv, han_stream_t stream) {
   HAN_REQUIRE(part && outv, "null pointer");
   HAN_REQUIRE(nblocks > 0 && cols > 0, "sizes");
-  reduce_partials_kernel<<<(unsigned)ceil_div64(cols, 128), 128, 0, as_stream(stream)>>>(part, nblocks, cols, outv);
+  reduce_partials_kernel<<<(unsigned)ceil_div64(cols, 32), 256, 0, as_stream(stream)>>>(part, nblocks, cols, outv);
   return check_launch(__func__);
 }
 

@@ -180,8 +180,9 @@ project_bwd_tc_kernel(const float* __restrict__ X, int64_t n, int64_t F, int64_t
     const int64_t f = f0 + q * 32 + lane;
     float* dst = part + ((int64_t)blockIdx.y * F + f) * NC;
     const int nchains = (nkb + BT_CHAIN_KB - 1) / BT_CHAIN_KB;
-    if (nchains == 0 && f < F)
-      for (int c = 0; c < NC; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    // The partial was zeroed by the launcher; every chain is ADDED with red.global (fire-and-forget: no load round
+    // trip, so the drain never paces the MMAs).  Each address belongs to one thread of one CTA and same-address
+    // reductions of one thread apply in program order, so the sums are deterministic.
     for (int chain = 0; chain < nchains; ++chain) {
       const int a = chain & 1;
       bt_mbar_wait(accfull0 + 8 * a, (uint32_t)((chain >> 1) & 1));
@@ -193,16 +194,11 @@ project_bwd_tc_kernel(const float* __restrict__ X, int64_t n, int64_t F, int64_t
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (f < F) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float4 o = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
-                                   __uint_as_float(v[4 * c + 3]));
-            float4* dp = reinterpret_cast<float4*>(dst + c0 + 4 * c);
-            if (chain > 0) {
-              const float4 p4 = *dp;
-              o.x += p4.x; o.y += p4.y; o.z += p4.z; o.w += p4.w;
-            }
-            *dp = o;
-          }
+          for (int c = 0; c < 8; ++c)
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + c0 + 4 * c), "f"(__uint_as_float(v[4 * c])),
+                         "f"(__uint_as_float(v[4 * c + 1])), "f"(__uint_as_float(v[4 * c + 2])),
+                         "f"(__uint_as_float(v[4 * c + 3]))
+                         : "memory");
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -307,6 +303,7 @@ int han_project_bwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const 
   HAN_SMEM_ATTR_ONCE(project_bwd_tc_kernel<3>, BT_SMEM_BYTES);
   dim3 grid((unsigned)ceil_div64(F, BT_BM), (unsigned)splits);
   float* part = reinterpret_cast<float*>(ws);
+  cudaMemsetAsync(part, 0, (size_t)splits * F * G * 64 * sizeof(float), st);    // the drains accumulate into it
   if (mode == 1)
     project_bwd_tc_kernel<1><<<grid, BT_THREADS, BT_SMEM_BYTES, st>>>(X, n, F, ldx, dS, G, rows_per_split, part);
   else if (mode == 2)

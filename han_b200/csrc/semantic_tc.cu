@@ -341,6 +341,398 @@ semantic_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
   }
 }
 
+
+// =====================================================================================================================
+// K-F on tcgen05: backward of the semantic layer (TF autodiff of utils/layers.py:152-159), D = 64, A = 128.
+//
+//   g[r] = <dout[n], Z[r]>      ds = beta (g - sum_q beta_q g_q)   (per node; paper mode: ds = dsbar[p])
+//   v = tanh(Z w + b)           RECOMPUTED here (GEMM1) instead of being stored by the forward and read back:
+//                               4.1 GB of writes + 4.1 GB of reads per step on the 2M-node config buy 24 MMAs per tile
+//   dv = ds u (1 - v^2)         du += ds v     db += dv
+//   dZ = beta dout + dv w^T     (GEMM2)        dw += Z^T dv   (GEMM3, accumulated over the CTA's tiles)
+//
+// One persistent CTA per SM walks tiles of 128 (node, meta-path) rows.  All three contractions run as 3xTF32 on
+// tcgen05.mma with TMEM accumulators, from ONE shared-memory copy of every operand:
+//   Z  tile  [128 r][64 d], hi | lo: K-major A of GEMM1 (K = d) and MN-major A of GEMM3 (M = d, K = r)
+//   w^T      [128 a][64 d], hi | lo: K-major B of GEMM1 (N = a, K = d) and MN-major B of GEMM2 (N = d, K = a)
+//   dv panel [128 r][32 a], hi | lo: K-major A of GEMM2 (K = a) and MN-major B of GEMM3 (N = a, K = r)
+// dv goes through shared memory one 32-column panel at a time (the full 128 x 128 hi/lo tile would not fit next to
+// Z and w): the epilogue warps turn accumulator columns [32j, 32j+32) of GEMM1 into a dv panel while the MMAs of
+// panel j-1 run.  GEMM3 is M = 64 (d) x N = 32 (a) x K = 128 (r) per panel; its accumulator (64 TMEM-lane rows in the
+// half-subpartition layout: row m in lane (m % 16) + 32 (m / 16)) is drained every second tile with red.global.add
+// into this CTA's partial, because the tensor core's truncating accumulate drifts with the chain length (see
+// project_bwd_tc.cu).  du / db column sums: warp transpose-reduce (31 shuffles per 32 columns), registers across tiles.
+//   warp 0    TMA: w^T once; the raw Z tile of tile i+1 into a landing buffer while tile i is processed
+//   warp 1    TMEM allocator + single-thread MMA issuer
+//   warps 2-5 split / g / ds, panels, dZ epilogue, dw drain (thread = row)
+constexpr uint32_t SB_PANEL_BYTES = ST_BM * 32 * 4;                 // [128 rows][32 floats] = 16 KB
+constexpr uint32_t SB_W_OFF = 0;                                    // w^T hi (2 panels) | lo (2 panels)      64 KB
+constexpr uint32_t SB_ZH_OFF = SB_W_OFF + 4 * SB_PANEL_BYTES;       // Z hi (2 panels)                        32 KB
+constexpr uint32_t SB_ZL_OFF = SB_ZH_OFF + 2 * SB_PANEL_BYTES;      // Z lo                                   32 KB
+constexpr uint32_t SB_LAND_OFF = SB_ZL_OFF + 2 * SB_PANEL_BYTES;    // raw Z of the next tile                 32 KB
+constexpr uint32_t SB_DVH_OFF = SB_LAND_OFF + 2 * SB_PANEL_BYTES;   // dv panel hi                            16 KB
+constexpr uint32_t SB_DVL_OFF = SB_DVH_OFF + SB_PANEL_BYTES;        // dv panel lo                            16 KB
+constexpr uint32_t SB_PAR_OFF = SB_DVL_OFF + SB_PANEL_BYTES;        // b[128] | u[128] | gs[128] | bts[128] | red[4][2][128]
+constexpr uint32_t SB_PAR_BYTES = 4 * (4 * 128 + 4 * 2 * 128);
+constexpr uint32_t SB_BAR_OFF = SB_PAR_OFF + SB_PAR_BYTES;
+constexpr uint32_t SB_SMEM_BYTES = 1024 + SB_BAR_OFF + 256;
+constexpr int SB_CHAIN_TILES = 2;                                   // dw accumulation chain: 2 tiles = 256 rows
+
+// MN-major, SWIZZLE_128B matrix descriptor: 8 K-rows of 128 B form one swizzle atom (SBO = 1024 B between
+// atoms along K); LBO = byte distance between blocks of 32 elements along M/N (one panel here)
+__device__ __forceinline__ uint64_t st_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// tanh to ~1e-7 absolute (the contract is max-norm relative 1e-5 on O(1) values): 2 MUFU + 3 FMA-class ops
+__device__ __forceinline__ float st_tanh(float x) {
+  const float e = __expf(2.f * x);
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+// lane l ends up with the sum over the 32 lanes of x[l]
+__device__ __forceinline__ float st_col_sums(float (&x)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? x[i] : x[i + off];
+      const float keep = up ? x[i + off] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return x[0];
+}
+
+__global__ void __launch_bounds__(192, 1)
+semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmWhi,
+                       const __grid_constant__ CUtensorMap tmWlo, int64_t n, int P, const float* __restrict__ dout,
+                       const float* __restrict__ beta, const float* __restrict__ b, const float* __restrict__ u,
+                       int mode, const float* __restrict__ dsbar, float* __restrict__ dZ, float* const* __restrict__ dz_tab,
+                       int64_t dz_stride, float* __restrict__ part) {
+  constexpr int D = ST_D, A = ST_A;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (st_smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - st_smem_u32(smem_raw));
+  float* par = reinterpret_cast<float*>(gen + SB_PAR_OFF);
+  float* bs = par;              // b[128]
+  float* us = par + 128;        // u[128]
+  float* gs = par + 256;        // g of the tile's rows
+  float* bts = par + 384;       // beta of the tile's rows
+  float* red = par + 512;       // [4 warps][du 128 | db 128]
+  const uint32_t bars = base + SB_BAR_OFF;
+  const uint32_t w_full = bars, land_full = bars + 8, land_free = bars + 16, z_ready = bars + 24, acc1_full = bars + 32,
+                 acc1_free = bars + 40, dvp_full = bars + 48, dvp_free = bars + 56, dz_full = bars + 64, dz_free = bars + 72,
+                 g3_done = bars + 80, dw_full = bars + 88, dw_free = bars + 96;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + SB_BAR_OFF + 128);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nodes_per_tile = ST_BM / P;
+  const int rows_per_tile = nodes_per_tile * P;
+  const int64_t total_rows = n * P;
+  const int64_t n_tiles = ceil_div64(n, nodes_per_tile);
+  const int64_t my_tiles = (n_tiles > (int64_t)blockIdx.x) ? ceil_div64(n_tiles - blockIdx.x, gridDim.x) : 0;
+
+  for (int i = threadIdx.x; i < A; i += 192) {
+    bs[i] = b[i];
+    us[i] = u[i];
+  }
+  if (threadIdx.x == 0) {
+    st_mbar_init(w_full, 1);
+    st_mbar_init(land_full, 1);
+    st_mbar_init(land_free, 128);
+    st_mbar_init(z_ready, 128);
+    st_mbar_init(acc1_full, 1);
+    st_mbar_init(acc1_free, 128);
+    st_mbar_init(dvp_full, 128);
+    st_mbar_init(dvp_free, 1);
+    st_mbar_init(dz_full, 1);
+    st_mbar_init(dz_free, 128);
+    st_mbar_init(g3_done, 1);
+    st_mbar_init(dw_full, 1);
+    st_mbar_init(dw_free, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(st_smem_u32(tmem_slot)),
+                 "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_acc1 = tmem_base, t_dz = tmem_base + 128, t_dw = tmem_base + 192;   // columns
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0 && my_tiles > 0) {
+      st_mbar_expect_tx(w_full, 4 * SB_PANEL_BYTES);
+      for (int kb = 0; kb < 2; ++kb) {
+        st_tma_load_2d(base + SB_W_OFF + kb * SB_PANEL_BYTES, &tmWhi, kb * ST_BK, 0, w_full);
+        st_tma_load_2d(base + SB_W_OFF + (2 + kb) * SB_PANEL_BYTES, &tmWlo, kb * ST_BK, 0, w_full);
+      }
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        if (it > 0) st_mbar_wait(land_free, (uint32_t)((it - 1) & 1));
+        const int64_t tile = blockIdx.x + it * gridDim.x;
+        const int row0 = (int)(tile * rows_per_tile);
+        st_mbar_expect_tx(land_full, 2 * SB_PANEL_BYTES);
+        st_tma_load_2d(base + SB_LAND_OFF, &tmZ, 0, row0, land_full);
+        st_tma_load_2d(base + SB_LAND_OFF + SB_PANEL_BYTES, &tmZ, ST_BK, row0, land_full);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0 && my_tiles > 0) {
+      constexpr uint32_t kTf32 = (1u << 4) | (2u << 7) | (2u << 10);
+      const uint32_t id1 = kTf32 | ((uint32_t)(A >> 3) << 17) | ((uint32_t)(ST_BM >> 4) << 24);               // 128 x 128, K | K
+      const uint32_t id2 = kTf32 | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(ST_BM >> 4) << 24);   // 128 x 64,  K | MN
+      const uint32_t id3 = kTf32 | (1u << 15) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);  // 64 x 32, MN | MN
+      const uint32_t wT = base + SB_W_OFF, zh = base + SB_ZH_OFF, zl = base + SB_ZL_OFF;
+      const uint32_t dvh = base + SB_DVH_OFF, dvl = base + SB_DVL_OFF;
+      st_mbar_wait(w_full, 0);
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const bool last = it + 1 == my_tiles;
+        // ---- GEMM1: acc1 = Z w  (recompute of the pre-activation) ----
+        st_mbar_wait(z_ready, (uint32_t)(it & 1));
+        if (it > 0) st_mbar_wait(acc1_free, (uint32_t)((it - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t a_hi = st_desc(zh + kb * SB_PANEL_BYTES), a_lo = st_desc(zl + kb * SB_PANEL_BYTES);
+          const uint64_t b_hi = st_desc(wT + kb * SB_PANEL_BYTES), b_lo = st_desc(wT + (2 + kb) * SB_PANEL_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            st_umma_tf32(t_acc1, a_lo + adv, b_hi + adv, id1, (kb | k) != 0);
+            st_umma_tf32(t_acc1, a_hi + adv, b_lo + adv, id1, 1u);
+            st_umma_tf32(t_acc1, a_hi + adv, b_hi + adv, id1, 1u);
+          }
+        }
+        st_umma_commit(acc1_full);
+        // ---- per dv panel: GEMM2 (dZ += dv w^T) and GEMM3 (dw += Z^T dv) ----
+        for (int j = 0; j < 4; ++j) {
+          const int64_t pc = it * 4 + j;
+          st_mbar_wait(dvp_full, (uint32_t)(pc & 1));
+          if (j == 0 && it > 0) st_mbar_wait(dz_free, (uint32_t)((it - 1) & 1));
+          if (j == 0 && (it % SB_CHAIN_TILES) == 0 && it >= SB_CHAIN_TILES)
+            st_mbar_wait(dw_free, (uint32_t)(((it / SB_CHAIN_TILES) - 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          // GEMM2: A = dv panel (K-major, K = 32 a), B = w^T rows a in [32j, 32j+32) read MN-major (N = d)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            const uint64_t a_hi = st_desc(dvh) + adv, a_lo = st_desc(dvl) + adv;
+            const uint32_t wrow = (uint32_t)((32 * j + 8 * k) * 128);
+            const uint64_t b_hi = st_desc_mn(wT + wrow, SB_PANEL_BYTES), b_lo = st_desc_mn(wT + 2 * SB_PANEL_BYTES + wrow, SB_PANEL_BYTES);
+            st_umma_tf32(t_dz, a_lo, b_hi, id2, (j | k) != 0);
+            st_umma_tf32(t_dz, a_hi, b_lo, id2, 1u);
+            st_umma_tf32(t_dz, a_hi, b_hi, id2, 1u);
+          }
+          // GEMM3: A = Z^T (MN-major: M = d = 2 blocks of 32, K = 8 rows per step), B = dv panel (MN-major, N = 32 a)
+          const uint32_t first = ((it % SB_CHAIN_TILES) == 0) ? 0u : 1u;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const uint32_t koff = (uint32_t)(k * 1024);
+            const uint64_t a_hi = st_desc_mn(zh + koff, SB_PANEL_BYTES), a_lo = st_desc_mn(zl + koff, SB_PANEL_BYTES);
+            const uint64_t b_hi = st_desc_mn(dvh + koff, SB_PANEL_BYTES), b_lo = st_desc_mn(dvl + koff, SB_PANEL_BYTES);
+            const uint32_t acc = t_dw + (uint32_t)(32 * j);
+            st_umma_tf32(acc, a_lo, b_hi, id3, (k != 0) ? 1u : first);
+            st_umma_tf32(acc, a_hi, b_lo, id3, 1u);
+            st_umma_tf32(acc, a_hi, b_hi, id3, 1u);
+          }
+          st_umma_commit(dvp_free);
+        }
+        st_umma_commit(dz_full);
+        st_umma_commit(g3_done);
+        if ((it % SB_CHAIN_TILES) == SB_CHAIN_TILES - 1 || last) st_umma_commit(dw_full);
+      }
+    }
+  } else {
+    // ===== warps 2-5: thread = row of the tile =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float du_acc[4] = {0.f, 0.f, 0.f, 0.f}, db_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float* my_part = part + (size_t)blockIdx.x * ((size_t)D * A + 2 * A);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const bool last = it + 1 == my_tiles;
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t node0 = tile * nodes_per_tile;
+      const int64_t row0 = node0 * P;
+      const int rows_here = (int)min((int64_t)rows_per_tile, total_rows - row0);
+      const bool live = r < rows_here;
+      const int64_t node = node0 + r / P;
+      const float* drow = dout + node * D;
+      // ---- split the landed raw tile into hi / lo, g = <dout, Z> on the way ----
+      st_mbar_wait(land_full, (uint32_t)(it & 1));
+      if (it > 0) st_mbar_wait(g3_done, (uint32_t)((it - 1) & 1));        // GEMM3 of the previous tile has read Z hi / lo
+      float g = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t off = kb * SB_PANEL_BYTES + st_sw128(r, 4 * c);
+          const uint4 x = *reinterpret_cast<const uint4*>(gen + SB_LAND_OFF + off);
+          uint4 h, l;
+          h.x = x.x & 0xFFFFE000u; l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
+          h.y = x.y & 0xFFFFE000u; l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
+          h.z = x.z & 0xFFFFE000u; l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
+          h.w = x.w & 0xFFFFE000u; l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
+          *reinterpret_cast<uint4*>(gen + SB_ZH_OFF + off) = h;
+          *reinterpret_cast<uint4*>(gen + SB_ZL_OFF + off) = l;
+          if (live) {
+            const float4 dd = ldg4(drow + kb * 32 + 4 * c);
+            g = fmaf(__uint_as_float(x.x), dd.x, g);
+            g = fmaf(__uint_as_float(x.y), dd.y, g);
+            g = fmaf(__uint_as_float(x.z), dd.z, g);
+            g = fmaf(__uint_as_float(x.w), dd.w, g);
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      st_mbar_arrive(z_ready);
+      st_mbar_arrive(land_free);
+      const float bt = live ? beta[row0 + r] : 0.f;
+      gs[r] = g;
+      bts[r] = bt;
+      st_bar_epi<128>();
+      float ds = 0.f;
+      if (live) {
+        if (mode == HAN_SEM_REFERENCE) {
+          const int nl = r / P;
+          float dot = 0.f;
+          for (int pp = 0; pp < P; ++pp) dot = fmaf(bts[nl * P + pp], gs[nl * P + pp], dot);
+          ds = bt * (g - dot);
+        } else {
+          ds = dsbar[r % P];
+        }
+      }
+      st_bar_epi<128>();          // gs / bts are rewritten by the next tile
+      // ---- panels: v = tanh(acc1 + b), dv = ds u (1 - v^2) -> shared memory; du, db column sums ----
+      st_mbar_wait(acc1_full, (uint32_t)(it & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        uint32_t acc[32];
+        st_tmem_ld32(lane_base + (uint32_t)(32 * j), acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (j == 3) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          st_mbar_arrive(acc1_free);
+        }
+        float y[32], dv[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float v = st_tanh(__uint_as_float(acc[c]) + bs[32 * j + c]);
+          y[c] = ds * v;
+          dv[c] = ds * us[32 * j + c] * (1.f - v * v);
+        }
+        const int64_t pc = it * 4 + j;
+        if (pc > 0) st_mbar_wait(dvp_free, (uint32_t)((pc - 1) & 1));     // the MMAs of the previous panel have read it
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t off = st_sw128(r, 4 * c);
+          uint4 h, l;
+          h.x = __float_as_uint(dv[4 * c]) & 0xFFFFE000u;     l.x = __float_as_uint(dv[4 * c] - __uint_as_float(h.x));
+          h.y = __float_as_uint(dv[4 * c + 1]) & 0xFFFFE000u; l.y = __float_as_uint(dv[4 * c + 1] - __uint_as_float(h.y));
+          h.z = __float_as_uint(dv[4 * c + 2]) & 0xFFFFE000u; l.z = __float_as_uint(dv[4 * c + 2] - __uint_as_float(h.z));
+          h.w = __float_as_uint(dv[4 * c + 3]) & 0xFFFFE000u; l.w = __float_as_uint(dv[4 * c + 3] - __uint_as_float(h.w));
+          *reinterpret_cast<uint4*>(gen + SB_DVH_OFF + off) = h;
+          *reinterpret_cast<uint4*>(gen + SB_DVL_OFF + off) = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        st_mbar_arrive(dvp_full);
+        du_acc[j] += st_col_sums(y, lane);
+        db_acc[j] += st_col_sums(dv, lane);
+      }
+      // ---- dZ = beta dout + dv w^T ----
+      st_mbar_wait(dz_full, (uint32_t)(it & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float* zrow = nullptr;
+      if (live) zrow = (dz_tab != nullptr) ? dz_tab[r % P] + node * dz_stride : dZ + (row0 + r) * D;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t acc[32];
+        st_tmem_ld32(lane_base + 128u + (uint32_t)(32 * hh), acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (live) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 dd = ldg4(drow + 32 * hh + 4 * c);
+            *reinterpret_cast<float4*>(zrow + 32 * hh + 4 * c) =
+                make_float4(fmaf(bt, dd.x, __uint_as_float(acc[4 * c])), fmaf(bt, dd.y, __uint_as_float(acc[4 * c + 1])),
+                            fmaf(bt, dd.z, __uint_as_float(acc[4 * c + 2])), fmaf(bt, dd.w, __uint_as_float(acc[4 * c + 3])));
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      st_mbar_arrive(dz_free);
+      // ---- every second tile: drain the dw accumulator (rows d = 16 q + lane for lane < 16) ----
+      if ((it % SB_CHAIN_TILES) == SB_CHAIN_TILES - 1 || last) {
+        st_mbar_wait(dw_full, (uint32_t)((it / SB_CHAIN_TILES) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          uint32_t acc[32];
+          st_tmem_ld32(lane_base + 192u + (uint32_t)(32 * j), acc);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (lane < 16) {
+            float* dst = my_part + (size_t)(16 * q + lane) * A + 32 * j;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4 * c), "f"(__uint_as_float(acc[4 * c])),
+                           "f"(__uint_as_float(acc[4 * c + 1])), "f"(__uint_as_float(acc[4 * c + 2])),
+                           "f"(__uint_as_float(acc[4 * c + 3]))
+                           : "memory");
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        st_mbar_arrive(dw_free);
+      }
+    }
+    // ---- du / db: the four warps' column sums in a fixed order ----
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[q * 256 + 32 * j + lane] = du_acc[j];
+      red[q * 256 + 128 + 32 * j + lane] = db_acc[j];
+    }
+    st_bar_epi<128>();
+    {
+      const int t = threadIdx.x - 64;     // 0..127 = column a
+      const float du = red[0 * 256 + t] + red[1 * 256 + t] + red[2 * 256 + t] + red[3 * 256 + t];
+      const float db = red[0 * 256 + 128 + t] + red[1 * 256 + 128 + t] + red[2 * 256 + 128 + t] + red[3 * 256 + 128 + t];
+      my_part[(size_t)D * A + t] = db;
+      my_part[(size_t)D * A + A + t] = du;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// per-CTA partials [dw (D*A) | db (A) | du (A)] -> dw, db, du
+__global__ void st_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, float* __restrict__ dw,
+                                     float* __restrict__ db, float* __restrict__ du) {
+  const int64_t cols = (int64_t)ST_D * ST_A + 2 * ST_A;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int k = 0; k < nblocks; ++k) s += part[(int64_t)k * cols + c];
+  if (c < (int64_t)ST_D * ST_A) dw[c] = s;
+  else if (c < (int64_t)ST_D * ST_A + ST_A) db[c - (int64_t)ST_D * ST_A] = s;
+  else du[c - (int64_t)ST_D * ST_A - ST_A] = s;
+}
+
 typedef CUresult (*StEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -415,6 +807,45 @@ int han_semantic_fwd_tc(const float* Z, int64_t n, int P, int D, int A, const fl
   else
     semantic_fwd_tc_kernel<4><<<grid, 64 + 512, ST_SMEM_BYTES, st>>>(tmZ, tmWhi, tmWlo, n, P, b, u, mode, out, beta,
                                                                    vsave, scores);
+  return check_launch(__func__);
+}
+
+size_t han_semantic_bwd_tc_workspace_bytes(void) {
+  return (size_t)2 * ST_A * ST_D * sizeof(float) + (size_t)kNumSMs * ((size_t)ST_D * ST_A + 2 * ST_A) * sizeof(float);
+}
+
+int han_semantic_bwd_tc(const float* dout, const float* Z, const float* beta, int64_t n, int P, int D, int A,
+                        const float* w, const float* b, const float* u, int mode, const float* dsbar, float* dZ,
+                        float* dw, float* db, float* du, void* ws, size_t ws_bytes, float* const* dz_tab,
+                        int64_t dz_stride, han_stream_t stream) {
+  HAN_REQUIRE(dout && Z && beta && w && b && u && (dZ || dz_tab) && dw && db && du && ws, "null pointer");
+  HAN_REQUIRE(D == ST_D && A == ST_A, "the tensor-core semantic backward is built for D = 64, A = 128");
+  HAN_REQUIRE(n > 0 && P > 0 && P <= 64 && n * P < ((int64_t)1 << 31), "n > 0, 1 <= P <= 64, n*P < 2^31");
+  HAN_REQUIRE(mode == HAN_SEM_REFERENCE || dsbar, "paper mode needs dsbar");
+  HAN_REQUIRE(!dz_tab || (dz_stride >= D && dz_stride % 4 == 0), "dz_stride");
+  HAN_REQUIRE(ws_bytes >= han_semantic_bwd_tc_workspace_bytes(), "workspace too small");
+  HAN_REQUIRE(((uintptr_t)Z % 16 == 0) && ((uintptr_t)ws % 16 == 0) && ((uintptr_t)dout % 16 == 0) &&
+              ((uintptr_t)dZ % 16 == 0), "16-byte alignment");
+  cudaStream_t st = as_stream(stream);
+  float* wt_hi = reinterpret_cast<float*>(ws);
+  float* wt_lo = wt_hi + ST_A * ST_D;
+  float* part = wt_lo + ST_A * ST_D;
+  st_wt_split_kernel<<<(ST_A * ST_D + 255) / 256, 256, 0, st>>>(w, wt_hi, wt_lo);
+  CUtensorMap tmZ, tmWhi, tmWlo;
+  int rc = st_make_map(&tmZ, Z, ST_D, (uint64_t)(n * P), ST_D, ST_BM);
+  if (rc) return rc;
+  rc = st_make_map(&tmWhi, wt_hi, ST_D, ST_A, ST_D, ST_A);
+  if (rc) return rc;
+  rc = st_make_map(&tmWlo, wt_lo, ST_D, ST_A, ST_D, ST_A);
+  if (rc) return rc;
+  HAN_SMEM_ATTR_ONCE(semantic_bwd_tc_kernel, SB_SMEM_BYTES);
+  const int64_t n_tiles = ceil_div64(n, ST_BM / P);
+  const unsigned grid = (unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+  cudaMemsetAsync(part, 0, (size_t)grid * ((size_t)ST_D * ST_A + 2 * ST_A) * sizeof(float), st);   // the dw drains accumulate
+  semantic_bwd_tc_kernel<<<grid, 192, SB_SMEM_BYTES, st>>>(tmZ, tmWhi, tmWlo, n, P, dout, beta, b, u, mode, dsbar, dZ, dz_tab,
+                                                         dz_stride, part);
+  const int64_t cols = (int64_t)ST_D * ST_A + 2 * ST_A;
+  st_bwd_reduce_kernel<<<(unsigned)ceil_div64(cols, 128), 128, 0, st>>>(part, (int)grid, dw, db, du);
   return check_launch(__func__);
 }
 

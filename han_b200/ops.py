@@ -25,6 +25,7 @@ DETERMINISTIC = _os.environ.get("HAN_DF1_RED", "0") != "1"
 # Semantic layer on tcgen05 (semantic_tc.cu), D = 64, A = 128: on by default; HAN_SEM_TC=0 selects the
 # mma.sync kernels of semantic.cu (any instantiated (D, A)).
 SEM_TC = _os.environ.get("HAN_SEM_TC", "1") != "0"
+SEM_TC_EG = int(_os.environ.get("HAN_SEM_TC_EG", "1"))     # epilogue warp groups of the tcgen05 semantic forward
 
 
 def _empty(shape, device, dtype=torch.float32):
@@ -367,13 +368,15 @@ class SemanticAttentionFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             out = _empty((n, D), dev)
             beta = _empty((n, P), dev)
-            vsave = _empty((n * P, A), dev)
+            tc = SEM_TC and (D, A) == (64, 128) and P <= 64
+            # the tcgen05 backward recomputes tanh(Z w + b) from Z: nothing to store (saves 2 x 4 B x n P A of HBM traffic)
+            vsave = None if tc else _empty((n * P, A), dev)
             def fwd(out_, beta_, scores_):
-                if SEM_TC and (D, A) == (64, 128) and P <= 64:
+                if tc:
                     ws_bytes = query("han_semantic_tc_workspace_bytes")
                     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                     call("han_semantic_fwd_tc", ptr(Z), n, P, D, A, ptr(w), ptr(b), ptr(u), mode, ptr(out_), ptr(beta_),
-                         ptr(vsave), ptr(scores_), ptr(ws), ws_bytes, int(SEM_TC), stream_ptr())
+                         None, ptr(scores_), ptr(ws), ws_bytes, SEM_TC_EG, stream_ptr())
                 else:
                     call("han_semantic_fwd", ptr(Z), n, P, D, A, ptr(w), ptr(b), ptr(u), mode, ptr(out_), ptr(beta_),
                          ptr(vsave), ptr(scores_), stream_ptr())
@@ -391,8 +394,8 @@ class SemanticAttentionFn(torch.autograd.Function):
                 call("han_semantic_combine", ptr(Z), n, P, D, ptr(beta_vec), ptr(out), ptr(beta),
                      stream_ptr())
                 ctx.n_total = n_total
-        ctx.mode, ctx.dist = mode, dist
-        ctx.save_for_backward(Z, w, u, beta, vsave, beta_vec if beta_vec is not None else beta)
+        ctx.mode, ctx.dist, ctx.tc = mode, dist, tc
+        ctx.save_for_backward(Z, w, u, beta, vsave if vsave is not None else b, beta_vec if beta_vec is not None else beta)
         ctx.mark_non_differentiable(beta)
         return out, beta
 
@@ -424,11 +427,18 @@ class SemanticAttentionFn(torch.autograd.Function):
                 dz_tab, dz_stride = None, 0
                 dZ = _empty((n, P, D), dev)
             dw, db, du = _empty((D, A), dev), _empty((A,), dev), _empty((A,), dev)
-            ws_bytes = query("han_semantic_bwd_workspace_bytes", P, D, A)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            call("han_semantic_bwd", ptr(dout), ptr(Z), ptr(beta), ptr(vsave), n, P, D, A, ptr(w), ptr(u),
-                 ctx.mode, ptr(dsbar), None if route is not None else ptr(dZ), ptr(dw), ptr(db), ptr(du), ptr(ws),
-                 ws_bytes, dz_tab, dz_stride, stream_ptr())
+            if ctx.tc:
+                ws_bytes = query("han_semantic_bwd_tc_workspace_bytes")
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                call("han_semantic_bwd_tc", ptr(dout), ptr(Z), ptr(beta), n, P, D, A, ptr(w), ptr(vsave), ptr(u),
+                     ctx.mode, ptr(dsbar), None if route is not None else ptr(dZ), ptr(dw), ptr(db), ptr(du), ptr(ws),
+                     ws_bytes, dz_tab, dz_stride, stream_ptr())     # (the saved slot holds b here)
+            else:
+                ws_bytes = query("han_semantic_bwd_workspace_bytes", P, D, A)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                call("han_semantic_bwd", ptr(dout), ptr(Z), ptr(beta), ptr(vsave), n, P, D, A, ptr(w), ptr(u),
+                     ctx.mode, ptr(dsbar), None if route is not None else ptr(dZ), ptr(dw), ptr(db), ptr(du), ptr(ws),
+                     ws_bytes, dz_tab, dz_stride, stream_ptr())
         return dZ, dw, db, du, None, None
 
 

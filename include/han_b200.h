@@ -271,17 +271,24 @@ int han_semantic_shape_supported(int D, int A);
 int han_semantic_fwd(const float* Z, int64_t n, int P, int D, int A, const float* w, const float* b,
                      const float* u, int mode, float* out, float* beta, float* vsave, float* scores,
                      han_stream_t stream);
-/* EXPERIMENTAL (opt-in, HAN_SEM_TC=1; parity-green on B200, 2.60 ms vs 2.78 ms for the default kernel on the 2M
- * config -- epilogue-bound, hence not the default): the same forward for D = 64, A = 128 on
+/* Default for D = 64, A = 128 (HAN_SEM_TC=0 selects han_semantic_fwd): the same forward on
  * tcgen05 tensor cores -- persistent CTAs, w^T resident in shared memory, TMA ring for Z, 3xTF32 accumulation in
  * double-buffered TMEM, epilogue of tile i under the MMAs of tile i+1 (han_b200/csrc/semantic_tc.cu).
- * ws: han_semantic_tc_workspace_bytes() bytes (the transposed hi/lo split of w).  epilogue_groups: 1 (the
- * validated configuration: 4 epilogue warps) or 2 / 4 (8 / 16 epilogue warps sharing each row's columns; written
- * after the GPU budget of round 1 ran out, to be validated). */
+ * ws: han_semantic_tc_workspace_bytes() bytes (the transposed hi/lo split of w).  epilogue_groups: 1, 2 or 4
+ * (4 / 8 / 16 epilogue warps; groups share each row's columns). */
 size_t han_semantic_tc_workspace_bytes(void);
 int han_semantic_fwd_tc(const float* Z, int64_t n, int P, int D, int A, const float* w, const float* b,
                         const float* u, int mode, float* out, float* beta, float* vsave, float* scores, void* ws,
                         size_t ws_bytes, int epilogue_groups, han_stream_t stream);
+/* K-F on tcgen05 tensor cores (D = 64, A = 128; han_b200/csrc/semantic_tc.cu): v = tanh(Z w + b) is RECOMPUTED from Z
+ * (no vsave: the forward need not store it), dv w^T and Z^T dv run as 3xTF32 tcgen05.mma from one shared-memory copy
+ * of each operand (MN-major descriptors for the transposed uses), dw accumulates in TMEM with a drain every 256 rows.
+ * Same outputs and dz_tab routing as han_semantic_bwd.  ws: han_semantic_bwd_tc_workspace_bytes(). */
+size_t han_semantic_bwd_tc_workspace_bytes(void);
+int han_semantic_bwd_tc(const float* dout, const float* Z, const float* beta, int64_t n, int P, int D, int A,
+                        const float* w, const float* b, const float* u, int mode, const float* dsbar, float* dZ,
+                        float* dw, float* db, float* du, void* ws, size_t ws_bytes, float* const* dz_tab,
+                        int64_t dz_stride, han_stream_t stream);
 /* out[n] = sum_p beta_vec[p] Z[n,p]; beta (nullable) [n][P] receives the broadcast (han.pdf Eq. 9). */
 int han_semantic_combine(const float* Z, int64_t n, int P, int D, const float* beta_vec, float* out,
                          float* beta, han_stream_t stream);
