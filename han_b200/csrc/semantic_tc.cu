@@ -351,43 +351,84 @@ semantic_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
 //   dv = ds u (1 - v^2)         du += ds v     db += dv
 //   dZ = beta dout + dv w^T     (GEMM2)        dw += Z^T dv   (GEMM3, accumulated over the CTA's tiles)
 //
-// One persistent CTA per SM walks tiles of 128 (node, meta-path) rows.  All three contractions run as 3xTF32 on
-// tcgen05.mma with TMEM accumulators, from ONE shared-memory copy of every operand:
-//   Z  tile  [128 r][64 d], hi | lo: K-major A of GEMM1 (K = d) and MN-major A of GEMM3 (M = d, K = r)
-//   w^T      [128 a][64 d], hi | lo: K-major B of GEMM1 (N = a, K = d) and MN-major B of GEMM2 (N = d, K = a)
-//   dv panel [128 r][32 a], hi | lo: K-major A of GEMM2 (K = a) and MN-major B of GEMM3 (N = a, K = r)
-// dv goes through shared memory one 32-column panel at a time (the full 128 x 128 hi/lo tile would not fit next to
-// Z and w): the epilogue warps turn accumulator columns [32j, 32j+32) of GEMM1 into a dv panel while the MMAs of
-// panel j-1 run.  GEMM3 is M = 64 (d) x N = 32 (a) x K = 128 (r) per panel; its accumulator (64 TMEM-lane rows in the
-// half-subpartition layout: row m in lane (m % 16) + 32 (m / 16)) is drained every second tile with red.global.add
-// into this CTA's partial, because the tensor core's truncating accumulate drifts with the chain length (see
-// project_bwd_tc.cu).  du / db column sums: warp transpose-reduce (31 shuffles per 32 columns), registers across tiles.
-//   warp 0    TMA: w^T once; the raw Z tile of tile i+1 into a landing buffer while tile i is processed
+// FP32-grade products as BF16x3: every fp32 operand is cut into three bf16 pieces x = x1 + x2 + x3 (8 + 8 + 8 mantissa
+// bits, exact), and a b = a1b1 + a1b2 + a2b1 + a1b3 + a2b2 + a3b1 + O(2^-24) accumulates in fp32 in TMEM (six
+// kind::f16 MMAs of K = 16 per 16 reduction elements: the same instruction count as 3xTF32 with K = 8).  Why bf16 and
+// not tf32 here: each operand is needed in TWO orientations -- Z as the K-major A of GEMM1 (K = d) and the MN-major A
+// of GEMM3 (M = d, K = r); w^T as the K-major B of GEMM1 and the MN-major B of GEMM2; dv as the K-major A of GEMM2
+// and the MN-major B of GEMM3 -- and for 16-bit types ONE 128-byte-swizzled shared-memory tile serves both (a
+// [rows][64] tile read K-major has rows = M/N, read MN-major has rows = K), whereas MN-major tf32 operands need a
+// different swizzle (128B with 32-byte atoms), i.e. a second copy of everything, which does not fit.
+// Shared memory: w^T 3 x 16 KB, Z 3 x 16 KB, one dv panel (64 columns of a) 3 x 16 KB, raw-Z landing 32 KB.
+//
+// One persistent CTA per SM walks tiles of 128 (node, meta-path) rows:
+//   warp 0    TMA: w^T pieces once; the raw fp32 Z tile of tile i+1 into the landing buffer while tile i is processed
 //   warp 1    TMEM allocator + single-thread MMA issuer
-//   warps 2-5 split / g / ds, panels, dZ epilogue, dw drain (thread = row)
-constexpr uint32_t SB_PANEL_BYTES = ST_BM * 32 * 4;                 // [128 rows][32 floats] = 16 KB
-constexpr uint32_t SB_W_OFF = 0;                                    // w^T hi (2 panels) | lo (2 panels)      64 KB
-constexpr uint32_t SB_ZH_OFF = SB_W_OFF + 4 * SB_PANEL_BYTES;       // Z hi (2 panels)                        32 KB
-constexpr uint32_t SB_ZL_OFF = SB_ZH_OFF + 2 * SB_PANEL_BYTES;      // Z lo                                   32 KB
-constexpr uint32_t SB_LAND_OFF = SB_ZL_OFF + 2 * SB_PANEL_BYTES;    // raw Z of the next tile                 32 KB
-constexpr uint32_t SB_DVH_OFF = SB_LAND_OFF + 2 * SB_PANEL_BYTES;   // dv panel hi                            16 KB
-constexpr uint32_t SB_DVL_OFF = SB_DVH_OFF + SB_PANEL_BYTES;        // dv panel lo                            16 KB
-constexpr uint32_t SB_PAR_OFF = SB_DVL_OFF + SB_PANEL_BYTES;        // b[128] | u[128] | gs[128] | bts[128] | red[4][2][128]
+//   warps 2-5 (thread = row): cut Z into bf16 pieces, g, ds; per panel: v, dv -> shared memory, du / db column sums
+//             (warp transpose-reduce, registers across tiles); dZ epilogue; dw drain
+// GEMM3 is M = 64 (d) x N = 64 (a panel) x K = 128 (r); its accumulator (TMEM half-subpartition layout: row m in lane
+// (m % 16) + 32 (m / 16)) is drained every second tile with red.global.add into this CTA's partial, because the tensor
+// core's truncating accumulate drifts with the chain length (see project_bwd_tc.cu).
+constexpr uint32_t SB_T16 = ST_BM * 64 * 2;                         // [128 rows][64 bf16] = 16 KB: one piece of a tile
+constexpr uint32_t SB_W_OFF = 0;                                    // w^T pieces 1..3                        48 KB
+constexpr uint32_t SB_Z_OFF = SB_W_OFF + 3 * SB_T16;                // Z pieces                               48 KB
+constexpr uint32_t SB_DV_OFF = SB_Z_OFF + 3 * SB_T16;               // dv panel pieces                        48 KB
+constexpr uint32_t SB_LAND_OFF = SB_DV_OFF + 3 * SB_T16;            // raw fp32 Z of the next tile (2 x 16 KB) 32 KB
+constexpr uint32_t SB_PAR_OFF = SB_LAND_OFF + 2 * ST_KB_BYTES;      // b[128] | u[128] | gs[128] | bts[128] | red[4][2][128]
 constexpr uint32_t SB_PAR_BYTES = 4 * (4 * 128 + 4 * 2 * 128);
 constexpr uint32_t SB_BAR_OFF = SB_PAR_OFF + SB_PAR_BYTES;
 constexpr uint32_t SB_SMEM_BYTES = 1024 + SB_BAR_OFF + 256;
 constexpr int SB_CHAIN_TILES = 2;                                   // dw accumulation chain: 2 tiles = 256 rows
 
-// MN-major, SWIZZLE_128B matrix descriptor: 8 K-rows of 128 B form one swizzle atom (SBO = 1024 B between
-// atoms along K); LBO = byte distance between blocks of 32 elements along M/N (one panel here)
-__device__ __forceinline__ uint64_t st_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+// MN-major, SWIZZLE_128B descriptor for 16-bit operands: 8 K-rows of 128 B (64 elements along M/N) form one
+// swizzle atom, SBO = 1024 B between atoms along K; a single 64-element block along M/N here (LBO unused)
+__device__ __forceinline__ uint64_t st_desc_mn(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)1 << 16;
   d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+__device__ __forceinline__ void st_umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the six partial products of a BF16x3 multiply, smallest terms first; a[i], b[i] = descriptors of piece i
+__device__ __forceinline__ void st_mma_bf16x3(uint32_t tmem_d, const uint64_t (&a)[3], const uint64_t (&b)[3], uint32_t idesc,
+                                              uint32_t accumulate) {
+  st_umma_bf16(tmem_d, a[0], b[2], idesc, accumulate);
+  st_umma_bf16(tmem_d, a[2], b[0], idesc, 1u);
+  st_umma_bf16(tmem_d, a[1], b[1], idesc, 1u);
+  st_umma_bf16(tmem_d, a[0], b[1], idesc, 1u);
+  st_umma_bf16(tmem_d, a[1], b[0], idesc, 1u);
+  st_umma_bf16(tmem_d, a[0], b[0], idesc, 1u);
+}
+// x = p1 + p2 + p3 exactly, each piece a bf16 (kept in the top half of a 32-bit word)
+__device__ __forceinline__ void st_cut3(float x, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+  p1 = __float_as_uint(x) & 0xFFFF0000u;
+  const float r1 = x - __uint_as_float(p1);
+  p2 = __float_as_uint(r1) & 0xFFFF0000u;
+  const float r2 = r1 - __uint_as_float(p2);
+  p3 = __float_as_uint(r2) & 0xFFFF0000u;
+}
+__device__ __forceinline__ uint32_t st_pack(uint32_t lo_elem, uint32_t hi_elem) {   // two bf16 (top halves) -> one word
+  return __byte_perm(lo_elem, hi_elem, 0x7632);
+}
+// eight consecutive fp32 values of row r -> one 16-byte chunk (index c8) of each of the three bf16 piece tiles
+__device__ __forceinline__ void st_store8(uint8_t* t1, uint8_t* t2, uint8_t* t3, int r, int c8, const float (&x)[8]) {
+  uint32_t p1[8], p2[8], p3[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) st_cut3(x[i], p1[i], p2[i], p3[i]);
+  const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4));
+  *reinterpret_cast<uint4*>(t1 + off) = make_uint4(st_pack(p1[0], p1[1]), st_pack(p1[2], p1[3]), st_pack(p1[4], p1[5]), st_pack(p1[6], p1[7]));
+  *reinterpret_cast<uint4*>(t2 + off) = make_uint4(st_pack(p2[0], p2[1]), st_pack(p2[2], p2[3]), st_pack(p2[4], p2[5]), st_pack(p2[6], p2[7]));
+  *reinterpret_cast<uint4*>(t3 + off) = make_uint4(st_pack(p3[0], p3[1]), st_pack(p3[2], p3[3]), st_pack(p3[4], p3[5]), st_pack(p3[6], p3[7]));
 }
 // tanh to ~1e-7 absolute (the contract is max-norm relative 1e-5 on O(1) values): 2 MUFU + 3 FMA-class ops
 __device__ __forceinline__ float st_tanh(float x) {
@@ -409,12 +450,25 @@ __device__ __forceinline__ float st_col_sums(float (&x)[32], int lane) {
   return x[0];
 }
 
+// w [D][A] fp32 -> w^T [A][D] as three bf16 piece matrices
+__global__ void st_wt_cut3_kernel(const float* __restrict__ w, uint16_t* __restrict__ w1, uint16_t* __restrict__ w2,
+                                  uint16_t* __restrict__ w3) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ST_A * ST_D) return;
+  const int a = idx / ST_D, d = idx % ST_D;
+  uint32_t p1, p2, p3;
+  st_cut3(w[d * ST_A + a], p1, p2, p3);
+  w1[idx] = (uint16_t)(p1 >> 16);
+  w2[idx] = (uint16_t)(p2 >> 16);
+  w3[idx] = (uint16_t)(p3 >> 16);
+}
+
 __global__ void __launch_bounds__(192, 1)
-semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmWhi,
-                       const __grid_constant__ CUtensorMap tmWlo, int64_t n, int P, const float* __restrict__ dout,
-                       const float* __restrict__ beta, const float* __restrict__ b, const float* __restrict__ u,
-                       int mode, const float* __restrict__ dsbar, float* __restrict__ dZ, float* const* __restrict__ dz_tab,
-                       int64_t dz_stride, float* __restrict__ part) {
+semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW1,
+                       const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3, int64_t n, int P,
+                       const float* __restrict__ dout, const float* __restrict__ beta, const float* __restrict__ b,
+                       const float* __restrict__ u, int mode, const float* __restrict__ dsbar, float* __restrict__ dZ,
+                       float* const* __restrict__ dz_tab, int64_t dz_stride, float* __restrict__ part) {
   constexpr int D = ST_D, A = ST_A;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (st_smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -473,79 +527,67 @@ semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0 && my_tiles > 0) {
-      st_mbar_expect_tx(w_full, 4 * SB_PANEL_BYTES);
-      for (int kb = 0; kb < 2; ++kb) {
-        st_tma_load_2d(base + SB_W_OFF + kb * SB_PANEL_BYTES, &tmWhi, kb * ST_BK, 0, w_full);
-        st_tma_load_2d(base + SB_W_OFF + (2 + kb) * SB_PANEL_BYTES, &tmWlo, kb * ST_BK, 0, w_full);
-      }
+      st_mbar_expect_tx(w_full, 3 * SB_T16);
+      st_tma_load_2d(base + SB_W_OFF, &tmW1, 0, 0, w_full);
+      st_tma_load_2d(base + SB_W_OFF + SB_T16, &tmW2, 0, 0, w_full);
+      st_tma_load_2d(base + SB_W_OFF + 2 * SB_T16, &tmW3, 0, 0, w_full);
       for (int64_t it = 0; it < my_tiles; ++it) {
         if (it > 0) st_mbar_wait(land_free, (uint32_t)((it - 1) & 1));
         const int64_t tile = blockIdx.x + it * gridDim.x;
         const int row0 = (int)(tile * rows_per_tile);
-        st_mbar_expect_tx(land_full, 2 * SB_PANEL_BYTES);
+        st_mbar_expect_tx(land_full, 2 * ST_KB_BYTES);
         st_tma_load_2d(base + SB_LAND_OFF, &tmZ, 0, row0, land_full);
-        st_tma_load_2d(base + SB_LAND_OFF + SB_PANEL_BYTES, &tmZ, ST_BK, row0, land_full);
+        st_tma_load_2d(base + SB_LAND_OFF + ST_KB_BYTES, &tmZ, ST_BK, row0, land_full);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0 && my_tiles > 0) {
-      constexpr uint32_t kTf32 = (1u << 4) | (2u << 7) | (2u << 10);
-      const uint32_t id1 = kTf32 | ((uint32_t)(A >> 3) << 17) | ((uint32_t)(ST_BM >> 4) << 24);               // 128 x 128, K | K
-      const uint32_t id2 = kTf32 | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(ST_BM >> 4) << 24);   // 128 x 64,  K | MN
-      const uint32_t id3 = kTf32 | (1u << 15) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);  // 64 x 32, MN | MN
-      const uint32_t wT = base + SB_W_OFF, zh = base + SB_ZH_OFF, zl = base + SB_ZL_OFF;
-      const uint32_t dvh = base + SB_DVH_OFF, dvl = base + SB_DVL_OFF;
+      constexpr uint32_t kBf16 = (1u << 4) | (1u << 7) | (1u << 10);      // D = f32, A = B = bf16
+      const uint32_t id1 = kBf16 | ((uint32_t)(A >> 3) << 17) | ((uint32_t)(ST_BM >> 4) << 24);                       // 128 x 128, K | K
+      const uint32_t id2 = kBf16 | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(ST_BM >> 4) << 24);           // 128 x 64,  K | MN
+      const uint32_t id3 = kBf16 | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24); // 64 x 64,  MN | MN
+      const uint32_t wT = base + SB_W_OFF, zt = base + SB_Z_OFF, dvt = base + SB_DV_OFF;
       st_mbar_wait(w_full, 0);
       for (int64_t it = 0; it < my_tiles; ++it) {
         const bool last = it + 1 == my_tiles;
-        // ---- GEMM1: acc1 = Z w  (recompute of the pre-activation) ----
+        // ---- GEMM1: acc1 = Z w  (recompute of the pre-activation); K = d = 64 = 4 steps of 16 ----
         st_mbar_wait(z_ready, (uint32_t)(it & 1));
         if (it > 0) st_mbar_wait(acc1_free, (uint32_t)((it - 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t a_hi = st_desc(zh + kb * SB_PANEL_BYTES), a_lo = st_desc(zl + kb * SB_PANEL_BYTES);
-          const uint64_t b_hi = st_desc(wT + kb * SB_PANEL_BYTES), b_lo = st_desc(wT + (2 + kb) * SB_PANEL_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adv = (uint64_t)((k * 32) >> 4);
-            st_umma_tf32(t_acc1, a_lo + adv, b_hi + adv, id1, (kb | k) != 0);
-            st_umma_tf32(t_acc1, a_hi + adv, b_lo + adv, id1, 1u);
-            st_umma_tf32(t_acc1, a_hi + adv, b_hi + adv, id1, 1u);
-          }
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t adv = (uint64_t)((k * 32) >> 4);
+          const uint64_t a[3] = {st_desc(zt) + adv, st_desc(zt + SB_T16) + adv, st_desc(zt + 2 * SB_T16) + adv};
+          const uint64_t bb[3] = {st_desc(wT) + adv, st_desc(wT + SB_T16) + adv, st_desc(wT + 2 * SB_T16) + adv};
+          st_mma_bf16x3(t_acc1, a, bb, id1, k != 0);
         }
         st_umma_commit(acc1_full);
-        // ---- per dv panel: GEMM2 (dZ += dv w^T) and GEMM3 (dw += Z^T dv) ----
-        for (int j = 0; j < 4; ++j) {
-          const int64_t pc = it * 4 + j;
+        // ---- per dv panel (64 columns of a): GEMM2 (dZ += dv w^T) and GEMM3 (dw += Z^T dv) ----
+        for (int j = 0; j < 2; ++j) {
+          const int64_t pc = it * 2 + j;
           st_mbar_wait(dvp_full, (uint32_t)(pc & 1));
           if (j == 0 && it > 0) st_mbar_wait(dz_free, (uint32_t)((it - 1) & 1));
           if (j == 0 && (it % SB_CHAIN_TILES) == 0 && it >= SB_CHAIN_TILES)
             st_mbar_wait(dw_free, (uint32_t)(((it / SB_CHAIN_TILES) - 1) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          // GEMM2: A = dv panel (K-major, K = 32 a), B = w^T rows a in [32j, 32j+32) read MN-major (N = d)
+          // GEMM2: A = dv panel (K-major, K = 64 a), B = w^T rows a in [64j, 64j+64) read MN-major (N = d = 64)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t adv = (uint64_t)((k * 32) >> 4);
-            const uint64_t a_hi = st_desc(dvh) + adv, a_lo = st_desc(dvl) + adv;
-            const uint32_t wrow = (uint32_t)((32 * j + 8 * k) * 128);
-            const uint64_t b_hi = st_desc_mn(wT + wrow, SB_PANEL_BYTES), b_lo = st_desc_mn(wT + 2 * SB_PANEL_BYTES + wrow, SB_PANEL_BYTES);
-            st_umma_tf32(t_dz, a_lo, b_hi, id2, (j | k) != 0);
-            st_umma_tf32(t_dz, a_hi, b_lo, id2, 1u);
-            st_umma_tf32(t_dz, a_hi, b_hi, id2, 1u);
+            const uint32_t wrow = (uint32_t)((64 * j + 16 * k) * 128);
+            const uint64_t a[3] = {st_desc(dvt) + adv, st_desc(dvt + SB_T16) + adv, st_desc(dvt + 2 * SB_T16) + adv};
+            const uint64_t bb[3] = {st_desc_mn(wT + wrow), st_desc_mn(wT + SB_T16 + wrow), st_desc_mn(wT + 2 * SB_T16 + wrow)};
+            st_mma_bf16x3(t_dz, a, bb, id2, (j | k) != 0);
           }
-          // GEMM3: A = Z^T (MN-major: M = d = 2 blocks of 32, K = 8 rows per step), B = dv panel (MN-major, N = 32 a)
+          // GEMM3: A = Z^T (MN-major: M = d = 64, 16 rows of r per step), B = dv panel (MN-major, N = 64 a)
           const uint32_t first = ((it % SB_CHAIN_TILES) == 0) ? 0u : 1u;
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const uint32_t koff = (uint32_t)(k * 1024);
-            const uint64_t a_hi = st_desc_mn(zh + koff, SB_PANEL_BYTES), a_lo = st_desc_mn(zl + koff, SB_PANEL_BYTES);
-            const uint64_t b_hi = st_desc_mn(dvh + koff, SB_PANEL_BYTES), b_lo = st_desc_mn(dvl + koff, SB_PANEL_BYTES);
-            const uint32_t acc = t_dw + (uint32_t)(32 * j);
-            st_umma_tf32(acc, a_lo, b_hi, id3, (k != 0) ? 1u : first);
-            st_umma_tf32(acc, a_hi, b_lo, id3, 1u);
-            st_umma_tf32(acc, a_hi, b_hi, id3, 1u);
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t koff = (uint32_t)(k * 16 * 128);
+            const uint64_t a[3] = {st_desc_mn(zt + koff), st_desc_mn(zt + SB_T16 + koff), st_desc_mn(zt + 2 * SB_T16 + koff)};
+            const uint64_t bb[3] = {st_desc_mn(dvt + koff), st_desc_mn(dvt + SB_T16 + koff), st_desc_mn(dvt + 2 * SB_T16 + koff)};
+            st_mma_bf16x3(t_dw + (uint32_t)(64 * j), a, bb, id3, (k != 0) ? 1u : first);
           }
           st_umma_commit(dvp_free);
         }
@@ -561,6 +603,8 @@ semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     float du_acc[4] = {0.f, 0.f, 0.f, 0.f}, db_acc[4] = {0.f, 0.f, 0.f, 0.f};
     float* my_part = part + (size_t)blockIdx.x * ((size_t)D * A + 2 * A);
+    uint8_t* z1 = gen + SB_Z_OFF;
+    uint8_t* dv1 = gen + SB_DV_OFF;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const bool last = it + 1 == my_tiles;
       const int64_t tile = blockIdx.x + it * gridDim.x;
@@ -570,30 +614,24 @@ semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
       const bool live = r < rows_here;
       const int64_t node = node0 + r / P;
       const float* drow = dout + node * D;
-      // ---- split the landed raw tile into hi / lo, g = <dout, Z> on the way ----
+      // ---- cut the landed raw tile into bf16 pieces, g = <dout, Z> on the way ----
       st_mbar_wait(land_full, (uint32_t)(it & 1));
-      if (it > 0) st_mbar_wait(g3_done, (uint32_t)((it - 1) & 1));        // GEMM3 of the previous tile has read Z hi / lo
+      if (it > 0) st_mbar_wait(g3_done, (uint32_t)((it - 1) & 1));        // GEMM3 of the previous tile has read the Z pieces
       float g = 0.f;
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
+      for (int c8 = 0; c8 < 8; ++c8) {          // 8 floats = d in [8 c8, 8 c8 + 8): K-block c8 / 4, 16-byte chunks 2 (c8 % 4), +1
+        float x[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t off = kb * SB_PANEL_BYTES + st_sw128(r, 4 * c);
-          const uint4 x = *reinterpret_cast<const uint4*>(gen + SB_LAND_OFF + off);
-          uint4 h, l;
-          h.x = x.x & 0xFFFFE000u; l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
-          h.y = x.y & 0xFFFFE000u; l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
-          h.z = x.z & 0xFFFFE000u; l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
-          h.w = x.w & 0xFFFFE000u; l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
-          *reinterpret_cast<uint4*>(gen + SB_ZH_OFF + off) = h;
-          *reinterpret_cast<uint4*>(gen + SB_ZL_OFF + off) = l;
-          if (live) {
-            const float4 dd = ldg4(drow + kb * 32 + 4 * c);
-            g = fmaf(__uint_as_float(x.x), dd.x, g);
-            g = fmaf(__uint_as_float(x.y), dd.y, g);
-            g = fmaf(__uint_as_float(x.z), dd.z, g);
-            g = fmaf(__uint_as_float(x.w), dd.w, g);
-          }
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t off = (uint32_t)(c8 >> 2) * ST_KB_BYTES + st_sw128(r, 4 * (2 * (c8 & 3) + hh));
+          const float4 v4 = *reinterpret_cast<const float4*>(gen + SB_LAND_OFF + off);
+          x[4 * hh] = v4.x; x[4 * hh + 1] = v4.y; x[4 * hh + 2] = v4.z; x[4 * hh + 3] = v4.w;
+        }
+        st_store8(z1, z1 + SB_T16, z1 + 2 * SB_T16, r, c8, x);
+        if (live) {
+          const float4 d0 = ldg4(drow + 8 * c8), d1 = ldg4(drow + 8 * c8 + 4);
+          g = fmaf(x[0], d0.x, g); g = fmaf(x[1], d0.y, g); g = fmaf(x[2], d0.z, g); g = fmaf(x[3], d0.w, g);
+          g = fmaf(x[4], d1.x, g); g = fmaf(x[5], d1.y, g); g = fmaf(x[6], d1.z, g); g = fmaf(x[7], d1.w, g);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -619,38 +657,37 @@ semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
       st_mbar_wait(acc1_full, (uint32_t)(it & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        uint32_t acc[32];
-        st_tmem_ld32(lane_base + (uint32_t)(32 * j), acc);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (j == 3) {
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          st_mbar_arrive(acc1_free);
-        }
-        float y[32], dv[32];
+      for (int j = 0; j < 2; ++j) {
+        const int64_t pc = it * 2 + j;
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const int c0 = 64 * j + 32 * hh;
+          uint32_t acc[32];
+          st_tmem_ld32(lane_base + (uint32_t)c0, acc);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (j == 1 && hh == 1) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            st_mbar_arrive(acc1_free);
+          }
+          float y[32], dv[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float v = st_tanh(__uint_as_float(acc[c]) + bs[32 * j + c]);
-          y[c] = ds * v;
-          dv[c] = ds * us[32 * j + c] * (1.f - v * v);
-        }
-        const int64_t pc = it * 4 + j;
-        if (pc > 0) st_mbar_wait(dvp_free, (uint32_t)((pc - 1) & 1));     // the MMAs of the previous panel have read it
+          for (int c = 0; c < 32; ++c) {
+            const float v = st_tanh(__uint_as_float(acc[c]) + bs[c0 + c]);
+            y[c] = ds * v;
+            dv[c] = ds * us[c0 + c] * (1.f - v * v);
+          }
+          if (hh == 0 && pc > 0) st_mbar_wait(dvp_free, (uint32_t)((pc - 1) & 1));   // the previous panel's MMAs have read it
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t off = st_sw128(r, 4 * c);
-          uint4 h, l;
-          h.x = __float_as_uint(dv[4 * c]) & 0xFFFFE000u;     l.x = __float_as_uint(dv[4 * c] - __uint_as_float(h.x));
-          h.y = __float_as_uint(dv[4 * c + 1]) & 0xFFFFE000u; l.y = __float_as_uint(dv[4 * c + 1] - __uint_as_float(h.y));
-          h.z = __float_as_uint(dv[4 * c + 2]) & 0xFFFFE000u; l.z = __float_as_uint(dv[4 * c + 2] - __uint_as_float(h.z));
-          h.w = __float_as_uint(dv[4 * c + 3]) & 0xFFFFE000u; l.w = __float_as_uint(dv[4 * c + 3] - __uint_as_float(h.w));
-          *reinterpret_cast<uint4*>(gen + SB_DVH_OFF + off) = h;
-          *reinterpret_cast<uint4*>(gen + SB_DVL_OFF + off) = l;
+          for (int c8 = 0; c8 < 4; ++c8) {
+            const float x[8] = {dv[8 * c8], dv[8 * c8 + 1], dv[8 * c8 + 2], dv[8 * c8 + 3],
+                                dv[8 * c8 + 4], dv[8 * c8 + 5], dv[8 * c8 + 6], dv[8 * c8 + 7]};
+            st_store8(dv1, dv1 + SB_T16, dv1 + 2 * SB_T16, r, 4 * hh + c8, x);
+          }
+          du_acc[2 * j + hh] += st_col_sums(y, lane);
+          db_acc[2 * j + hh] += st_col_sums(dv, lane);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         st_mbar_arrive(dvp_full);
-        du_acc[j] += st_col_sums(y, lane);
-        db_acc[j] += st_col_sums(dv, lane);
       }
       // ---- dZ = beta dout + dv w^T ----
       st_mbar_wait(dz_full, (uint32_t)(it & 1));
@@ -761,6 +798,31 @@ static int st_make_map(CUtensorMap* m, const float* ptr, uint64_t inner, uint64_
   return 0;
 }
 
+// [rows][64 bf16] row-major, box = 64 x box_rows, 128-byte swizzle
+static int st_make_map_bf16(CUtensorMap* m, const uint16_t* ptr, uint64_t rows, uint32_t box_rows) {
+  static StEncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<StEncodeTiledFn>(p);
+  }
+  if (!fn) return fail_arg("han_semantic_bwd_tc", "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {64, rows};
+  cuuint64_t strides[1] = {64 * sizeof(uint16_t)};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_error, sizeof(g_last_error), "han_semantic_bwd_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return -2;
+  }
+  return 0;
+}
+
 }  // namespace han
 
 using namespace han;
@@ -811,7 +873,7 @@ int han_semantic_fwd_tc(const float* Z, int64_t n, int P, int D, int A, const fl
 }
 
 size_t han_semantic_bwd_tc_workspace_bytes(void) {
-  return (size_t)2 * ST_A * ST_D * sizeof(float) + (size_t)kNumSMs * ((size_t)ST_D * ST_A + 2 * ST_A) * sizeof(float);
+  return (size_t)3 * ST_A * ST_D * sizeof(uint16_t) + (size_t)kNumSMs * ((size_t)ST_D * ST_A + 2 * ST_A) * sizeof(float);
 }
 
 int han_semantic_bwd_tc(const float* dout, const float* Z, const float* beta, int64_t n, int P, int D, int A,
@@ -827,23 +889,26 @@ int han_semantic_bwd_tc(const float* dout, const float* Z, const float* beta, in
   HAN_REQUIRE(((uintptr_t)Z % 16 == 0) && ((uintptr_t)ws % 16 == 0) && ((uintptr_t)dout % 16 == 0) &&
               ((uintptr_t)dZ % 16 == 0), "16-byte alignment");
   cudaStream_t st = as_stream(stream);
-  float* wt_hi = reinterpret_cast<float*>(ws);
-  float* wt_lo = wt_hi + ST_A * ST_D;
-  float* part = wt_lo + ST_A * ST_D;
-  st_wt_split_kernel<<<(ST_A * ST_D + 255) / 256, 256, 0, st>>>(w, wt_hi, wt_lo);
-  CUtensorMap tmZ, tmWhi, tmWlo;
+  uint16_t* w1 = reinterpret_cast<uint16_t*>(ws);
+  uint16_t* w2 = w1 + ST_A * ST_D;
+  uint16_t* w3 = w2 + ST_A * ST_D;
+  float* part = reinterpret_cast<float*>(w3 + ST_A * ST_D);
+  st_wt_cut3_kernel<<<(ST_A * ST_D + 255) / 256, 256, 0, st>>>(w, w1, w2, w3);
+  CUtensorMap tmZ, tmW1, tmW2, tmW3;
   int rc = st_make_map(&tmZ, Z, ST_D, (uint64_t)(n * P), ST_D, ST_BM);
   if (rc) return rc;
-  rc = st_make_map(&tmWhi, wt_hi, ST_D, ST_A, ST_D, ST_A);
+  rc = st_make_map_bf16(&tmW1, w1, ST_A, ST_A);
   if (rc) return rc;
-  rc = st_make_map(&tmWlo, wt_lo, ST_D, ST_A, ST_D, ST_A);
+  rc = st_make_map_bf16(&tmW2, w2, ST_A, ST_A);
+  if (rc) return rc;
+  rc = st_make_map_bf16(&tmW3, w3, ST_A, ST_A);
   if (rc) return rc;
   HAN_SMEM_ATTR_ONCE(semantic_bwd_tc_kernel, SB_SMEM_BYTES);
   const int64_t n_tiles = ceil_div64(n, ST_BM / P);
   const unsigned grid = (unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
   cudaMemsetAsync(part, 0, (size_t)grid * ((size_t)ST_D * ST_A + 2 * ST_A) * sizeof(float), st);   // the dw drains accumulate
-  semantic_bwd_tc_kernel<<<grid, 192, SB_SMEM_BYTES, st>>>(tmZ, tmWhi, tmWlo, n, P, dout, beta, b, u, mode, dsbar, dZ, dz_tab,
-                                                         dz_stride, part);
+  semantic_bwd_tc_kernel<<<grid, 192, SB_SMEM_BYTES, st>>>(tmZ, tmW1, tmW2, tmW3, n, P, dout, beta, b, u, mode, dsbar, dZ,
+                                                         dz_tab, dz_stride, part);
   const int64_t cols = (int64_t)ST_D * ST_A + 2 * ST_A;
   st_bwd_reduce_kernel<<<(unsigned)ceil_div64(cols, 128), 128, 0, st>>>(part, (int)grid, dw, db, du);
   return check_launch(__func__);
