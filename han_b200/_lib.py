@@ -70,6 +70,10 @@ _SIGNATURES = {
     "han_semantic_bwd_tc_workspace_bytes": (SZ, []),
     "han_semantic_bwd_tc": (c_int, [P, P, P, I64, I, I, I, P, P, P, I, P, P, P, P, P, P, SZ, P, I64, P]),
     "han_semantic_fwd_tc": (c_int, [P, I64, I, I, I, P, P, P, I, P, P, P, P, P, SZ, I, P]),
+    "han_dense_blocks": (c_int, []),
+    "han_dense_fwd": (c_int, [P, I64, I, I64, P, I, P, P, P]),
+    "han_dense_bwd": (c_int, [P, I64, I, I64, P, I, P, P, P, P, P]),
+    "han_masked_ce": (c_int, [P, P, P, P, I64, I, P, P, P]),
     "han_adam_l2_step": (c_int, [P, P, P, P, I64, P, FL, FL, FL, FL, FL, P]),
     "han_project_dx": (c_int, [P, I64, I, I, P, I64, I64, P, I64, I, P, FL, I, I64, P]),
 }
@@ -121,7 +125,7 @@ KERNELS_PER_CALL = {
     "han_attn_coefs": 1, "han_attn_bwd_prep": 1,
     "han_csr_chunk_rows": 1, "han_attn_fwd_chunked": 1, "han_attn_bwd_src_chunked": 1, "han_attn_bwd_dst": 1,
     "han_attn_bwd_finish": 1, "han_reduce_partials": 1, "han_semantic_fwd": 1, "han_semantic_combine": 1,
-    "han_semantic_bwd": 2, "han_adam_l2_step": 1, "han_project_dx": 1,
+    "han_semantic_bwd": 2, "han_adam_l2_step": 1, "han_dense_fwd": 1, "han_dense_bwd": 1, "han_masked_ce": 1, "han_project_dx": 1,
     "han_attn_fwd_chunked_split": 2, "han_attn_bwd_src_chunked_split": 2, "han_semantic_fwd_tc": 2, "han_semantic_bwd_tc": 3,
 }
 

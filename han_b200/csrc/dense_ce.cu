@@ -1,0 +1,277 @@
+// The classifier and the training loss of the step (models/gat.py:66-72 `tf.layers.dense(final_embed, nb_classes)`;
+// models/base_gattn.py:41-48 `masked_softmax_cross_entropy`) as hand-written kernels, so that the timed step launches
+// no stock-library GEMM / softmax kernels.  Exact-FP32 FFMA: these are skinny products (n x D by D x C with D = 64 and
+// C = 3..349) that are bound by reading final_embed once and writing the logits once.
+//
+//   han_dense_fwd : Y = X W + b                                   one pass over X, W resident in shared memory
+//   han_dense_bwd : dX = dY W^T ; dW = X^T dY ; db = sum dY       persistent CTAs, dW / db in registers across tiles,
+//                                                                 deterministic two-stage reduce (han_reduce_partials)
+//   han_masked_ce : loss = sum_i mask_i xent_i / sum mask ; dlogits = (softmax * sum(labels) - labels) mask_i / sum mask
+//                   (tf.nn.softmax_cross_entropy_with_logits: labels need not be one-hot; no gradient to them)
+#include "han_common.cuh"
+
+namespace han {
+
+constexpr int DN_ROWS = 64;        // rows per tile
+constexpr int DN_THREADS = 256;
+constexpr int DN_MAXC = 384;
+constexpr int DN_MAXD = 64;
+
+// ---- forward: thread = 4 rows x columns tx, tx+16, ... ------------------------------------------------------------
+__global__ void __launch_bounds__(DN_THREADS)
+dense_fwd_kernel(const float* __restrict__ X, int64_t n, int D, int64_t ldx, const float* __restrict__ W, int C,
+                 const float* __restrict__ b, float* __restrict__ Y) {
+  extern __shared__ __align__(16) float smem[];
+  const int CP = C | 1;                         // odd leading dimension: column-strided reads are conflict-free
+  float* Ws = smem;                             // [D][CP]
+  float* Xs = Ws + (size_t)D * CP;              // [DN_ROWS][D + 1]
+  float* bsm = Xs + (size_t)DN_ROWS * (D + 1);  // [C]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int i = tid; i < D * C; i += DN_THREADS) Ws[(i / C) * CP + (i % C)] = W[i];
+  for (int i = tid; i < C; i += DN_THREADS) bsm[i] = b[i];
+  const int64_t n_tiles = ceil_div64(n, DN_ROWS);
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * DN_ROWS;
+    __syncthreads();
+    for (int i = tid; i < DN_ROWS * D; i += DN_THREADS) {
+      const int r = i / D, d = i % D;
+      Xs[r * (D + 1) + d] = (r0 + r < n) ? ldg_stream_f32(X + (r0 + r) * ldx + d) : 0.f;
+    }
+    __syncthreads();
+    for (int cb = 0; cb < C; cb += 64) {
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int d = 0; d < D; ++d) {
+        float xv[4], wv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[i] = Xs[(4 * ty + i) * (D + 1) + d];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = cb + tx + 16 * j;
+          wv[j] = (c < C) ? Ws[d * CP + c] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t r = r0 + 4 * ty + i;
+        if (r < n) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = cb + tx + 16 * j;
+            if (c < C) Y[r * C + c] = acc[i][j] + bsm[c];
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---- backward ---------------------------------------------------------------------------------------------------------
+// Per tile: dX rows (thread = 4 rows x d = tx, tx+16, ...) and the dW / db contributions (thread = (d, c = cq + 4 j)).
+template <int CT>   // CT = ceil(C / 4): dW columns per thread
+__global__ void __launch_bounds__(DN_THREADS)
+dense_bwd_kernel(const float* __restrict__ X, int64_t n, int D, int64_t ldx, const float* __restrict__ W, int C,
+                 const float* __restrict__ dY, const float* __restrict__ scale, float* __restrict__ dX,
+                 float* __restrict__ part) {
+  extern __shared__ __align__(16) float smem[];
+  const int CP = C | 1;
+  float* Ws = smem;                               // [D][CP]
+  float* Xs = Ws + (size_t)D * CP;                // [DN_ROWS][D + 1]
+  float* Gs = Xs + (size_t)DN_ROWS * (D + 1);     // [DN_ROWS][CP]   dY tile (times the upstream scalar)
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int i = tid; i < D * C; i += DN_THREADS) Ws[(i / C) * CP + (i % C)] = W[i];
+  const float sc = scale ? *scale : 1.f;
+  const int dd = tid >> 2, cq = tid & 3;          // dW: this thread's feature d (D <= 64) and column residue
+  float dw[CT];
+#pragma unroll
+  for (int j = 0; j < CT; ++j) dw[j] = 0.f;
+  float dbv = 0.f, dbv2 = 0.f;                    // db: thread t sums column t (and t + 256)
+  const int64_t n_tiles = ceil_div64(n, DN_ROWS);
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * DN_ROWS;
+    __syncthreads();
+    for (int i = tid; i < DN_ROWS * D; i += DN_THREADS) {
+      const int r = i / D, d = i % D;
+      Xs[r * (D + 1) + d] = (r0 + r < n) ? ldg_stream_f32(X + (r0 + r) * ldx + d) : 0.f;
+    }
+    for (int i = tid; i < DN_ROWS * C; i += DN_THREADS) {
+      const int r = i / C, c = i % C;
+      Gs[r * CP + c] = (r0 + r < n) ? sc * ldg_stream_f32(dY + (r0 + r) * C + c) : 0.f;
+    }
+    __syncthreads();
+    // dX = dY W^T
+    if (dX != nullptr) {
+      for (int db0 = 0; db0 < D; db0 += 64) {
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int c = 0; c < C; ++c) {
+          float gv[4], wv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) gv[i] = Gs[(4 * ty + i) * CP + c];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int d = db0 + tx + 16 * j;
+            wv[j] = (d < D) ? Ws[d * CP + c] : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gv[i], wv[j], acc[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t r = r0 + 4 * ty + i;
+          if (r < n) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int d = db0 + tx + 16 * j;
+              if (d < D) dX[r * D + d] = acc[i][j];
+            }
+          }
+        }
+      }
+    }
+    // dW += X^T dY, db += column sums
+    if (dd < D) {
+      for (int r = 0; r < DN_ROWS; ++r) {
+        const float xv = Xs[r * (D + 1) + dd];
+#pragma unroll
+        for (int j = 0; j < CT; ++j) {
+          const int c = cq + 4 * j;
+          if (c < C) dw[j] = fmaf(xv, Gs[r * CP + c], dw[j]);
+        }
+      }
+    }
+    if (tid < C) {
+      for (int r = 0; r < DN_ROWS; ++r) dbv += Gs[r * CP + tid];
+    }
+    if (tid + DN_THREADS < C) {
+      for (int r = 0; r < DN_ROWS; ++r) dbv2 += Gs[r * CP + tid + DN_THREADS];
+    }
+  }
+  // per-CTA partials: [dW (D*C) | db (C)]
+  float* my = part + (size_t)blockIdx.x * ((size_t)D * C + C);
+  if (dd < D) {
+#pragma unroll
+    for (int j = 0; j < CT; ++j) {
+      const int c = cq + 4 * j;
+      if (c < C) my[(size_t)dd * C + c] = dw[j];
+    }
+  }
+  if (tid < C) my[(size_t)D * C + tid] = dbv;
+  if (tid + DN_THREADS < C) my[(size_t)D * C + tid + DN_THREADS] = dbv2;
+}
+
+// ---- masked softmax cross-entropy: warp per row --------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+masked_ce_kernel(const float* __restrict__ logits, const float* __restrict__ labels, const float* __restrict__ mask,
+                 const float* __restrict__ mask_total, int64_t n, int C, float* __restrict__ loss_part,
+                 float* __restrict__ dlogits) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_total = 1.f / *mask_total;
+  float loss = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n; row += (int64_t)gridDim.x * 8) {
+    const float* lg = logits + row * C;
+    const float* lb = labels + row * C;
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lg[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f, ls = 0.f, dot = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float l = lg[c], y = lb[c];
+      se += expf(l - mx);
+      ls += y;
+      dot = fmaf(y, l, dot);
+    }
+    se = warp_sum(se);
+    ls = warp_sum(ls);
+    dot = warp_sum(dot);
+    const float lse = mx + logf(se);
+    const float wgt = mask[row] * inv_total;
+    loss += (lse * ls - dot) * wgt;                       // -sum_c y_c log_softmax_c
+    if (dlogits != nullptr) {
+      const float rinv = 1.f / se;
+      for (int c = lane; c < C; c += 32) dlogits[row * C + c] = (expf(lg[c] - mx) * rinv * ls - lb[c]) * wgt;
+    }
+  }
+  // lanes hold identical sums; one value per warp, 8 warps per CTA summed in a fixed order
+  __shared__ float ws[8];
+  if (lane == 0) ws[warp] = loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < 8; ++k) s += ws[k];
+    loss_part[blockIdx.x] = s;
+  }
+}
+
+static size_t dense_fwd_smem(int D, int C) { return ((size_t)D * (C | 1) + (size_t)DN_ROWS * (D + 1) + C) * sizeof(float); }
+static size_t dense_bwd_smem(int D, int C) {
+  return ((size_t)D * (C | 1) + (size_t)DN_ROWS * (D + 1) + (size_t)DN_ROWS * (C | 1)) * sizeof(float);
+}
+
+}  // namespace han
+
+using namespace han;
+
+extern "C" {
+
+int han_dense_blocks(void) { return kNumSMs * 2; }
+
+int han_dense_fwd(const float* X, int64_t n, int D, int64_t ldx, const float* W, int C, const float* b, float* Y,
+                  han_stream_t stream) {
+  HAN_REQUIRE(X && W && b && Y, "null pointer");
+  HAN_REQUIRE(n > 0 && D > 0 && D <= DN_MAXD && C > 0 && C <= DN_MAXC && ldx >= D, "sizes: D <= 64, C <= 384");
+  const size_t smem = dense_fwd_smem(D, C);
+  HAN_SMEM_ATTR_ONCE(dense_fwd_kernel, dense_fwd_smem(DN_MAXD, DN_MAXC));
+  const int64_t tiles = ceil_div64(n, DN_ROWS);
+  const unsigned grid = (unsigned)(tiles < han_dense_blocks() ? tiles : han_dense_blocks());
+  dense_fwd_kernel<<<grid, DN_THREADS, smem, as_stream(stream)>>>(X, n, D, ldx, W, C, b, Y);
+  return check_launch(__func__);
+}
+
+/* part: [han_dense_blocks()][D*C + C] per-CTA partials of dW | db (reduce with han_reduce_partials).
+ * scale (nullable): device scalar multiplied into dY (the upstream gradient of a scalar loss). dX nullable. */
+int han_dense_bwd(const float* X, int64_t n, int D, int64_t ldx, const float* W, int C, const float* dY,
+                  const float* scale, float* dX, float* part, han_stream_t stream) {
+  HAN_REQUIRE(X && W && dY && part, "null pointer");
+  HAN_REQUIRE(n > 0 && D > 0 && D <= DN_MAXD && C > 0 && C <= DN_MAXC && ldx >= D, "sizes: D <= 64, C <= 384");
+  const size_t smem = dense_bwd_smem(D, C);
+  cudaStream_t st = as_stream(stream);
+  const unsigned grid = (unsigned)han_dense_blocks();     // every CTA writes its partial (zeros if it has no tile)
+  const int ct = (C + 3) / 4;
+#define LAUNCH(CT)                                                                                             \
+  {                                                                                                            \
+    HAN_SMEM_ATTR_ONCE(dense_bwd_kernel<CT>, dense_bwd_smem(DN_MAXD, CT * 4 > DN_MAXC ? DN_MAXC : CT * 4));    \
+    dense_bwd_kernel<CT><<<grid, DN_THREADS, smem, st>>>(X, n, D, ldx, W, C, dY, scale, dX, part);             \
+  }
+  if (ct <= 4) LAUNCH(4)
+  else if (ct <= 16) LAUNCH(16)
+  else if (ct <= 48) LAUNCH(48)
+  else LAUNCH(96)
+#undef LAUNCH
+  return check_launch(__func__);
+}
+
+/* loss_part: [han_dense_blocks()] per-CTA partial sums of the loss; dlogits nullable (evaluation). */
+int han_masked_ce(const float* logits, const float* labels, const float* mask, const float* mask_total, int64_t n,
+                  int C, float* loss_part, float* dlogits, han_stream_t stream) {
+  HAN_REQUIRE(logits && labels && mask && mask_total && loss_part, "null pointer");
+  HAN_REQUIRE(n > 0 && C > 0, "sizes");
+  masked_ce_kernel<<<(unsigned)han_dense_blocks(), 256, 0, as_stream(stream)>>>(logits, labels, mask, mask_total, n, C,
+                                                                               loss_part, dlogits);
+  return check_launch(__func__);
+}
+
+}  // extern "C"

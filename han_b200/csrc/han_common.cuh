@@ -67,6 +67,11 @@ __device__ __forceinline__ float4 ldg4_stream(const float* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ float ldg_stream_f32(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ int ldg_stream_i32(const int* p) {
   int r;
   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));

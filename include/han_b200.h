@@ -261,6 +261,23 @@ int han_reduce_partials(const float* part, int nblocks, int64_t cols, float* out
 int han_adam_l2_step(float* p, const float* g, float* m, float* v, int64_t n, const int* step_ptr,
                      float lr, float beta1, float beta2, float eps, float l2_coef, han_stream_t stream);
 
+/* ---- Classifier and training loss. Replace models/gat.py:66-72 (tf.layers.dense) and models/base_gattn.py:41-48 ------ */
+/* Exact-FP32 kernels (han_b200/csrc/dense_ce.cu) for D <= 64, C <= 384.
+ * han_dense_fwd: Y [n][C] = X [n][ldx] (D columns used) * W [D][C] + b [C].
+ * han_dense_bwd: dX [n][D] (nullable) = dY W^T; per-CTA partials of dW [D][C] | db [C] into
+ *   part [han_dense_blocks()][D*C + C] (reduce with han_reduce_partials); scale (nullable): device scalar multiplied
+ *   into dY (the upstream gradient of a scalar loss).
+ * han_masked_ce: loss = sum_i mask_i * (-sum_c labels_ic log_softmax(logits_i)_c) / *mask_total as per-CTA partials
+ *   loss_part [han_dense_blocks()]; dlogits (nullable) [n][C] = (softmax_i * sum_c labels_ic - labels_i) * mask_i /
+ *   *mask_total.  mask_total is a DEVICE scalar (sum of the mask over ALL ranks in sharded runs). */
+int han_dense_blocks(void);
+int han_dense_fwd(const float* X, int64_t n, int D, int64_t ldx, const float* W, int C, const float* b, float* Y,
+                  han_stream_t stream);
+int han_dense_bwd(const float* X, int64_t n, int D, int64_t ldx, const float* W, int C, const float* dY,
+                  const float* scale, float* dX, float* part, han_stream_t stream);
+int han_masked_ce(const float* logits, const float* labels, const float* mask, const float* mask_total, int64_t n,
+                  int C, float* loss_part, float* dlogits, han_stream_t stream);
+
 /* ---- K-C / K-F: semantic attention. Replaces utils/layers.py:152-159 ------------------------ */
 /* Z [n][P][D], w [D][A], b [A], u [A].  Supported (D,A): han_semantic_shape_supported.
  * HAN_SEM_REFERENCE: writes out [n][D] and beta [n][P] (per-node softmax over meta-paths, :156).
