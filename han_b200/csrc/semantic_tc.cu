@@ -20,6 +20,7 @@
 //               weighted sum from the Z tile still sitting in the ring (Z = hi + lo exactly).
 // The epilogue of tile i runs under the MMAs of tile i+1 (second accumulator) and the TMA of tile i+2.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "han_common.cuh"
 
@@ -87,6 +88,20 @@ __device__ __forceinline__ void st_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) 
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void st_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+template <int N>
+__device__ __forceinline__ void st_tmem_ldN(uint32_t taddr, uint32_t (&r)[N]) {
+  if constexpr (N == 32) st_tmem_ld32(taddr, r);
+  else st_tmem_ld16(taddr, r);
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t st_desc(uint32_t smem_addr) {
@@ -435,16 +450,27 @@ __device__ __forceinline__ float st_tanh(float x) {
   const float e = __expf(2.f * x);
   return 1.f - __fdividef(2.f, e + 1.f);
 }
-// lane l ends up with the sum over the 32 lanes of x[l]
-__device__ __forceinline__ float st_col_sums(float (&x)[32], int lane) {
+// Sum over the 32 lanes of each of the N columns held as x[0..N): N = 32 leaves column l in lane l, N = 16 leaves
+// column l >> 1 in lanes l (both lanes of a pair hold it).  Reduce-scatter butterfly: N - 1 (+1) shuffles.
+template <int N>
+__device__ __forceinline__ float st_col_sums(float (&x)[N], int lane) {
+  int n = N;
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
+    if (n > 1) {
+      const int h = n >> 1;
+      const bool up = (lane & off) != 0;
 #pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = up ? x[i] : x[i + off];
-      const float keep = up ? x[i + off] : x[i];
-      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      for (int i = 0; i < N / 2; ++i) {
+        if (i < h) {
+          const float send = up ? x[i] : x[i + h];
+          const float keep = up ? x[i + h] : x[i];
+          x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      n = h;
+    } else {
+      x[0] += __shfl_xor_sync(0xffffffffu, x[0], off);
     }
   }
   return x[0];
@@ -463,7 +489,10 @@ __global__ void st_wt_cut3_kernel(const float* __restrict__ w, uint16_t* __restr
   w3[idx] = (uint16_t)(p3 >> 16);
 }
 
-__global__ void __launch_bounds__(192, 1)
+// NH = epilogue threads per tile row (2 or 4): with one warp per scheduler the epilogue is latency-bound (ncu:
+// issue slots 24 % busy, 6.3 cycles between issues); NH warps per TMEM lane quarter share each row's columns.
+template <int NH>
+__global__ void __launch_bounds__(64 + 128 * NH, 1)
 semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW1,
                        const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3, int64_t n, int P,
                        const float* __restrict__ dout, const float* __restrict__ beta, const float* __restrict__ b,
@@ -478,7 +507,9 @@ semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
   float* us = par + 128;        // u[128]
   float* gs = par + 256;        // g of the tile's rows
   float* bts = par + 384;       // beta of the tile's rows
-  float* red = par + 512;       // [4 warps][du 128 | db 128]
+  float* red = par + 512;       // [4 quarters][du 128 | db 128]   (also: g partials [NH][128] inside a tile)
+  constexpr int NE = 128 * NH;  // epilogue threads
+  constexpr int CW = 64 / NH;   // panel columns per epilogue thread
   const uint32_t bars = base + SB_BAR_OFF;
   const uint32_t w_full = bars, land_full = bars + 8, land_free = bars + 16, z_ready = bars + 24, acc1_full = bars + 32,
                  acc1_free = bars + 40, dvp_full = bars + 48, dvp_free = bars + 56, dz_full = bars + 64, dz_free = bars + 72,
@@ -492,24 +523,24 @@ semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
   const int64_t n_tiles = ceil_div64(n, nodes_per_tile);
   const int64_t my_tiles = (n_tiles > (int64_t)blockIdx.x) ? ceil_div64(n_tiles - blockIdx.x, gridDim.x) : 0;
 
-  for (int i = threadIdx.x; i < A; i += 192) {
+  for (int i = threadIdx.x; i < A; i += 64 + NE) {
     bs[i] = b[i];
     us[i] = u[i];
   }
   if (threadIdx.x == 0) {
     st_mbar_init(w_full, 1);
     st_mbar_init(land_full, 1);
-    st_mbar_init(land_free, 128);
-    st_mbar_init(z_ready, 128);
+    st_mbar_init(land_free, NE);
+    st_mbar_init(z_ready, NE);
     st_mbar_init(acc1_full, 1);
-    st_mbar_init(acc1_free, 128);
-    st_mbar_init(dvp_full, 128);
+    st_mbar_init(acc1_free, NE);
+    st_mbar_init(dvp_full, NE);
     st_mbar_init(dvp_free, 1);
     st_mbar_init(dz_full, 1);
-    st_mbar_init(dz_free, 128);
+    st_mbar_init(dz_free, NE);
     st_mbar_init(g3_done, 1);
     st_mbar_init(dw_full, 1);
-    st_mbar_init(dw_free, 128);
+    st_mbar_init(dw_free, NE);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -597,14 +628,16 @@ semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
       }
     }
   } else {
-    // ===== warps 2-5: thread = row of the tile =====
-    const int q = warp & 3;
+    // ===== epilogue warps: NH threads per row of the tile (sub = which share of the row's columns) =====
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int sub = (warp - 2) >> 2;            // 0 .. NH-1
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    float du_acc[4] = {0.f, 0.f, 0.f, 0.f}, db_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float du_acc[2] = {0.f, 0.f}, db_acc[2] = {0.f, 0.f};      // per panel: column 64 j + CW sub + (lane or lane / 2)
     float* my_part = part + (size_t)blockIdx.x * ((size_t)D * A + 2 * A);
     uint8_t* z1 = gen + SB_Z_OFF;
     uint8_t* dv1 = gen + SB_DV_OFF;
+    float* gpart = red;                         // [NH][128] partial g of this tile (red is only needed at the very end)
     for (int64_t it = 0; it < my_tiles; ++it) {
       const bool last = it + 1 == my_tiles;
       const int64_t tile = blockIdx.x + it * gridDim.x;
@@ -614,12 +647,13 @@ semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
       const bool live = r < rows_here;
       const int64_t node = node0 + r / P;
       const float* drow = dout + node * D;
-      // ---- cut the landed raw tile into bf16 pieces, g = <dout, Z> on the way ----
+      // ---- cut the landed raw tile into bf16 pieces (8 / NH chunks of 8 floats per thread), g = <dout, Z> on the way ----
       st_mbar_wait(land_full, (uint32_t)(it & 1));
       if (it > 0) st_mbar_wait(g3_done, (uint32_t)((it - 1) & 1));        // GEMM3 of the previous tile has read the Z pieces
       float g = 0.f;
 #pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {          // 8 floats = d in [8 c8, 8 c8 + 8): K-block c8 / 4, 16-byte chunks 2 (c8 % 4), +1
+      for (int cc = 0; cc < 8 / NH; ++cc) {     // 8 floats = d in [8 c8, 8 c8 + 8): K-block c8 / 4, 16-byte chunks 2 (c8 % 4), +1
+        const int c8 = sub * (8 / NH) + cc;
         float x[8];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -638,72 +672,75 @@ semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
       st_mbar_arrive(z_ready);
       st_mbar_arrive(land_free);
       const float bt = live ? beta[row0 + r] : 0.f;
-      gs[r] = g;
-      bts[r] = bt;
-      st_bar_epi<128>();
+      gpart[sub * 128 + r] = g;
+      if (sub == 0) bts[r] = bt;
+      st_bar_epi<NE>();
+      if (sub == 0) {
+        float gt = gpart[r];
+#pragma unroll
+        for (int k = 1; k < NH; ++k) gt += gpart[k * 128 + r];
+        gs[r] = gt;
+      }
+      st_bar_epi<NE>();
       float ds = 0.f;
       if (live) {
         if (mode == HAN_SEM_REFERENCE) {
           const int nl = r / P;
           float dot = 0.f;
           for (int pp = 0; pp < P; ++pp) dot = fmaf(bts[nl * P + pp], gs[nl * P + pp], dot);
-          ds = bt * (g - dot);
+          ds = bt * (gs[r] - dot);
         } else {
           ds = dsbar[r % P];
         }
       }
-      st_bar_epi<128>();          // gs / bts are rewritten by the next tile
+      st_bar_epi<NE>();          // gs / bts / gpart are rewritten by the next tile
       // ---- panels: v = tanh(acc1 + b), dv = ds u (1 - v^2) -> shared memory; du, db column sums ----
       st_mbar_wait(acc1_full, (uint32_t)(it & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
       for (int j = 0; j < 2; ++j) {
         const int64_t pc = it * 2 + j;
-#pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-          const int c0 = 64 * j + 32 * hh;
-          uint32_t acc[32];
-          st_tmem_ld32(lane_base + (uint32_t)c0, acc);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (j == 1 && hh == 1) {
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            st_mbar_arrive(acc1_free);
-          }
-          float y[32], dv[32];
+        const int c0 = 64 * j + CW * sub;
+        uint32_t acc[CW];
+        st_tmem_ldN<CW>(lane_base + (uint32_t)c0, acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (j == 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          st_mbar_arrive(acc1_free);
+        }
+        float y[CW], dv[CW];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float v = st_tanh(__uint_as_float(acc[c]) + bs[c0 + c]);
-            y[c] = ds * v;
-            dv[c] = ds * us[c0 + c] * (1.f - v * v);
-          }
-          if (hh == 0 && pc > 0) st_mbar_wait(dvp_free, (uint32_t)((pc - 1) & 1));   // the previous panel's MMAs have read it
+        for (int c = 0; c < CW; ++c) {
+          const float v = st_tanh(__uint_as_float(acc[c]) + bs[c0 + c]);
+          y[c] = ds * v;
+          dv[c] = ds * us[c0 + c] * (1.f - v * v);
+        }
+        if (pc > 0) st_mbar_wait(dvp_free, (uint32_t)((pc - 1) & 1));     // the previous panel's MMAs have read it
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            const float x[8] = {dv[8 * c8], dv[8 * c8 + 1], dv[8 * c8 + 2], dv[8 * c8 + 3],
-                                dv[8 * c8 + 4], dv[8 * c8 + 5], dv[8 * c8 + 6], dv[8 * c8 + 7]};
-            st_store8(dv1, dv1 + SB_T16, dv1 + 2 * SB_T16, r, 4 * hh + c8, x);
-          }
-          du_acc[2 * j + hh] += st_col_sums(y, lane);
-          db_acc[2 * j + hh] += st_col_sums(dv, lane);
+        for (int c8 = 0; c8 < CW / 8; ++c8) {
+          const float x[8] = {dv[8 * c8], dv[8 * c8 + 1], dv[8 * c8 + 2], dv[8 * c8 + 3],
+                              dv[8 * c8 + 4], dv[8 * c8 + 5], dv[8 * c8 + 6], dv[8 * c8 + 7]};
+          st_store8(dv1, dv1 + SB_T16, dv1 + 2 * SB_T16, r, sub * (CW / 8) + c8, x);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         st_mbar_arrive(dvp_full);
+        du_acc[j] += st_col_sums<CW>(y, lane);
+        db_acc[j] += st_col_sums<CW>(dv, lane);
       }
-      // ---- dZ = beta dout + dv w^T ----
+      // ---- dZ = beta dout + dv w^T : this thread's 64 / NH columns ----
       st_mbar_wait(dz_full, (uint32_t)(it & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float* zrow = nullptr;
       if (live) zrow = (dz_tab != nullptr) ? dz_tab[r % P] + node * dz_stride : dZ + (row0 + r) * D;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t acc[32];
-        st_tmem_ld32(lane_base + 128u + (uint32_t)(32 * hh), acc);
+      {
+        uint32_t acc[CW];
+        st_tmem_ldN<CW>(lane_base + 128u + (uint32_t)(CW * sub), acc);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (live) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 dd = ldg4(drow + 32 * hh + 4 * c);
-            *reinterpret_cast<float4*>(zrow + 32 * hh + 4 * c) =
+          for (int c = 0; c < CW / 4; ++c) {
+            const float4 dd = ldg4(drow + CW * sub + 4 * c);
+            *reinterpret_cast<float4*>(zrow + CW * sub + 4 * c) =
                 make_float4(fmaf(bt, dd.x, __uint_as_float(acc[4 * c])), fmaf(bt, dd.y, __uint_as_float(acc[4 * c + 1])),
                             fmaf(bt, dd.z, __uint_as_float(acc[4 * c + 2])), fmaf(bt, dd.w, __uint_as_float(acc[4 * c + 3])));
           }
@@ -711,12 +748,13 @@ semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       st_mbar_arrive(dz_free);
-      // ---- every second tile: drain the dw accumulator (rows d = 16 q + lane for lane < 16) ----
+      // ---- every second tile: drain the dw accumulator (rows d = 16 q + lane for lane < 16; 128 / NH columns per thread) ----
       if ((it % SB_CHAIN_TILES) == SB_CHAIN_TILES - 1 || last) {
         st_mbar_wait(dw_full, (uint32_t)((it / SB_CHAIN_TILES) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
+        for (int jj = 0; jj < 4 / NH; ++jj) {
+          const int j = sub * (4 / NH) + jj;
           uint32_t acc[32];
           st_tmem_ld32(lane_base + 192u + (uint32_t)(32 * j), acc);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -734,14 +772,18 @@ semantic_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
         st_mbar_arrive(dw_free);
       }
     }
-    // ---- du / db: the four warps' column sums in a fixed order ----
+    // ---- du / db: the four quarters' column sums in a fixed order ----
+    st_bar_epi<NE>();
+    if (CW == 32 || (lane & 1) == 0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      red[q * 256 + 32 * j + lane] = du_acc[j];
-      red[q * 256 + 128 + 32 * j + lane] = db_acc[j];
+      for (int j = 0; j < 2; ++j) {
+        const int col = 64 * j + CW * sub + (CW == 32 ? lane : (lane >> 1));
+        red[q * 256 + col] = du_acc[j];
+        red[q * 256 + 128 + col] = db_acc[j];
+      }
     }
-    st_bar_epi<128>();
-    {
+    st_bar_epi<NE>();
+    if (threadIdx.x - 64 < 128) {
       const int t = threadIdx.x - 64;     // 0..127 = column a
       const float du = red[0 * 256 + t] + red[1 * 256 + t] + red[2 * 256 + t] + red[3 * 256 + t];
       const float db = red[0 * 256 + 128 + t] + red[1 * 256 + 128 + t] + red[2 * 256 + 128 + t] + red[3 * 256 + 128 + t];
@@ -903,12 +945,21 @@ int han_semantic_bwd_tc(const float* dout, const float* Z, const float* beta, in
   if (rc) return rc;
   rc = st_make_map_bf16(&tmW3, w3, ST_A, ST_A);
   if (rc) return rc;
-  HAN_SMEM_ATTR_ONCE(semantic_bwd_tc_kernel, SB_SMEM_BYTES);
+  HAN_SMEM_ATTR_ONCE(semantic_bwd_tc_kernel<2>, SB_SMEM_BYTES);
+  HAN_SMEM_ATTR_ONCE(semantic_bwd_tc_kernel<4>, SB_SMEM_BYTES);
   const int64_t n_tiles = ceil_div64(n, ST_BM / P);
   const unsigned grid = (unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
   cudaMemsetAsync(part, 0, (size_t)grid * ((size_t)ST_D * ST_A + 2 * ST_A) * sizeof(float), st);   // the dw drains accumulate
-  semantic_bwd_tc_kernel<<<grid, 192, SB_SMEM_BYTES, st>>>(tmZ, tmW1, tmW2, tmW3, n, P, dout, beta, b, u, mode, dsbar, dZ,
-                                                         dz_tab, dz_stride, part);
+  static const int nh = []() {
+    const char* e = getenv("HAN_SEM_BWD_NH");        // epilogue threads per row: 4 (default) or 2
+    return (e && e[0] == '2') ? 2 : 4;
+  }();
+  if (nh == 2)
+    semantic_bwd_tc_kernel<2><<<grid, 64 + 256, SB_SMEM_BYTES, st>>>(tmZ, tmW1, tmW2, tmW3, n, P, dout, beta, b, u, mode, dsbar,
+                                                                   dZ, dz_tab, dz_stride, part);
+  else
+    semantic_bwd_tc_kernel<4><<<grid, 64 + 512, SB_SMEM_BYTES, st>>>(tmZ, tmW1, tmW2, tmW3, n, P, dout, beta, b, u, mode, dsbar,
+                                                                   dZ, dz_tab, dz_stride, part);
   const int64_t cols = (int64_t)ST_D * ST_A + 2 * ST_A;
   st_bwd_reduce_kernel<<<(unsigned)ceil_div64(cols, 128), 128, 0, st>>>(part, (int)grid, dw, db, du);
   return check_launch(__func__);
