@@ -141,6 +141,11 @@ class BaseGAttN:
     @staticmethod
     def masked_softmax_cross_entropy(logits, labels, mask):
         """models/base_gattn.py:41-48.  logits (N,C); labels one-hot (N,C); mask (N,)."""
+        if logits.is_cuda and logits.dtype == torch.float32:
+            # one kernel: loss partials + d(loss)/d(logits); mean(loss * mask / mean(mask)) == sum(loss * mask) / sum(mask)
+            from . import ops
+            mask = mask.to(torch.float32)
+            return ops.masked_ce(logits, labels, mask, mask.sum())
         labels = labels.to(logits.dtype)
         loss = -(labels * torch.log_softmax(logits, dim=-1)).sum(-1)     # :43-44
         mask = mask.to(logits.dtype)                                      # :45

@@ -405,9 +405,13 @@ class RowShard:
         1/W of the L2 term, so that the all-reduced gradients equal the single-process ones."""
         mask = mask.to(logits.dtype)
         mask_total = self.all_reduce_sum(mask.sum().reshape(1))          # stays on the device: no host sync
-        labels = labels.to(logits.dtype)
-        xent = -(labels * torch.log_softmax(logits, dim=-1)).sum(-1)
-        ce = ((xent * mask).sum() / mask_total).squeeze(0)
+        if logits.is_cuda and logits.dtype == torch.float32:
+            from . import ops
+            ce = ops.masked_ce(logits, labels, mask, mask_total)
+        else:
+            labels = labels.to(logits.dtype)
+            xent = -(labels * torch.log_softmax(logits, dim=-1)).sum(-1)
+            ce = ((xent * mask).sum() / mask_total).squeeze(0)
         return ce if train_op is None else ce + train_op.l2_loss() / self.world
 
     def all_reduce_flat(self, flat: torch.Tensor) -> None:

@@ -223,8 +223,10 @@ class HeteGAT_multi(BaseGAttN):
             mode=semantic_mode, dist=tile if tile is not None else dist)
 
         out = []
+        own = ops.dense_supported(final_embed.shape[1], params.Wc[0].shape[1])   # D <= 64, C <= 384: own kernels
         for i in range(n_heads[-1]):                                        # :66-68
-            out.append(torch.addmm(params.bc[i], final_embed, params.Wc[i]))
+            out.append(ops.dense(final_embed, params.Wc[i], params.bc[i]) if own
+                       else torch.addmm(params.bc[i], final_embed, params.Wc[i]))
         logits = out[0] if len(out) == 1 else torch.stack(out).sum(0) / n_heads[-1]   # :72
         logits = logits.unsqueeze(0)                                        # :76
         if return_coef:

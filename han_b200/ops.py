@@ -525,6 +525,81 @@ def semantic_attention(Z, w, b, u, mode: str = "reference", dist=None):
     return SemanticAttentionFn.apply(Z, w, b, u, m, dist)
 
 
+class DenseFn(torch.autograd.Function):
+    """``tf.layers.dense(x, units)`` (models/gat.py:66-68): y = x W + b, exact FP32, own kernels (dense_ce.cu)."""
+
+    @staticmethod
+    def forward(ctx, X, W, b):
+        _lib.require_cuda(X, W, b)
+        X, W, b = X.contiguous(), W.contiguous(), b.contiguous()
+        n, D = X.shape
+        C = W.shape[1]
+        Y = _empty((n, C), X.device)
+        with torch.cuda.device(X.device):
+            call("han_dense_fwd", ptr(X), n, D, X.stride(0), ptr(W), C, ptr(b), ptr(Y), stream_ptr())
+        ctx.save_for_backward(X, W)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        X, W = ctx.saved_tensors
+        n, D = X.shape
+        C = W.shape[1]
+        dev = X.device
+        dY = dY.contiguous()
+        NB = query("han_dense_blocks")
+        with torch.cuda.device(dev):
+            dX = _empty((n, D), dev) if ctx.needs_input_grad[0] else None
+            part = _empty((NB, D * C + C), dev)
+            call("han_dense_bwd", ptr(X), n, D, X.stride(0), ptr(W), C, ptr(dY), None, ptr(dX), ptr(part), stream_ptr())
+            flat = _empty((D * C + C,), dev)
+            call("han_reduce_partials", ptr(part), NB, D * C + C, ptr(flat), stream_ptr())
+        return dX, flat[:D * C].view(D, C), flat[D * C:]
+
+
+def dense_supported(D: int, C: int) -> bool:
+    return D <= 64 and C <= 384
+
+
+def dense(X, W, b):
+    return DenseFn.apply(X, W, b)
+
+
+class MaskedCEFn(torch.autograd.Function):
+    """``masked_softmax_cross_entropy`` (models/base_gattn.py:41-48): sum_i mask_i xent_i / mask_total with
+    xent = -sum_c labels log_softmax(logits); one kernel computes the loss partials AND d(loss)/d(logits), the
+    backward only scales by the upstream scalar.  ``mask_total`` is a device scalar (the global mask sum)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, mask, mask_total):
+        _lib.require_cuda(logits, labels, mask, mask_total)
+        logits = logits.contiguous()
+        labels = labels.to(torch.float32).contiguous()
+        mask = mask.to(torch.float32).contiguous()
+        mask_total = mask_total.to(torch.float32).reshape(1).contiguous()
+        n, C = logits.shape
+        dev = logits.device
+        NB = query("han_dense_blocks")
+        with torch.cuda.device(dev):
+            part = _empty((NB, 1), dev)
+            dlogits = _empty((n, C), dev) if ctx.needs_input_grad[0] else None
+            call("han_masked_ce", ptr(logits), ptr(labels), ptr(mask), ptr(mask_total), n, C, ptr(part), ptr(dlogits),
+                 stream_ptr())
+            loss = _empty((1,), dev)
+            call("han_reduce_partials", ptr(part), NB, 1, ptr(loss), stream_ptr())
+        ctx.save_for_backward(dlogits)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g, None, None, None
+
+
+def masked_ce(logits, labels, mask, mask_total):
+    return MaskedCEFn.apply(logits, labels, mask, mask_total)
+
+
 def activation_code(activation) -> int:
     """Maps the reference's ``activation`` argument (tf.nn.elu or ``lambda x: x``,
     models/gat.py:10,28) to the kernel's epilogue selector."""

@@ -325,10 +325,14 @@ class TileShard:
         """This rank's share of masked CE over the GLOBAL mask (models/base_gattn.py:41-48) plus 1/W of the L2
         term; logits / labels / mask are this rank's SEMANTIC rows."""
         mask = mask.to(logits.dtype)
-        mask_total = self.all_reduce_sum(mask.sum().reshape(1))
-        labels = labels.to(logits.dtype)
-        xent = -(labels * torch.log_softmax(logits, dim=-1)).sum(-1)
-        ce = ((xent * mask).sum() / mask_total).squeeze(0)
+        mask_total = self.all_reduce_sum(mask.sum().reshape(1))          # stays on the device: no host sync
+        if logits.is_cuda and logits.dtype == torch.float32:
+            from . import ops
+            ce = ops.masked_ce(logits, labels, mask, mask_total)
+        else:
+            labels = labels.to(logits.dtype)
+            xent = -(labels * torch.log_softmax(logits, dim=-1)).sum(-1)
+            ce = ((xent * mask).sum() / mask_total).squeeze(0)
         return ce if train_op is None else ce + train_op.l2_loss() / self.world
 
     def all_reduce_grads(self, module: torch.nn.Module) -> None:
