@@ -206,18 +206,18 @@ def hb_bias(mask_rows: np.ndarray) -> np.ndarray:
 
 
 def algorithmic_bytes(name, wl):
-    """ALGORITHMIC bytes of one launch set (all P meta-paths) of the two gather kernels (DESIGN.md):
-       han_attn_fwd    : (4 + 4*TS) B/edge + (8 + 4K + 4D + 4D + 8K) B/row
-       han_attn_bwd_src: (4 + 4 + 4*RS + 4K) B/edge + (8 + 4*TS + 4D + 4K) B/source row"""
+    """ALGORITHMIC bytes of one launch set (all P meta-paths) of the two gather kernels (DESIGN.md section 4):
+       han_attn_fwd_chunked    : (4 + 4*TS) B/edge + (8 + 4K f1 + 4K lse + 4K c + 3 * 4D [out, V, V']) B/row
+       han_attn_bwd_src_chunked: (4 + 4*RS) B/edge + (8 + 4*TS + 4D + 4K) B/source row"""
     K, D = K_HEADS, K_HEADS * HID
     TS, RS = 72, 88
     E = sum(g.nnz for g in wl["graphs"])
     n = wl["hi"] - wl["lo"]
     P = len(wl["graphs"])
-    if name in ("han_attn_fwd", "han_attn_fwd_chunked", "han_attn_fwd_chunked_split"):
-        return (4 + 4 * TS) * E + (8 + 4 * K + 8 * D + 4 * K) * n * P
-    if name in ("han_attn_bwd_src", "han_attn_bwd_src_chunked", "han_attn_bwd_src_chunked_split"):
-        return (8 + 4 * RS + 4 * K) * E + (8 + 4 * TS + 4 * D + 4 * K) * n * P
+    if name in ("han_attn_fwd_chunked", "han_attn_fwd_chunked_split"):
+        return (4 + 4 * TS) * E + (8 + 12 * K + 12 * D) * n * P
+    if name in ("han_attn_bwd_src_chunked", "han_attn_bwd_src_chunked_split"):
+        return (4 + 4 * RS) * E + (8 + 4 * TS + 4 * D + 4 * K) * n * P
     return None
 
 

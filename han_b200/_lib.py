@@ -47,18 +47,17 @@ _SIGNATURES = {
     "han_csr_chunk_edges": (c_int64, [I64]),
     "han_csr_num_chunks": (c_int64, [I64]),
     "han_csr_chunk_rows": (c_int, [P, I64, I64, P, P]),
-    "han_attn_fwd_chunked": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, I64, I64, P, FL, I, I64, P]),
-    "han_attn_bwd_src_chunked": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P, P, P, FL, I, I64, P]),
-    "han_attn_fwd_chunked_split": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, I64, I64, P, FL, I, I64,
-                                           P, P, P, P, I, P]),
-    "han_attn_bwd_src_chunked_split": (c_int, [P, P, P, P, I64, I64, P, P, I, I, P, P, P, P, P, P, FL, I, I64,
-                                               P, P, P, P, I, P]),
+    "han_attn_fwd_chunked": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, I64, I64, P, P, P, FL, I,
+                                     I64, P]),
+    "han_attn_bwd_src_chunked": (c_int, [P, P, P, I64, I64, P, P, I, I, P, P, P, P, FL, I, I64, P]),
+    "han_attn_fwd_chunked_split": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, I64, I64, P, P, P, FL, I,
+                                           I64, P, P, P, P, I, P]),
+    "han_attn_bwd_src_chunked_split": (c_int, [P, P, P, I64, I64, P, P, I, I, P, P, P, P, FL, I, I64, P, P, P, P, I, P]),
     "han_project_fwd_drop": (c_int, [P, I64, I64, I64, P, I64, I, I, I, P, P, P, P, P, P, P, P, FL, I, I64, P]),
     "han_project_bwd_drop_workspace_bytes": (SZ, [I64, I64, I]),
     "han_project_bwd_drop": (c_int, [P, I64, I64, I64, P, I, I, I, P, I64, P, SZ, P, FL, I, I64, P]),
     "han_reduce_blocks": (c_int, []),
-    "han_attn_bwd_prep": (c_int, [P, I64, P, I64, P, P, I64, I, I, I, P, P, I64, P]),
-    "han_attn_bwd_dst": (c_int, [P, I64, I64, P, I, P, P]),
+    "han_attn_bwd_prep": (c_int, [P, I64, P, I64, P, P, I64, I, I, I, P, P, I64, P, P, P, P]),
     "han_attn_bwd_finish": (c_int, [P, I64, I, I, P, P, P, P, P, P, P, P, FL, I, I64, P]),
     "han_reduce_partials": (c_int, [P, I, I64, P, P]),
     "han_semantic_shape_supported": (c_int, [I, I]),
@@ -123,7 +122,7 @@ KERNELS_PER_CALL = {
     "han_dense_row_counts": 1, "han_scan_counts": 3, "han_dense_fill_indices": 1, "han_csr_transpose": 7,
     "han_csr_sort_rows": 2, "han_project_fwd": None, "han_project_bwd": 2,
     "han_attn_coefs": 1, "han_attn_bwd_prep": 1,
-    "han_csr_chunk_rows": 1, "han_attn_fwd_chunked": 1, "han_attn_bwd_src_chunked": 1, "han_attn_bwd_dst": 1,
+    "han_csr_chunk_rows": 1, "han_attn_fwd_chunked": 1, "han_attn_bwd_src_chunked": 1,
     "han_attn_bwd_finish": 1, "han_reduce_partials": 1, "han_semantic_fwd": 1, "han_semantic_combine": 1,
     "han_semantic_bwd": 2, "han_adam_l2_step": 1, "han_dense_fwd": 1, "han_dense_bwd": 1, "han_masked_ce": 1, "han_project_dx": 1,
     "han_attn_fwd_chunked_split": 2, "han_attn_bwd_src_chunked_split": 2, "han_semantic_fwd_tc": 2, "han_semantic_bwd_tc": 3,

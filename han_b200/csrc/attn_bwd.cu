@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const float* __restrict__ dout, int64_t dout_stride, const float* __restrict__ out,
                      int64_t out_stride, const float* __restrict__ vsave, float* __restrict__ R,
                      int64_t n_dst, int act, float* __restrict__ dbias_partial, float* __restrict__ Rmc,
-                     int64_t r_row0) {
+                     int64_t r_row0, const float* __restrict__ vsave2, const float* __restrict__ csave,
+                     float* __restrict__ df1) {
   constexpr int D = K * H;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
   // thread = (row, head); a block covers 256/K consecutive rows; grid-stride over row tiles
@@ -53,7 +54,7 @@ attn_bwd_prep_kernel(const float* __restrict__ dout, int64_t dout_stride, const 
   for (int64_t r0 = (int64_t)blockIdx.x * ROWS; r0 < n_dst; r0 += (int64_t)gridDim.x * ROWS) {
     const int64_t row = r0 + rsub;
     if (row < n_dst) {
-      float delta = 0.f;
+      float delta = 0.f, dv2 = 0.f;
 #pragma unroll
       for (int q = 0; q < H / 4; ++q) {
         float4 g = ldg4_stream(dout + row * dout_stride + head * H + 4 * q);
@@ -67,12 +68,18 @@ attn_bwd_prep_kernel(const float* __restrict__ dout, int64_t dout_stride, const 
         }
         const float4 v = ldg4_stream(vsave + row * D + head * H + 4 * q);
         delta += g.x * v.x + g.y * v.y + g.z * v.z + g.w * v.w;
+        if (df1 != nullptr) {
+          const float4 v2 = ldg4_stream(vsave2 + row * D + head * H + 4 * q);
+          dv2 += g.x * v2.x + g.y * v2.y + g.z * v2.z + g.w * v2.w;
+        }
         if (Rmc != nullptr)   // sharded: the record goes to every rank's copy with one multicast store
           mc_store4(Rmc + (r_row0 + row) * RS + head * H + 4 * q, g);
         else
           *reinterpret_cast<float4*>(R + row * RS + head * H + 4 * q) = g;
         colsum[4 * q] += g.x; colsum[4 * q + 1] += g.y; colsum[4 * q + 2] += g.z; colsum[4 * q + 3] += g.w;
       }
+      // df1_i = sum_j dl_ij = <dV_i, V'_i> - delta_i c_i : row-local thanks to the forward's second aggregate
+      if (df1 != nullptr) df1[row * K + head] = dv2 - delta * csave[row * K + head];
       if (Rmc != nullptr) {
         float* rp = Rmc + (r_row0 + row) * RS + D + head;
         mc_store1(rp, R[row * RS + D + head]);              // f1  (written by the projection, local)
@@ -93,51 +100,6 @@ attn_bwd_prep_kernel(const float* __restrict__ dout, int64_t dout_stride, const 
     for (int r = 0; r < ROWS; ++r) s += red[r * D + c];
     dbias_partial[(int64_t)blockIdx.x * D + c] = s;
   }
-}
-
-// ---- by-destination segmented sum of dl ---------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(256)
-attn_bwd_dst_kernel(const int64_t* __restrict__ indptr, int64_t n_dst, const float* __restrict__ dl_edge,
-                    float* __restrict__ df1) {
-  constexpr int SLOTS = 32 / K;
-  const int lane = threadIdx.x & 31;
-  const int head = lane % K, slot = lane / K;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n_dst) return;
-  const int64_t start = indptr[row], end = indptr[row + 1];
-  float s0 = 0.f, s1 = 0.f;
-  int64_t e = start + slot;
-  for (; e + SLOTS < end; e += 2 * SLOTS) {  // 32 lanes read 128 contiguous bytes, 2 in flight
-    s0 += __ldg(dl_edge + e * K + head);
-    s1 += __ldg(dl_edge + (e + SLOTS) * K + head);
-  }
-  if (e < end) s0 += __ldg(dl_edge + e * K + head);
-  float s = s0 + s1;
-#pragma unroll
-  for (int off = K; off < 32; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  if (slot == 0) df1[row * K + head] = s;
-}
-
-// short-row variant (sharded runs: ~degree/world edges per row): a K-lane group owns a row, 32/K rows per warp
-template <int K>
-__global__ void __launch_bounds__(256)
-attn_bwd_dst_short_kernel(const int64_t* __restrict__ indptr, int64_t n_dst, const float* __restrict__ dl_edge,
-                          float* __restrict__ df1) {
-  constexpr int SLOTS = 32 / K;
-  const int lane = threadIdx.x & 31;
-  const int head = lane % K, slot = lane / K;
-  const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * SLOTS + slot;
-  if (row >= n_dst) return;
-  const int64_t start = indptr[row], end = indptr[row + 1];
-  float s0 = 0.f, s1 = 0.f;
-  int64_t e = start;
-  for (; e + 1 < end; e += 2) {
-    s0 += __ldg(dl_edge + e * K + head);
-    s1 += __ldg(dl_edge + (e + 1) * K + head);
-  }
-  if (e < end) s0 += __ldg(dl_edge + e * K + head);
-  df1[row * K + head] = s0 + s1;
 }
 
 // ---- finish: row-local; dS_tot = dS_agg + df1 a1^T + df2 a2^T and parameter-gradient partials ----
@@ -270,41 +232,23 @@ int han_multicast_copy(const float* src, float* dst_mc, int64_t n_floats, han_st
 
 int han_attn_bwd_prep(const float* dout, int64_t dout_stride, const float* out, int64_t out_stride,
                       const float* vsave, float* R, int64_t n_dst, int K, int H, int act,
-                      float* dbias_partial, float* R_mc, int64_t r_row0, han_stream_t stream) {
+                      float* dbias_partial, float* R_mc, int64_t r_row0, const float* vsave2, const float* csave,
+                      float* df1, han_stream_t stream) {
   HAN_REQUIRE(dout && out && vsave && R && dbias_partial, "null pointer");
   HAN_REQUIRE(n_dst > 0 && r_row0 >= 0, "n_dst > 0 required");
   HAN_REQUIRE(dout_stride % 4 == 0 && out_stride % 4 == 0, "strides must be multiples of 4 floats");
   HAN_REQUIRE((uintptr_t)R_mc % 16 == 0, "multicast records must be 16-byte aligned");
+  HAN_REQUIRE(!df1 || (vsave2 && csave && (uintptr_t)vsave2 % 16 == 0), "df1 needs vsave2 and csave");
 #define X(k, h)                                                                                        \
   if (K == k && H == h) {                                                                              \
     attn_bwd_prep_kernel<k, h><<<kReduceBlocks, 256, 0, as_stream(stream)>>>(                          \
-        dout, dout_stride, out, out_stride, vsave, R, n_dst, act, dbias_partial, R_mc, r_row0);        \
+        dout, dout_stride, out, out_stride, vsave, R, n_dst, act, dbias_partial, R_mc, r_row0, vsave2,   \
+        csave, df1);                                                                                   \
     return check_launch(__func__);                                                                     \
   }
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H)");
-}
-
-int han_attn_bwd_dst(const int64_t* indptr, int64_t n_dst, int64_t nnz, const float* dl_edge, int K, float* df1,
-                     han_stream_t stream) {
-  HAN_REQUIRE(indptr && dl_edge && df1, "null pointer");
-  HAN_REQUIRE(n_dst > 0 && nnz >= 0, "n_dst > 0 required");
-  cudaStream_t st = as_stream(stream);
-  const bool short_rows = nnz < 16 * n_dst;   // mean degree < 16: one K-lane group per row
-#define HAN_DST(k)                                                                                       \
-  case k:                                                                                                \
-    if (short_rows)                                                                                      \
-      attn_bwd_dst_short_kernel<k><<<(unsigned)ceil_div64(n_dst, 8 * (32 / k)), 256, 0, st>>>(indptr, n_dst, dl_edge, df1); \
-    else                                                                                                 \
-      attn_bwd_dst_kernel<k><<<(unsigned)ceil_div64(n_dst, 8), 256, 0, st>>>(indptr, n_dst, dl_edge, df1); \
-    break;
-  switch (K) {
-    HAN_DST(1) HAN_DST(2) HAN_DST(4) HAN_DST(8) HAN_DST(16)
-    default: return fail_arg(__func__, "unsupported K");
-  }
-#undef HAN_DST
-  return check_launch(__func__);
 }
 
 int han_attn_bwd_finish(const float* T, int64_t n, int K, int H, const float* a1, const float* a2,

@@ -77,7 +77,8 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
                         int act, float* __restrict__ out, int64_t out_stride, float* __restrict__ vsave,
                         const float* __restrict__ colmean, const float* __restrict__ ew,
                         const float* __restrict__ resid, int64_t resid_stride, float* const* __restrict__ out2_tab,
-                        int64_t out2_block_rows, int64_t out2_stride, DropCoef dc, SplitRows sp) {
+                        int64_t out2_block_rows, int64_t out2_stride, float* __restrict__ vsave2,
+                        float* __restrict__ csave, DropCoef dc, SplitRows sp) {
   constexpr int D = K * H;
   constexpr int TS = ((D + K + 3) / 4) * 4;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
@@ -145,6 +146,14 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
   float acc[H];
 #pragma unroll
   for (int h = 0; h < H; ++h) acc[h] = 0.f;
+  // Second aggregate, kept for the backward: with k_ij = leaky'(l_ij) (* w_ij for sp_attn_head),
+  //   V'_i = sum_j alpha~_ij k_ij S_j   and   c_i = sum_j alpha_ij k_ij
+  // make df1_i = sum_j dl_ij = <dV_i, V'_i> - delta_i c_i a ROW-LOCAL quantity: the backward needs neither a
+  // per-edge dl array nor a by-destination pass (nor, sharded, a reduce-scatter).
+  const bool train = vsave2 != nullptr;
+  float acc2[H], cacc = 0.f;
+#pragma unroll
+  for (int h = 0; h < H; ++h) acc2[h] = 0.f;
 
   auto finalize_row = [&]() {
     // merge the SLOTS partial softmax states of each head
@@ -161,16 +170,29 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
         const float ao = __shfl_xor_sync(0xffffffffu, acc[h], off);
         acc[h] = acc[h] * s0 + ao * s1;
       }
+      if (train) {
+        const float co = __shfl_xor_sync(0xffffffffu, cacc, off);
+        cacc = cacc * s0 + co * s1;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float ao = __shfl_xor_sync(0xffffffffu, acc2[h], off);
+          acc2[h] = acc2[h] * s0 + ao * s1;
+        }
+      }
       m = mn;
     }
     if constexpr (SPLIT) {
-      if (pslot >= 0) {   // a segment of a cut row: leave (max, normaliser, un-normalised aggregate) for the merge
+      if (pslot >= 0) {   // a segment of a cut row: leave (max, normaliser, un-normalised aggregates) for the merge
         if (slot == 0) {
-          float* pp = sp.part + ((int64_t)pslot * K + head) * (H + 2);
+          float* pp = sp.part + ((int64_t)pslot * K + head) * (2 * H + 3);
           pp[0] = m;
           pp[1] = l;
+          pp[2] = cacc;
 #pragma unroll
-          for (int h = 0; h < H; ++h) pp[2 + h] = acc[h];
+          for (int h = 0; h < H; ++h) {
+            pp[3 + h] = acc[h];
+            pp[3 + H + h] = acc2[h];
+          }
         }
         return;
       }
@@ -182,6 +204,14 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
         lse = m + __logf(l);
 #pragma unroll
         for (int h = 0; h < H; ++h) acc[h] *= rinv;
+        if (train) {
+          csave[(int64_t)rr * K + head] = cacc * rinv;
+          float* v2 = vsave2 + (int64_t)rr * D + head * H;
+#pragma unroll
+          for (int qv = 0; qv < HV; ++qv)
+            *reinterpret_cast<float4*>(v2 + 4 * qv) = make_float4(acc2[4 * qv] * rinv, acc2[4 * qv + 1] * rinv,
+                                                                  acc2[4 * qv + 2] * rinv, acc2[4 * qv + 3] * rinv);
+        }
       } else {
         // row without any edge: dense path = uniform 1/N over ALL nodes
         lse = 0.f;
@@ -234,8 +264,12 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
     }
     m = -INFINITY;
     l = 0.f;
+    cacc = 0.f;
 #pragma unroll
-    for (int h = 0; h < H; ++h) acc[h] = 0.f;
+    for (int h = 0; h < H; ++h) {
+      acc[h] = 0.f;
+      acc2[h] = 0.f;
+    }
   };
 
   int64_t pos = e_lo;
@@ -255,7 +289,12 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
         if (ei < seg_end) {
           const float* rp = buf + (int)(ei - bs) * TS;
           float lg = f1v + rp[D + head];
-          if (ew) lg *= wbuf[(int)(ei - bs)];
+          float kfac = 1.f;                    // d l_ij / d (f1_i + f2_j)
+          if (ew) {
+            kfac = wbuf[(int)(ei - bs)];
+            lg *= kfac;
+          }
+          if (lg <= 0.f) kfac *= kLeakySlope;  // times leaky'(l_ij)
           const float e = leaky(lg);
           const float mnew = fmaxf(m, e);
           const float sc = __expf(m - mnew);   // m = -inf -> 0
@@ -273,7 +312,15 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
             acc[4 * qv + 1] = fmaf(acc[4 * qv + 1], sc, pk * v.y);
             acc[4 * qv + 2] = fmaf(acc[4 * qv + 2], sc, pk * v.z);
             acc[4 * qv + 3] = fmaf(acc[4 * qv + 3], sc, pk * v.w);
+            if (train) {
+              const float pk2 = pk * kfac;
+              acc2[4 * qv + 0] = fmaf(acc2[4 * qv + 0], sc, pk2 * v.x);
+              acc2[4 * qv + 1] = fmaf(acc2[4 * qv + 1], sc, pk2 * v.y);
+              acc2[4 * qv + 2] = fmaf(acc2[4 * qv + 2], sc, pk2 * v.z);
+              acc2[4 * qv + 3] = fmaf(acc2[4 * qv + 3], sc, pk2 * v.w);
+            }
           }
+          if (train) cacc = fmaf(cacc, sc, p * kfac);
           m = mnew;
         }
       }
@@ -295,13 +342,12 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
 // -------------------------------------------------------------------------------------------------
 // backward, by source (transposed structure)
 // -------------------------------------------------------------------------------------------------
-template <int K, int H, int STAGES, bool SPLIT, bool RED>
+template <int K, int H, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(kStreamWarps * 32, 3)
 attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t* __restrict__ t_indices,
-                            const int32_t* __restrict__ perm, const int32_t* __restrict__ chunk_rows,
+                            const int32_t* __restrict__ chunk_rows,
                             int64_t n_chunks, const float* __restrict__ Tsrc, const float* __restrict__ R,
                             float* __restrict__ dS_agg, float* __restrict__ df2,
-                            float* __restrict__ dl_edge, float* __restrict__ df1_red,
                             const float* __restrict__ ew_t, DropCoef dc, SplitRows sp) {
   constexpr int D = K * H;
   constexpr int TS = ((D + K + 3) / 4) * 4;
@@ -315,8 +361,7 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int head = lane % K, slot = lane / K;
   float* ring = smem + (size_t)w * STAGES * kBatch * RS;
-  int* perm_s = reinterpret_cast<int*>(smem + (size_t)kStreamWarps * STAGES * kBatch * RS) + w * STAGES * kBatch;
-  int* row_s = perm_s + kStreamWarps * STAGES * kBatch;
+  int* row_s = reinterpret_cast<int*>(smem + (size_t)kStreamWarps * STAGES * kBatch * RS) + w * STAGES * kBatch;
   // edge weights in transposed-edge order (sp_attn_head); region present only when ew_t != nullptr
   float* w_s = reinterpret_cast<float*>(row_s - w * STAGES * kBatch + kStreamWarps * STAGES * kBatch) + w * STAGES * kBatch;
   const uint32_t cseed = dc.thr ? stream_seed(*dc.seed_ptr, 3u, dc.metapath, (uint32_t)head) : 0u;
@@ -329,11 +374,10 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
   const int nb = (int)((e_hi - e_lo + kBatch - 1) / kBatch);
 
   int q = 0;
-  int row_pref = 0, perm_pref = 0;
+  int row_pref = 0;
   float w_pref = 1.f;
   if (lane < kBatch && e_lo + lane < e_hi) {
     row_pref = ldg_stream_i32(t_indices + e_lo + lane);
-    perm_pref = ldg_stream_i32(perm + e_lo + lane);
     if (ew_t) w_pref = __ldg(ew_t + e_lo + lane);
   }
   auto issue = [&]() {
@@ -350,14 +394,12 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
         if (c < TOT && rec < cnt) cp_async16(dst + rec * RS + off * 4, R + (int64_t)i_row * RS + off * 4);
       }
       if (lane < kBatch) {
-        perm_s[st * kBatch + lane] = perm_pref;
         row_s[st * kBatch + lane] = row_pref;
         if (ew_t) w_s[st * kBatch + lane] = w_pref;
       }
       const int64_t nbs = bs + kBatch;
       if (lane < kBatch && nbs + lane < e_hi) {
         row_pref = ldg_stream_i32(t_indices + nbs + lane);
-        perm_pref = ldg_stream_i32(perm + nbs + lane);
         if (ew_t) w_pref = __ldg(ew_t + nbs + lane);
       }
     }
@@ -440,7 +482,6 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
     __syncwarp();
     const int st = b % STAGES;
     const float* buf = ring + (size_t)st * kBatch * RS;
-    const int* pbuf = perm_s + st * kBatch;
     const int* rbuf = row_s + st * kBatch;
     const float* wbuf = w_s + st * kBatch;
     const int64_t bs = e_lo + (int64_t)b * kBatch;
@@ -449,9 +490,6 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
       const int64_t seg_end = min(row_end, be);
       for (int64_t g = pos; g < seg_end; g += SLOTS) {
         const int64_t ei = g + slot;
-        float dl = 0.f;
-        int drow = 0;
-        (void)drow;
         if (ei < seg_end) {
           const int rec = (int)(ei - bs);
           const float* rp = buf + rec * RS;
@@ -476,27 +514,8 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
             acc[4 * qv + 2] = fmaf(am, g4.z, acc[4 * qv + 2]);
             acc[4 * qv + 3] = fmaf(am, g4.w, acc[4 * qv + 3]);
           }
-          dl = a * (da * mk - rp[D + 2 * K + head]) * (lg > 0.f ? 1.f : kLeakySlope) * wt;
-          df2acc += dl;
-          if constexpr (RED) drow = rbuf[rec];
-          else dl_edge[(int64_t)pbuf[rec] * K + head] = dl;
-        }
-        if constexpr (RED) {
-          // df1[dst] += dl without the per-edge round trip through memory: one 16-byte vector reduction per
-          // 4 heads, resolved in L2 (the whole df1 array is N*K*4 bytes).  Summation order is not fixed.
-          constexpr int VEC = K >= 4 ? 4 : K;
-          const float d1 = __shfl_down_sync(0xffffffffu, dl, 1);
-          const float d2 = __shfl_down_sync(0xffffffffu, dl, 2);
-          const float d3 = __shfl_down_sync(0xffffffffu, dl, 3);
-          if (ei < seg_end && (head % VEC) == 0) {
-            float* dp = df1_red + (int64_t)drow * K + head;
-            if (VEC == 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dp), "f"(dl), "f"(d1), "f"(d2), "f"(d3) : "memory");
-            else if (VEC == 2)
-              asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(dp), "f"(dl), "f"(d1) : "memory");
-            else
-              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dp), "f"(dl) : "memory");
-          }
+          // dl_ij feeds df2_j only: df1_i = sum_j dl_ij is row-local since the forward kept V' and c (prep kernel)
+          df2acc += a * (da * mk - rp[D + 2 * K + head]) * (lg > 0.f ? 1.f : kLeakySlope) * wt;
         }
       }
       pos = seg_end;
@@ -521,7 +540,8 @@ attn_fwd_merge_kernel(const int32_t* __restrict__ heavy_rows, const int32_t* __r
                       const float* __restrict__ part, float* __restrict__ R, const float* __restrict__ bias, int act,
                       float* __restrict__ out, int64_t out_stride, float* __restrict__ vsave,
                       const float* __restrict__ resid, int64_t resid_stride, float* const* __restrict__ out2_tab,
-                      int64_t out2_block_rows, int64_t out2_stride) {
+                      int64_t out2_block_rows, int64_t out2_stride, float* __restrict__ vsave2,
+                      float* __restrict__ csave) {
   constexpr int D = K * H;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
   constexpr int SLOTS = 32 / K;
@@ -530,37 +550,56 @@ attn_fwd_merge_kernel(const int32_t* __restrict__ heavy_rows, const int32_t* __r
   const int lane = threadIdx.x & 31, head = lane % K, slot = lane / K;
   const int rr = heavy_rows[hw];
   const int s_lo = heavy_ptr[hw], s_hi = heavy_ptr[hw + 1];
-  float m = -INFINITY, l = 0.f, acc[H];
+  float m = -INFINITY, l = 0.f, cc = 0.f, acc[H], acc2[H];
 #pragma unroll
-  for (int h = 0; h < H; ++h) acc[h] = 0.f;
-  auto combine = [&](float mo, float lo, const float* ao) {
+  for (int h = 0; h < H; ++h) {
+    acc[h] = 0.f;
+    acc2[h] = 0.f;
+  }
+  auto combine = [&](float mo, float lo, float co, const float* ao, const float* a2o) {
     const float mn = fmaxf(m, mo);
     const float s0 = (m == -INFINITY) ? 0.f : __expf(m - mn);
     const float s1 = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
     l = l * s0 + lo * s1;
+    cc = cc * s0 + co * s1;
 #pragma unroll
-    for (int h = 0; h < H; ++h) acc[h] = acc[h] * s0 + ao[h] * s1;
+    for (int h = 0; h < H; ++h) {
+      acc[h] = acc[h] * s0 + ao[h] * s1;
+      acc2[h] = acc2[h] * s0 + a2o[h] * s1;
+    }
     m = mn;
   };
   for (int sgm = s_lo + slot; sgm < s_hi; sgm += SLOTS) {
-    const float* pp = part + ((int64_t)sgm * K + head) * (H + 2);
-    float ao[H];
+    const float* pp = part + ((int64_t)sgm * K + head) * (2 * H + 3);
+    float ao[H], a2o[H];
 #pragma unroll
-    for (int h = 0; h < H; ++h) ao[h] = pp[2 + h];
-    combine(pp[0], pp[1], ao);
+    for (int h = 0; h < H; ++h) {
+      ao[h] = pp[3 + h];
+      a2o[h] = pp[3 + H + h];
+    }
+    combine(pp[0], pp[1], pp[2], ao, a2o);
   }
 #pragma unroll
   for (int off = K; off < 32; off <<= 1) {
     const float mo = __shfl_xor_sync(0xffffffffu, m, off);
     const float lo = __shfl_xor_sync(0xffffffffu, l, off);
-    float ao[H];
+    const float co = __shfl_xor_sync(0xffffffffu, cc, off);
+    float ao[H], a2o[H];
 #pragma unroll
-    for (int h = 0; h < H; ++h) ao[h] = __shfl_xor_sync(0xffffffffu, acc[h], off);
-    combine(mo, lo, ao);
+    for (int h = 0; h < H; ++h) {
+      ao[h] = __shfl_xor_sync(0xffffffffu, acc[h], off);
+      a2o[h] = __shfl_xor_sync(0xffffffffu, acc2[h], off);
+    }
+    combine(mo, lo, co, ao, a2o);
   }
   if (slot == 0) {
     const float rinv = 1.f / l;
     R[(int64_t)rr * RS + D + K + head] = m + __logf(l);
+    if (vsave2 != nullptr) {
+      csave[(int64_t)rr * K + head] = cc * rinv;
+#pragma unroll
+      for (int h = 0; h < H; ++h) vsave2[(int64_t)rr * D + head * H + h] = acc2[h] * rinv;
+    }
     float* vp = vsave + (int64_t)rr * D + head * H;
     float* op = out + (int64_t)rr * out_stride + head * H;
 #pragma unroll
@@ -631,7 +670,7 @@ struct StreamCfg {
   static constexpr int FWD_STAGES = 3;
   static constexpr int BWD_STAGES = 3;
   static constexpr size_t fwd_smem = (size_t)kStreamWarps * FWD_STAGES * kBatch * (TS * 4 + 4);
-  static constexpr size_t bwd_smem = (size_t)kStreamWarps * BWD_STAGES * kBatch * (RS * 4 + 8);
+  static constexpr size_t bwd_smem = (size_t)kStreamWarps * BWD_STAGES * kBatch * (RS * 4 + 4);
   static constexpr size_t fwd_w_smem = (size_t)kStreamWarps * FWD_STAGES * kBatch * 4;   // + staged edge weights
   static constexpr size_t bwd_w_smem = (size_t)kStreamWarps * BWD_STAGES * kBatch * 4;
 };
@@ -647,38 +686,33 @@ static int launch_fwd_chunked(const int64_t* indptr, const int32_t* indices, con
                               int64_t n_chunks, const float* T, float* R, const float* bias, int act,
                               float* out, int64_t out_stride, float* vsave, const float* colmean,
                               const float* ew, const float* resid, int64_t resid_stride, float* const* out2_tab,
-                              int64_t out2_block_rows, int64_t out2_stride, DropCoef dc, SplitRows sp, HeavyRows hv,
-                              cudaStream_t st) {
+                              int64_t out2_block_rows, int64_t out2_stride, float* vsave2, float* csave, DropCoef dc,
+                              SplitRows sp, HeavyRows hv, cudaStream_t st) {
   using C = StreamCfg<K, H>;
   HAN_SMEM_ATTR_ONCE((attn_fwd_chunked_kernel<K, H, C::FWD_STAGES, SPLIT>), C::fwd_smem + C::fwd_w_smem);
   unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
   const size_t smem = C::fwd_smem + (ew ? C::fwd_w_smem : 0);
   attn_fwd_chunked_kernel<K, H, C::FWD_STAGES, SPLIT><<<grid, kStreamWarps * 32, smem, st>>>(
       indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, ew, resid, resid_stride, out2_tab,
-      out2_block_rows, out2_stride, dc, sp);
+      out2_block_rows, out2_stride, vsave2, csave, dc, sp);
   if (SPLIT && hv.n > 0)
     attn_fwd_merge_kernel<K, H><<<(unsigned)ceil_div64(hv.n, 4), 128, 0, st>>>(hv.rows, hv.ptr, hv.n, sp.part, R, bias, act,
                                                                             out, out_stride, vsave, resid, resid_stride, out2_tab,
-                                                                            out2_block_rows, out2_stride);
+                                                                            out2_block_rows, out2_stride, vsave2, csave);
   return check_launch("han_attn_fwd_chunked");
 }
 
 template <int K, int H, bool SPLIT>
-static int launch_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
+static int launch_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices,
                                   const int32_t* chunk_rows, int64_t n_chunks, const float* Tsrc,
-                                  const float* R, float* dS_agg, float* df2, float* dl_edge, float* df1_red,
+                                  const float* R, float* dS_agg, float* df2,
                                   const float* ew_t, DropCoef dc, SplitRows sp, HeavyRows hv, cudaStream_t st) {
   using C = StreamCfg<K, H>;
-  HAN_SMEM_ATTR_ONCE((attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, false>), C::bwd_smem + C::bwd_w_smem);
-  HAN_SMEM_ATTR_ONCE((attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, true>), C::bwd_smem + C::bwd_w_smem);
+  HAN_SMEM_ATTR_ONCE((attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT>), C::bwd_smem + C::bwd_w_smem);
   unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
   const size_t smem = C::bwd_smem + (ew_t ? C::bwd_w_smem : 0);
-  if (df1_red != nullptr)
-    attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, true><<<grid, kStreamWarps * 32, smem, st>>>(
-        t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, ew_t, dc, sp);
-  else
-    attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT, false><<<grid, kStreamWarps * 32, smem, st>>>(
-        t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, ew_t, dc, sp);
+  attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT><<<grid, kStreamWarps * 32, smem, st>>>(
+      t_indptr, t_indices, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, ew_t, dc, sp);
   if (SPLIT && hv.n > 0)
     attn_bwd_src_merge_kernel<K, H><<<(unsigned)ceil_div64(hv.n, 4), 128, 0, st>>>(hv.rows, hv.ptr, hv.n, sp.part, dS_agg, df2);
   return check_launch("han_attn_bwd_src_chunked");
@@ -718,8 +752,10 @@ int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const in
                          int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                          int K, int H, int act, float* out, int64_t out_stride, float* vsave,
                          const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
-                         float* const* out2_tab, int64_t out2_block_rows, int64_t out2_stride, const uint32_t* seed_ptr,
-                         float coef_keep, int metapath, int64_t row0, han_stream_t stream) {
+                         float* const* out2_tab, int64_t out2_block_rows, int64_t out2_stride, float* vsave2,
+                         float* csave, const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0,
+                         han_stream_t stream) {
+  HAN_REQUIRE((vsave2 == nullptr) == (csave == nullptr) && (uintptr_t)vsave2 % 16 == 0, "vsave2 / csave: both or neither");
   HAN_REQUIRE(!out2_tab || (out2_stride >= (int64_t)K * H && out2_stride % 4 == 0 && out2_block_rows > 0), "out2");
   HAN_REQUIRE(!resid || (resid_stride >= (int64_t)K * H && resid_stride % 4 == 0 && (uintptr_t)resid % 16 == 0), "resid");
   HAN_REQUIRE(indptr && chunk_rows && T && R && bias && out && vsave, "null pointer");
@@ -732,26 +768,25 @@ int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const in
               ((uintptr_t)bias % 16 == 0), "16-byte alignment");
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_fwd_chunked<k, h, false>(indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, edge_w, resid, resid_stride, out2_tab, out2_block_rows, out2_stride, dc, SplitRows{nullptr, nullptr}, HeavyRows{nullptr, nullptr, 0}, as_stream(stream));
+    return launch_fwd_chunked<k, h, false>(indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, edge_w, resid, resid_stride, out2_tab, out2_block_rows, out2_stride, vsave2, csave, dc, SplitRows{nullptr, nullptr}, HeavyRows{nullptr, nullptr, 0}, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
 }
 
-int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
+int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices,
                              const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                              const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                             float* dl_edge, float* df1_red, const float* edge_w_t, const uint32_t* seed_ptr,
+                             const float* edge_w_t, const uint32_t* seed_ptr,
                              float coef_keep, int metapath, int64_t row0, han_stream_t stream) {
-  HAN_REQUIRE(t_indptr && chunk_rows && Tsrc && R && dS_agg && df2 && (dl_edge || df1_red), "null pointer");
-  HAN_REQUIRE(!df1_red || (uintptr_t)df1_red % 16 == 0, "df1_red must be 16-byte aligned");
+  HAN_REQUIRE(t_indptr && chunk_rows && Tsrc && R && dS_agg && df2, "null pointer");
   HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
   const DropCoef dc = make_drop(seed_ptr, coef_keep, metapath, row0);
   HAN_REQUIRE(n_src > 0 && n_chunks > 0, "sizes");
   HAN_REQUIRE(((uintptr_t)R % 16 == 0) && ((uintptr_t)Tsrc % 16 == 0) && ((uintptr_t)dS_agg % 16 == 0), "16-byte alignment");
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_bwd_src_chunked<k, h, false>(t_indptr, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, edge_w_t, dc, SplitRows{nullptr, nullptr}, HeavyRows{nullptr, nullptr, 0}, as_stream(stream));
+    return launch_bwd_src_chunked<k, h, false>(t_indptr, t_indices, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, edge_w_t, dc, SplitRows{nullptr, nullptr}, HeavyRows{nullptr, nullptr, 0}, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
@@ -761,8 +796,9 @@ int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, 
                                int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                                int K, int H, int act, float* out, int64_t out_stride, float* vsave,
                                const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
-                               float* const* out2_tab, int64_t out2_block_rows, int64_t out2_stride,
-                               const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0, const int32_t* vmap,
+                               float* const* out2_tab, int64_t out2_block_rows, int64_t out2_stride, float* vsave2,
+                               float* csave, const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0,
+                               const int32_t* vmap,
                                float* part, const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
                                han_stream_t stream) {
   HAN_REQUIRE(!resid || (resid_stride >= (int64_t)K * H && resid_stride % 4 == 0 && (uintptr_t)resid % 16 == 0), "resid");
@@ -780,21 +816,20 @@ int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, 
   const HeavyRows hv{heavy_rows, heavy_ptr, n_heavy};
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_fwd_chunked<k, h, true>(indptr_v, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, edge_w, resid, resid_stride, out2_tab, out2_block_rows, out2_stride, dc, sp, hv, as_stream(stream));
+    return launch_fwd_chunked<k, h, true>(indptr_v, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, edge_w, resid, resid_stride, out2_tab, out2_block_rows, out2_stride, vsave2, csave, dc, sp, hv, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");
 }
 
-int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_indices, const int32_t* perm,
+int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_indices,
                                    const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                                    const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                                   float* dl_edge, float* df1_red, const float* edge_w_t, const uint32_t* seed_ptr,
+                                   const float* edge_w_t, const uint32_t* seed_ptr,
                                    float coef_keep, int metapath, int64_t row0, const int32_t* vmap, float* part,
                                    const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
                                    han_stream_t stream) {
-  HAN_REQUIRE(t_indptr_v && chunk_rows && Tsrc && R && dS_agg && df2 && (dl_edge || df1_red), "null pointer");
-  HAN_REQUIRE(!df1_red || (uintptr_t)df1_red % 16 == 0, "df1_red must be 16-byte aligned");
+  HAN_REQUIRE(t_indptr_v && chunk_rows && Tsrc && R && dS_agg && df2, "null pointer");
   HAN_REQUIRE(vmap && part && n_heavy >= 0 && (n_heavy == 0 || (heavy_rows && heavy_ptr)), "split view: vmap, part, heavy rows");
   HAN_REQUIRE(coef_keep > 0.f && coef_keep <= 1.f && (coef_keep == 1.f || seed_ptr), "coef_keep in (0,1], seed_ptr");
   const DropCoef dc = make_drop(seed_ptr, coef_keep, metapath, row0);
@@ -805,7 +840,7 @@ int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_i
   const HeavyRows hv{heavy_rows, heavy_ptr, n_heavy};
 #define X(k, h)         \
   if (K == k && H == h) \
-    return launch_bwd_src_chunked<k, h, true>(t_indptr_v, t_indices, perm, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, dl_edge, df1_red, edge_w_t, dc, sp, hv, as_stream(stream));
+    return launch_bwd_src_chunked<k, h, true>(t_indptr_v, t_indices, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, edge_w_t, dc, sp, hv, as_stream(stream));
   HAN_FOR_SHAPES(X)
 #undef X
   return fail_arg(__func__, "unsupported (K,H); see han_attn_shape_supported");

@@ -6,9 +6,9 @@ numbers as the single-device run" (SURVEY.md section 8(e)).
 
 Per meta-path and step:
   forward : all-gather of the projected node table T = [S | f2]   (n_pad x TS per rank)
-  backward: all-gather of the row records R = [dV | f1 | lse | delta] (n_pad x RS per rank), the
-            by-source pass then runs on the edges whose SOURCE is local, and the per-destination
-            sums df1 go back with one reduce-scatter (N x K floats)
+  backward: all-gather of the row records R = [dV | f1 | lse | delta] (n_pad x RS per rank); the
+            by-source pass then runs on the edges whose SOURCE is local; df1 is row-local (the forward
+            keeps a second aggregate), so nothing is reduced back across ranks
   once    : all-reduce of the parameter gradients and of the loss.
 Collectives run on a side stream and are ordered with events, so the gather of meta-path g+1
 overlaps the aggregation of meta-path g.
@@ -55,13 +55,10 @@ def merge_source_segments(counts: torch.Tensor, segments: Sequence[torch.Tensor]
 
 
 class _BackwardEdges:
-    """Edges (i, j) with j local, in both orders: by source (for the gather pass) and by destination
-    (for the df1 segmented sum)."""
+    """Edges (i, j) with j local, by source (for the gather pass of the backward)."""
 
-    def __init__(self, by_src: MetaPathGraph, by_dst_indptr: torch.Tensor, pos_in_dst: torch.Tensor):
+    def __init__(self, by_src: MetaPathGraph):
         self.by_src = by_src                # rows = local sources, indices = global destination ids
-        self.by_dst_indptr = by_dst_indptr  # int64[N_pad + 1]
-        self.pos_in_dst = pos_in_dst        # int32[nnz]: by-source edge -> slot in by-destination order
 
 
 class SymmetricTables:
@@ -291,11 +288,7 @@ class RowShard:
         n_loc = hi - lo
         segs = list(torch.split(recv, [int(x) for x in recv_split]))
         indptr, indices = merge_source_segments(recv_counts[:, :n_loc].contiguous(), segs)
-        by_src = MetaPathGraph(indptr, indices, n_loc, W * n_pad)
-        by_dst = by_src.transpose()                          # rows = padded global destinations
-        pos = torch.empty_like(by_dst.perm)
-        pos[by_dst.perm.long()] = torch.arange(by_dst.nnz, dtype=torch.int32, device=dev)
-        return _BackwardEdges(by_src, by_dst.indptr, pos)
+        return _BackwardEdges(MetaPathGraph(indptr, indices, n_loc, W * n_pad))
 
     def symmetric_tables(self, G: int, K: int, H: int, slot: int = 0) -> Optional[SymmetricTables]:
         """The multicast-mapped tables for this plan shape (allocated and rendezvoused once; a
@@ -357,47 +350,26 @@ class RowShard:
         return self.all_gather_rows(R)
 
     def backward_edges(self, plan, g: int, T_local: torch.Tensor, R_full: torch.Tensor, dS: torch.Tensor,
-                       df2: torch.Tensor) -> torch.Tensor:
-        """Runs the by-source gather pass on the edges whose source is local and returns df1 for the
-        local destination rows (after the reduce-scatter of the per-destination partial sums)."""
+                       df2: torch.Tensor) -> None:
+        """Runs the by-source gather pass on the edges whose source is local (dS, df2 of the local source rows) against
+        the records of ALL destination rows.  Nothing comes back across ranks: df1 is row-local (ops: prep kernel)."""
         be: _BackwardEdges = self._bwd[id(plan.graphs[g])]
         K, H = plan.K, plan.H
-        dev = T_local.device
         n_loc = T_local.shape[0]
         bs = be.by_src
-        from . import ops as _ops
-        cr, n_chunks = bs.chunks()
-        n_all = self.world * self.n_pad
         row0 = self.row_range(self.n_total)[0]
-        if not _ops.DETERMINISTIC:
-            # per-destination partial sums accumulated inside the gather pass (vector reductions in L2)
-            df1_part = torch.zeros(n_all, K, dtype=torch.float32, device=dev)
-            call("han_attn_bwd_src_chunked", ptr(bs.indptr), ptr(bs.indices), ptr(be.pos_in_dst), ptr(cr), n_chunks,
-                 n_loc, ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), None, ptr(df1_part), None, ptr(plan.seed),
-                 1.0 - plan.coef_drop, plan.metapath_id(g), row0, stream_ptr())
+        tv = bs.split_view()
+        if tv is not None:      # heavy source rows (power-law meta-paths): virtual-row view + merge
+            part = torch.empty((tv.n_slots, K, H + 2), dtype=torch.float32, device=T_local.device)
+            call("han_attn_bwd_src_chunked_split", ptr(tv.indptr_v), ptr(bs.indices), ptr(tv.chunk_rows), tv.n_chunks, n_loc,
+                 ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), None, ptr(plan.seed), 1.0 - plan.coef_drop,
+                 plan.metapath_id(g), row0, ptr(tv.vmap), ptr(part), ptr(tv.heavy_rows), ptr(tv.heavy_ptr), tv.n_heavy,
+                 stream_ptr())
         else:
-            dl = torch.empty(max(bs.nnz, 1), K, dtype=torch.float32, device=dev)
-            call("han_attn_bwd_src_chunked", ptr(bs.indptr), ptr(bs.indices), ptr(be.pos_in_dst), ptr(cr), n_chunks,
-                 n_loc, ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), ptr(dl), None, None, ptr(plan.seed),
-                 1.0 - plan.coef_drop, plan.metapath_id(g), row0, stream_ptr())
-            df1_part = torch.empty(n_all, K, dtype=torch.float32, device=dev)
-            call("han_attn_bwd_dst", ptr(be.by_dst_indptr), n_all, bs.nnz, ptr(dl), K, ptr(df1_part), stream_ptr())
-        # reduce-scatter on the side stream: it overlaps the next meta-path's gather pass; the caller
-        # waits on the returned event before the row-local finish
-        cur = torch.cuda.current_stream()
-        ready = torch.cuda.Event()
-        ready.record(cur)
-        out = torch.empty(self.n_pad, K, dtype=torch.float32, device=dev)
-        with torch.cuda.stream(self.comm_stream):
-            self.comm_stream.wait_event(ready)
-            _lib.trace_mark("reduce_scatter >")
-            td.reduce_scatter_tensor(out, df1_part, op=td.ReduceOp.SUM, group=self.group)
-            _lib.trace_mark("reduce_scatter <")
-            done = torch.cuda.Event()
-            done.record(self.comm_stream)
-        df1_part.record_stream(self.comm_stream)
-        out.record_stream(self.comm_stream)
-        return out, done
+            cr, n_chunks = bs.chunks()
+            call("han_attn_bwd_src_chunked", ptr(bs.indptr), ptr(bs.indices), ptr(cr), n_chunks, n_loc, ptr(T_local),
+                 ptr(R_full), K, H, ptr(dS), ptr(df2), None, ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), row0,
+                 stream_ptr())
 
     # ---- loss / gradients ------------------------------------------------------------------------
     def masked_loss(self, logits, labels, mask, train_op):

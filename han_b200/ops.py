@@ -17,11 +17,6 @@ from .graph import MetaPathGraph
 _ACT = {"elu": _lib.ACT_ELU, "identity": _lib.ACT_IDENTITY}
 
 import os as _os
-# df1 = sum over a destination's edges of dl.  Default (deterministic): dl is written per edge and summed in a
-# fixed order by han_attn_bwd_dst -- bitwise reproducible gradients, no atomics anywhere.  HAN_DF1_RED=1:
-# accumulated inside the by-source pass with 16-byte vector reductions that resolve in L2 (no per-edge dl array,
-# no by-destination pass): ~2 % faster on the 2M config, summation order not fixed run to run.
-DETERMINISTIC = _os.environ.get("HAN_DF1_RED", "0") != "1"
 # Semantic layer on tcgen05 (semantic_tc.cu), D = 64, A = 128: on by default; HAN_SEM_TC=0 selects the
 # mma.sync kernels of semantic.cu (any instantiated (D, A)).
 SEM_TC = _os.environ.get("HAN_SEM_TC", "1") != "0"
@@ -166,6 +161,10 @@ class NodeAttentionFn(torch.autograd.Function):
                 T_src = dist.all_gather_rows(T) if dist is not None else T    # NCCL all-gather on a side stream
             Z = _empty((n, G, D), dev)
             V = _empty((G, n, D), dev)
+            # second aggregate for the backward (V' and c: df1 becomes row-local); skipped for inference
+            train = torch.is_grad_enabled()
+            V2 = _empty((G, n, D), dev) if train else None
+            C1 = _empty((G, n, K), dev) if train else None
             plan.coefs = []
             for g, graph in enumerate(plan.graphs):
                 assert graph.n_rows == n, "graph rows must match the local rows of X"
@@ -186,17 +185,19 @@ class NodeAttentionFn(torch.autograd.Function):
                 sv = graph.split_view()
                 if sv is not None:
                     # heavy rows are cut into segments; a merge kernel combines their partial softmax states
-                    part = _empty((sv.n_slots, K, H + 2), dev)
+                    part = _empty((sv.n_slots, K, 2 * H + 3), dev)
                     call("han_attn_fwd_chunked_split", ptr(sv.indptr_v), ptr(graph.indices), ptr(sv.chunk_rows),
                          sv.n_chunks, n, ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]),
-                         G * D, ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, o2_tab, o2_rows, o2_stride, ptr(plan.seed),
-                         1.0 - plan.coef_drop, plan.metapath_id(g), row0, ptr(sv.vmap), ptr(part), ptr(sv.heavy_rows), ptr(sv.heavy_ptr),
-                         sv.n_heavy, stream_ptr())
+                         G * D, ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, o2_tab, o2_rows, o2_stride,
+                         ptr(V2[g]) if train else None, ptr(C1[g]) if train else None, ptr(plan.seed),
+                         1.0 - plan.coef_drop, plan.metapath_id(g), row0, ptr(sv.vmap), ptr(part), ptr(sv.heavy_rows),
+                         ptr(sv.heavy_ptr), sv.n_heavy, stream_ptr())
                 else:
                     cr, n_chunks = graph.chunks()
                     call("han_attn_fwd_chunked", ptr(graph.indptr), ptr(graph.indices), ptr(cr), n_chunks, n,
                          ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D,
-                         ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, o2_tab, o2_rows, o2_stride, ptr(plan.seed),
+                         ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, o2_tab, o2_rows, o2_stride,
+                         ptr(V2[g]) if train else None, ptr(C1[g]) if train else None, ptr(plan.seed),
                          1.0 - plan.coef_drop, plan.metapath_id(g), row0, stream_ptr())
                 if plan.want_coefs:
                     alpha = _empty((graph.nnz, K), dev)
@@ -208,6 +209,7 @@ class NodeAttentionFn(torch.autograd.Function):
         ctx.S_keep = S_keep
         ctx.W = W if ctx.needs_input_grad[1] else None     # only a stacked layer needs W again (for dX)
         ctx.has_res = res is not None
+        ctx.V2, ctx.C1 = V2, C1
         ctx.save_for_backward(X, a1, a2, T, R, V, Z)
         ctx.mark_non_differentiable()
         return Z
@@ -217,6 +219,9 @@ class NodeAttentionFn(torch.autograd.Function):
         plan: NodeAttentionPlan = ctx.plan
         X, a1, a2, T, R, V, Z = ctx.saved_tensors
         S_keep = ctx.S_keep
+        V2, C1 = ctx.V2, ctx.C1
+        if V2 is None:
+            raise _lib.HanError("backward of a forward that ran without grad mode (no second aggregate was kept)")
         G, K, H, D = plan.G, plan.K, plan.H, plan.D
         n, F = X.shape
         dev = X.device
@@ -226,6 +231,7 @@ class NodeAttentionFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             dS = _empty((G, n, D), dev)
             df2 = _empty((n, K), dev)
+            df1 = _empty((G, n, K), dev)
             part_bias = _empty((NB, D), dev)
             part_par = _empty((NB, 2 * D + 2 * K), dev)
             dbias = _empty((G, D), dev)
@@ -248,7 +254,8 @@ class NodeAttentionFn(torch.autograd.Function):
                 for ci, (c0, c1) in enumerate(bounds):
                     call("han_attn_bwd_prep", ptr(dZ[c0:, g, :]), G * D, ptr(Z[c0:, g, :]), G * D, ptr(V[g][c0:]),
                          ptr(R[g][c0:]), c1 - c0, K, H, plan.act, ptr(part_bias[ci * NB:]),
-                         tabs.R_mc_row(g, 0) if fused_mc else None, lo_row + c0, stream_ptr())
+                         tabs.R_mc_row(g, 0) if fused_mc else None, lo_row + c0, ptr(V2[g][c0:]), ptr(C1[g][c0:]),
+                         ptr(df1[g][c0:]), stream_ptr())
                     if push:
                         tabs.push_R(g, lo_row + c0, lo_row + c1)
                 call("han_reduce_partials", ptr(part_bias), len(bounds) * NB, D, ptr(dbias[g]), stream_ptr())
@@ -259,53 +266,27 @@ class NodeAttentionFn(torch.autograd.Function):
                 R_all = tabs.exchange_R(fused_mc)
             else:
                 R_all = dist.gather_records(R) if dist is not None else None   # NCCL, overlaps the passes
-            # 2) by-source gather pass, by-destination df1 sums, row-local finish
-            pending = []
+            # 2) by-source gather pass (dS, df2), then the row-local finish; df1 came out of the prep kernel
             for g, graph in enumerate(plan.graphs):
                 if dist is None:
                     gt = graph.transpose().wait_ready()
                     ew_t = graph.edge_weight_t()        # weights in transposed-edge order (None: 0/1 adjacency)
-                    red = not DETERMINISTIC
-                    dl = None if red else _empty((max(graph.nnz, 1), K), dev)
-                    df1 = torch.zeros((n, K), dtype=torch.float32, device=dev) if red else _empty((n, K), dev)
-                    df1_red = ptr(df1) if red else None
                     tv = gt.split_view()
                     if tv is not None:
                         part = _empty((tv.n_slots, K, H + 2), dev)
-                        call("han_attn_bwd_src_chunked_split", ptr(tv.indptr_v), ptr(gt.indices), ptr(gt.perm),
+                        call("han_attn_bwd_src_chunked_split", ptr(tv.indptr_v), ptr(gt.indices),
                              ptr(tv.chunk_rows), tv.n_chunks, n, ptr(T[g]), ptr(R[g]), K, H, ptr(dS[g]), ptr(df2),
-                             ptr(dl), df1_red, ptr(ew_t), ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), 0,
+                             ptr(ew_t), ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), 0,
                              ptr(tv.vmap), ptr(part), ptr(tv.heavy_rows), ptr(tv.heavy_ptr), tv.n_heavy, stream_ptr())
                     else:
                         cr, n_chunks = gt.chunks()
-                        call("han_attn_bwd_src_chunked", ptr(gt.indptr), ptr(gt.indices), ptr(gt.perm), ptr(cr),
-                             n_chunks, n, ptr(T[g]), ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(dl), df1_red, ptr(ew_t),
+                        call("han_attn_bwd_src_chunked", ptr(gt.indptr), ptr(gt.indices), ptr(cr),
+                             n_chunks, n, ptr(T[g]), ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(ew_t),
                              ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), 0, stream_ptr())
-                    sv = graph.split_view()
-                    if red:
-                        pass                                      # df1 is complete
-                    elif sv is not None:
-                        # df1 of a cut row: segment sums first, then the sum of its segments (same kernel)
-                        df1_v = _empty((sv.n_v, K), dev)
-                        call("han_attn_bwd_dst", ptr(sv.indptr_v), sv.n_v, graph.nnz, ptr(dl), K, ptr(df1_v), stream_ptr())
-                        call("han_attn_bwd_dst", ptr(sv.vptr), n, sv.n_v, ptr(df1_v), K, ptr(df1), stream_ptr())
-                    else:
-                        call("han_attn_bwd_dst", ptr(graph.indptr), n, graph.nnz, ptr(dl), K, ptr(df1), stream_ptr())
-                    del dl
                 else:
-                    # sharded: df1 comes back from a reduce-scatter that runs on the side stream while the
-                    # next meta-path's gather pass is already going; the finish is deferred (loop 3)
-                    df2_g = _empty((n, K), dev)
-                    pending.append((g, df2_g) + dist.backward_edges(plan, g, T[g], R_all[g], dS[g], df2_g))
-                    continue
-                call("han_attn_bwd_finish", ptr(T[g]), n, K, H, ptr(a1[g]), ptr(a2[g]), ptr(df1), ptr(df2),
-                     ptr(dS[g]), ptr(part_par), ptr(S_keep[g]) if S_keep is not None else None, ptr(plan.seed),
-                     1.0 - plan.in_drop, plan.metapath_id(g), lo_row, stream_ptr())
-                call("han_reduce_partials", ptr(part_par), NB, 2 * D + 2 * K, ptr(dpar[g]), stream_ptr())
-            # 3) sharded only: row-local finish once each meta-path's df1 has arrived
-            for g, df2_g, df1_g, done in pending:
-                torch.cuda.current_stream().wait_event(done)
-                call("han_attn_bwd_finish", ptr(T[g]), n, K, H, ptr(a1[g]), ptr(a2[g]), ptr(df1_g), ptr(df2_g),
+                    # sharded: the edges whose SOURCE is local, against the records of all destination rows
+                    dist.backward_edges(plan, g, T[g], R_all[g], dS[g], df2)
+                call("han_attn_bwd_finish", ptr(T[g]), n, K, H, ptr(a1[g]), ptr(a2[g]), ptr(df1[g]), ptr(df2),
                      ptr(dS[g]), ptr(part_par), ptr(S_keep[g]) if S_keep is not None else None, ptr(plan.seed),
                      1.0 - plan.in_drop, plan.metapath_id(g), lo_row, stream_ptr())
                 call("han_reduce_partials", ptr(part_par), NB, 2 * D + 2 * K, ptr(dpar[g]), stream_ptr())

@@ -148,25 +148,27 @@ int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const in
                          int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                          int K, int H, int act, float* out, int64_t out_stride, float* vsave,
                          const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
-                         float* const* out2_tab, int64_t out2_block_rows, int64_t out2_stride, const uint32_t* seed_ptr,
-                         float coef_keep, int metapath, int64_t row0, han_stream_t stream);
+                         float* const* out2_tab, int64_t out2_block_rows, int64_t out2_stride, float* vsave2,
+                         float* csave, const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0,
+                         han_stream_t stream);
+/* vsave2 [n_dst][D] / csave [n_dst][K] (both or neither; NULL for inference): the second aggregate kept for the
+ * backward.  With k_ij = leaky_relu'(l_ij) (times w_ij with edge weights),
+ *     V'_i = sum_j alpha~_ij k_ij S_j          c_i = sum_j alpha_ij k_ij
+ * make df1_i = sum_j dl_ij = <dV_i, V'_i> - delta_i c_i a ROW-LOCAL quantity (han_attn_bwd_prep): the backward needs no
+ * per-edge dl array, no by-destination pass and, sharded, no reduce-scatter of df1. */
 /* out2_tab (nullable): DEVICE array of base pointers, one per block of out2_block_rows destination rows: row i is also
  * stored to out2_tab[i / out2_block_rows] + (i % out2_block_rows) * out2_stride.  In tile-sharded multi-GPU runs the
  * pointers are peer-mapped addresses inside the other GPUs' semantic-layer inputs (symmetric memory): the re-sharding
  * all-to-all of Z is fused into K-B's epilogue as plain stores over NVLink (models/gat.py:58-60 across GPUs). */
 /* resid (nullable) [n_dst][resid_stride]: the residual term of utils/layers.py:38-40, added before the
  * activation: out_i = act(V_i + bias + resid_i).  Its gradient is dV (R[:, 0:D] after han_attn_bwd_prep). */
-int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, const int32_t* perm,
+int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices,
                              const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                              const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                             float* dl_edge, float* df1_red, const float* edge_w_t, const uint32_t* seed_ptr,
+                             const float* edge_w_t, const uint32_t* seed_ptr,
                              float coef_keep, int metapath, int64_t row0, han_stream_t stream);
 /* edge_w_t (nullable) [nnz]: the edge weights in TRANSPOSED-edge order (edge_w[perm[t]]); dl then carries the
  * factor w_ij (d l_ij / d f1_i = d l_ij / d f2_j = w_ij). */
-/* df1_red (nullable): when given, df1[dst][k] += dl is accumulated right here with 16-byte vector reductions
- * (red.global.add.v4.f32, resolved in L2; the caller zeroes df1 first) instead of writing dl per edge for
- * han_attn_bwd_dst: 64 bytes per edge less memory traffic, at the price of a summation order that is not
- * fixed run to run.  dl_edge may then be NULL.  Deterministic mode: df1_red = NULL. */
 /* Training-mode dropout of the attention coefficients (utils/layers.py:29-30: coefs scaled 1/keep where
  * kept, zeroed elsewhere, NOT re-normalised): coef_keep = 1 - coef_drop in (0,1]; 1 disables it.  The
  * mask bit of edge (dst i, src j), head k of meta-path `metapath` is a pure function of (*seed_ptr, i, j,
@@ -179,20 +181,22 @@ int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices, 
 int han_reduce_blocks(void);
 int han_attn_bwd_prep(const float* dout, int64_t dout_stride, const float* out, int64_t out_stride,
                       const float* vsave, float* R, int64_t n_dst, int K, int H, int act,
-                      float* dbias_partial, float* R_mc, int64_t r_row0, han_stream_t stream);
+                      float* dbias_partial, float* R_mc, int64_t r_row0, const float* vsave2, const float* csave,
+                      float* df1, han_stream_t stream);
+/* df1 (nullable) [n_dst][K] = <dV, vsave2> - delta * csave per head: the gradient w.r.t. f1 (see han_attn_fwd_chunked). */
 /* R_mc (nullable): multicast address of a symmetric record table [rows][RS]; when given, the complete
  * record (dV | f1 | lse | delta) of local row i is written to row r_row0 + i of every rank's copy
  * (prep fused with the all-gather of the records); f1 and lse are read from the local R. */
 
 /* by-source pass over the transposed structure (han_attn_bwd_src_chunked above): for source rows [0,n_src):
- *   dS_agg_j = sum_i alpha_ij dV_i ; df2_j = sum_i dl_ij ; dl_edge[perm[t]][K] = dl_ij
+ *   dS_agg_j = sum_i alpha_ij dV_i ; df2_j = sum_i dl_ij
  * where dl_ij = alpha_ij (dV_i.S_j - delta_i) * leaky'(f1_i + f2_j).  Tsrc rows = local sources. */
 
 /* Heavy rows (power-law meta-paths).  The same two passes over a VIRTUAL-row CSR: indptr_v [n_v+1] is the
  * CSR's offsets with cut points inserted so that no row exceeds a fixed number of edges (column array and
  * perm unchanged; chunk_rows built over indptr_v).  vmap [n_v][2] = (real row, partial slot or -1 for a row
- * that was not cut); part [n_slots][K][H+2] receives the per-segment partial state (forward: running max,
- * normaliser, un-normalised aggregate; backward: df2 and dS sums); heavy_rows [n_heavy] / heavy_ptr
+ * that was not cut); part receives the per-segment partial state: [n_slots][K][2H+3] forward (running max, normaliser,
+ * c, the two un-normalised aggregates), [n_slots][K][H+2] backward (df2 and dS sums); heavy_rows [n_heavy] / heavy_ptr
  * [n_heavy+1] list the cut rows and their slot ranges for the merge kernel (one warp per cut row), which is
  * launched right after the stream kernel.  Results are identical to the un-split entry points up to the
  * order of floating-point additions inside a cut row. */
@@ -200,21 +204,18 @@ int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, 
                                int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
                                int K, int H, int act, float* out, int64_t out_stride, float* vsave,
                                const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
-                               float* const* out2_tab, int64_t out2_block_rows, int64_t out2_stride,
-                               const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0, const int32_t* vmap,
+                               float* const* out2_tab, int64_t out2_block_rows, int64_t out2_stride, float* vsave2,
+                               float* csave, const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0,
+                               const int32_t* vmap,
                                float* part, const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
                                han_stream_t stream);
-int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_indices, const int32_t* perm,
+int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_indices,
                                    const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
                                    const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                                   float* dl_edge, float* df1_red, const float* edge_w_t, const uint32_t* seed_ptr,
+                                   const float* edge_w_t, const uint32_t* seed_ptr,
                                    float coef_keep, int metapath, int64_t row0, const int32_t* vmap, float* part,
                                    const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
                                    han_stream_t stream);
-
-/* by-destination pass: df1_i = sum_j dl_edge[e] over CSR row i -> df1 [n_dst][K]. */
-int han_attn_bwd_dst(const int64_t* indptr, int64_t n_dst, int64_t nnz, const float* dl_edge, int K, float* df1,
-                     han_stream_t stream);
 
 /* finish (row-local): dS_tot = dS_agg + df1 a1^T + df2 a2^T (in place into dS_agg);
  * partial sums for da1,da2 [K][H], db1,db2 [K]: part [han_reduce_blocks()][2*D + 2*K]. */

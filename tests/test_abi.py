@@ -53,7 +53,7 @@ def test_host_queries(lib):
 def test_invalid_arguments_return_negative_and_set_message(lib):
     # argument validation happens before any CUDA call, so this is safe without a GPU
     rc = lib.han_attn_fwd_chunked(None, None, None, 0, 0, None, None, None, 8, 8, 1, None, 64, None, None, None, None, 0,
-                                  None, 0, 0, None, 1.0, 0, 0, None)
+                                  None, 0, 0, None, None, None, 1.0, 0, 0, None)
     assert rc < 0
     assert b"han_attn_fwd_chunked" in lib.han_last_error()
     rc = lib.han_dense_row_counts(None, 0, 0, 4, 4, None, None, None)

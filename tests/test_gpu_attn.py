@@ -271,16 +271,16 @@ def test_heavy_rows_cut_into_segments_match_oracle(split, monkeypatch):
     assert torch.allclose(grads_p["W"][0], grads_u["W"][0], rtol=1e-4, atol=1e-7)
 
 
-def test_vector_reduction_df1_mode_matches_oracle(monkeypatch):
-    """HAN_DF1_RED=1: df1 accumulated inside the by-source pass with red.global.add.v4.f32 instead of the
-    per-edge dl array + han_attn_bwd_dst.  Same gradients up to summation order (plain and heavy-row graphs)."""
-    from han_b200 import graph as hg, ops
+def test_df1_is_row_local_on_plain_and_heavy_row_graphs(monkeypatch):
+    """The forward keeps a second aggregate (V' = sum alpha~ leaky' S, c = sum alpha leaky'), so that
+    df1_i = <dV_i, V'_i> - delta_i c_i needs no per-edge array and no by-destination pass; same gradients on a graph
+    with a full row / a hub column, un-split and through the virtual-row (split + merge) kernels."""
+    from han_b200 import graph as hg
     cfg = synth.tiny(seed=161, n=230, f=18, p=2, deg=7.0)
     cfg.masks[0][5, :] = True
     cfg.masks[0][:, 9] = True
     params = O.init_params(np.random.default_rng(162), [cfg.F] * cfg.P, cfg.C)
     out_o, grads_o = oracle_step(cfg, params)
-    monkeypatch.setattr(ops, "DETERMINISTIC", False)
     out_p, grads_p, _ = product_step(cfg, params)
     compare_step(out_o, grads_o, out_p, grads_p)
     monkeypatch.setattr(hg, "SPLIT_ROW_EDGES", 32)          # and through the virtual-row kernels
