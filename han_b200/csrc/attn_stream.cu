@@ -11,11 +11,13 @@
 #include "han_common.cuh"
 #include "han_rng.cuh"
 
+#include <stdlib.h>
+
 namespace han {
 
 constexpr int kMaxChunkEdges = 2048;   // edges per work item (whole rows; boundaries from chunk_rows)
 constexpr int kMinChunkEdges = 128;
-constexpr int kBatch = 16;          // records per cp.async group
+constexpr int kBatch = 16;          // records per cp.async group (default; template parameter B of the kernels)
 constexpr int kStreamWarps = 4;     // warps per CTA
 
 // attention-coefficient dropout arguments (thr == 0: disabled)
@@ -69,8 +71,8 @@ __global__ void chunk_rows_kernel(const int64_t* __restrict__ indptr, int64_t n_
 // -------------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------------
-template <int K, int H, int STAGES, bool SPLIT>
-__global__ void __launch_bounds__(kStreamWarps * 32, 4)
+template <int K, int H, int STAGES, int B, int MINB, bool SPLIT>
+__global__ void __launch_bounds__(kStreamWarps * 32, MINB)
 attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                         const int32_t* __restrict__ chunk_rows, int64_t n_chunks,
                         const float* __restrict__ T, float* __restrict__ R, const float* __restrict__ bias,
@@ -85,16 +87,16 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
   constexpr int SLOTS = 32 / K;
   constexpr int HV = H / 4;
   constexpr int REC_CHUNKS = TS / 4;
-  constexpr int TOT = kBatch * REC_CHUNKS;
+  constexpr int TOT = B * REC_CHUNKS;
   constexpr int PER_LANE = (TOT + 31) / 32;
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int head = lane % K, slot = lane / K;
-  float* ring = smem + (size_t)w * STAGES * kBatch * TS;
-  int* col_s = reinterpret_cast<int*>(smem + (size_t)kStreamWarps * STAGES * kBatch * TS) + w * STAGES * kBatch;
+  float* ring = smem + (size_t)w * STAGES * B * TS;
+  int* col_s = reinterpret_cast<int*>(smem + (size_t)kStreamWarps * STAGES * B * TS) + w * STAGES * B;
   // sp_attn_head (utils/layers.py:95-96): stored adjacency value w_ij scales the logit; staged like the columns.
   // The region exists only when ew != nullptr (the launcher sizes the dynamic shared memory accordingly).
-  float* w_s = reinterpret_cast<float*>(col_s - w * STAGES * kBatch + kStreamWarps * STAGES * kBatch) + w * STAGES * kBatch;
+  float* w_s = reinterpret_cast<float*>(col_s - w * STAGES * B + kStreamWarps * STAGES * B) + w * STAGES * B;
   // attention-coefficient dropout (utils/layers.py:29-30): mask bit from (seed, dst, src, head)
   const uint32_t cseed = dc.thr ? stream_seed(*dc.seed_ptr, 3u, dc.metapath, (uint32_t)head) : 0u;
 
@@ -103,16 +105,16 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
   const int r_lo = chunk_rows[chunk], r_hi = chunk_rows[chunk + 1];
   if (r_lo >= r_hi) return;
   const int64_t e_lo = indptr[r_lo], e_hi = indptr[r_hi];
-  const int nb = (int)((e_hi - e_lo + kBatch - 1) / kBatch);
+  const int nb = (int)((e_hi - e_lo + B - 1) / B);
 
   int q = 0;  // next batch to issue
-  int col_pref = (lane < kBatch && e_lo + lane < e_hi) ? ldg_stream_i32(indices + e_lo + lane) : 0;
-  float w_pref = (ew && lane < kBatch && e_lo + lane < e_hi) ? __ldg(ew + e_lo + lane) : 1.f;
+  int col_pref = (lane < B && e_lo + lane < e_hi) ? ldg_stream_i32(indices + e_lo + lane) : 0;
+  float w_pref = (ew && lane < B && e_lo + lane < e_hi) ? __ldg(ew + e_lo + lane) : 1.f;
   auto issue = [&]() {
     if (q < nb) {
-      const int64_t bs = e_lo + (int64_t)q * kBatch;
-      const int cnt = (int)min((int64_t)kBatch, e_hi - bs);
-      float* dst = ring + (size_t)(q % STAGES) * kBatch * TS;
+      const int64_t bs = e_lo + (int64_t)q * B;
+      const int cnt = (int)min((int64_t)B, e_hi - bs);
+      float* dst = ring + (size_t)(q % STAGES) * B * TS;
 #pragma unroll
       for (int i = 0; i < PER_LANE; ++i) {
         const int c = lane + 32 * i;
@@ -120,11 +122,11 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
         const int col = __shfl_sync(0xffffffffu, col_pref, rec & 31);
         if (c < TOT && rec < cnt) cp_async16(dst + rec * TS + off * 4, T + (int64_t)col * TS + off * 4);
       }
-      if (lane < kBatch) col_s[(q % STAGES) * kBatch + lane] = col_pref;
-      if (ew && lane < kBatch) w_s[(q % STAGES) * kBatch + lane] = w_pref;
-      const int64_t nbs = bs + kBatch;
-      col_pref = (lane < kBatch && nbs + lane < e_hi) ? ldg_stream_i32(indices + nbs + lane) : 0;
-      if (ew) w_pref = (lane < kBatch && nbs + lane < e_hi) ? __ldg(ew + nbs + lane) : 1.f;
+      if (lane < B) col_s[(q % STAGES) * B + lane] = col_pref;
+      if (ew && lane < B) w_s[(q % STAGES) * B + lane] = w_pref;
+      const int64_t nbs = bs + B;
+      col_pref = (lane < B && nbs + lane < e_hi) ? ldg_stream_i32(indices + nbs + lane) : 0;
+      if (ew) w_pref = (lane < B && nbs + lane < e_hi) ? __ldg(ew + nbs + lane) : 1.f;
     }
     cp_async_commit();
     ++q;
@@ -277,11 +279,11 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
     issue();
     cp_async_wait<STAGES - 1>();
     __syncwarp();
-    const float* buf = ring + (size_t)(b % STAGES) * kBatch * TS;
-    const int* cbuf = col_s + (b % STAGES) * kBatch;
-    const float* wbuf = w_s + (b % STAGES) * kBatch;
-    const int64_t bs = e_lo + (int64_t)b * kBatch;
-    const int64_t be = min(e_hi, bs + kBatch);
+    const float* buf = ring + (size_t)(b % STAGES) * B * TS;
+    const int* cbuf = col_s + (b % STAGES) * B;
+    const float* wbuf = w_s + (b % STAGES) * B;
+    const int64_t bs = e_lo + (int64_t)b * B;
+    const int64_t be = min(e_hi, bs + B);
     while (pos < be) {
       const int64_t seg_end = min(row_end, be);
       for (int64_t g = pos; g < seg_end; g += SLOTS) {
@@ -342,8 +344,8 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
 // -------------------------------------------------------------------------------------------------
 // backward, by source (transposed structure)
 // -------------------------------------------------------------------------------------------------
-template <int K, int H, int STAGES, bool SPLIT>
-__global__ void __launch_bounds__(kStreamWarps * 32, 3)
+template <int K, int H, int STAGES, int B, int MINB, bool SPLIT>
+__global__ void __launch_bounds__(kStreamWarps * 32, MINB)
 attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t* __restrict__ t_indices,
                             const int32_t* __restrict__ chunk_rows,
                             int64_t n_chunks, const float* __restrict__ Tsrc, const float* __restrict__ R,
@@ -355,15 +357,15 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
   constexpr int SLOTS = 32 / K;
   constexpr int HV = H / 4;
   constexpr int REC_CHUNKS = RS / 4;
-  constexpr int TOT = kBatch * REC_CHUNKS;
+  constexpr int TOT = B * REC_CHUNKS;
   constexpr int PER_LANE = (TOT + 31) / 32;
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int head = lane % K, slot = lane / K;
-  float* ring = smem + (size_t)w * STAGES * kBatch * RS;
-  int* row_s = reinterpret_cast<int*>(smem + (size_t)kStreamWarps * STAGES * kBatch * RS) + w * STAGES * kBatch;
+  float* ring = smem + (size_t)w * STAGES * B * RS;
+  int* row_s = reinterpret_cast<int*>(smem + (size_t)kStreamWarps * STAGES * B * RS) + w * STAGES * B;
   // edge weights in transposed-edge order (sp_attn_head); region present only when ew_t != nullptr
-  float* w_s = reinterpret_cast<float*>(row_s - w * STAGES * kBatch + kStreamWarps * STAGES * kBatch) + w * STAGES * kBatch;
+  float* w_s = reinterpret_cast<float*>(row_s - w * STAGES * B + kStreamWarps * STAGES * B) + w * STAGES * B;
   const uint32_t cseed = dc.thr ? stream_seed(*dc.seed_ptr, 3u, dc.metapath, (uint32_t)head) : 0u;
 
   const int64_t chunk = (int64_t)blockIdx.x * kStreamWarps + w;
@@ -371,21 +373,21 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
   const int r_lo = chunk_rows[chunk], r_hi = chunk_rows[chunk + 1];
   if (r_lo >= r_hi) return;
   const int64_t e_lo = t_indptr[r_lo], e_hi = t_indptr[r_hi];
-  const int nb = (int)((e_hi - e_lo + kBatch - 1) / kBatch);
+  const int nb = (int)((e_hi - e_lo + B - 1) / B);
 
   int q = 0;
   int row_pref = 0;
   float w_pref = 1.f;
-  if (lane < kBatch && e_lo + lane < e_hi) {
+  if (lane < B && e_lo + lane < e_hi) {
     row_pref = ldg_stream_i32(t_indices + e_lo + lane);
     if (ew_t) w_pref = __ldg(ew_t + e_lo + lane);
   }
   auto issue = [&]() {
     if (q < nb) {
-      const int64_t bs = e_lo + (int64_t)q * kBatch;
-      const int cnt = (int)min((int64_t)kBatch, e_hi - bs);
+      const int64_t bs = e_lo + (int64_t)q * B;
+      const int cnt = (int)min((int64_t)B, e_hi - bs);
       const int st = q % STAGES;
-      float* dst = ring + (size_t)st * kBatch * RS;
+      float* dst = ring + (size_t)st * B * RS;
 #pragma unroll
       for (int i = 0; i < PER_LANE; ++i) {
         const int c = lane + 32 * i;
@@ -393,12 +395,12 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
         const int i_row = __shfl_sync(0xffffffffu, row_pref, rec & 31);
         if (c < TOT && rec < cnt) cp_async16(dst + rec * RS + off * 4, R + (int64_t)i_row * RS + off * 4);
       }
-      if (lane < kBatch) {
-        row_s[st * kBatch + lane] = row_pref;
-        if (ew_t) w_s[st * kBatch + lane] = w_pref;
+      if (lane < B) {
+        row_s[st * B + lane] = row_pref;
+        if (ew_t) w_s[st * B + lane] = w_pref;
       }
-      const int64_t nbs = bs + kBatch;
-      if (lane < kBatch && nbs + lane < e_hi) {
+      const int64_t nbs = bs + B;
+      if (lane < B && nbs + lane < e_hi) {
         row_pref = ldg_stream_i32(t_indices + nbs + lane);
         if (ew_t) w_pref = __ldg(ew_t + nbs + lane);
       }
@@ -481,11 +483,11 @@ attn_bwd_src_chunked_kernel(const int64_t* __restrict__ t_indptr, const int32_t*
     cp_async_wait<STAGES - 1>();
     __syncwarp();
     const int st = b % STAGES;
-    const float* buf = ring + (size_t)st * kBatch * RS;
-    const int* rbuf = row_s + st * kBatch;
-    const float* wbuf = w_s + st * kBatch;
-    const int64_t bs = e_lo + (int64_t)b * kBatch;
-    const int64_t be = min(e_hi, bs + kBatch);
+    const float* buf = ring + (size_t)st * B * RS;
+    const int* rbuf = row_s + st * B;
+    const float* wbuf = w_s + st * B;
+    const int64_t bs = e_lo + (int64_t)b * B;
+    const int64_t be = min(e_hi, bs + B);
     while (pos < be) {
       const int64_t seg_end = min(row_end, be);
       for (int64_t g = pos; g < seg_end; g += SLOTS) {
@@ -661,18 +663,15 @@ static DropCoef make_drop(const uint32_t* seed_ptr, float keep, int metapath, in
   return dc;
 }
 
-template <int K, int H>
-struct StreamCfg {
+// ring geometry: STAGES batches of B records per warp (STAGES - 1 always in flight), MINB CTAs of 4 warps per SM
+template <int K, int H, int STAGES, int B>
+struct RingCfg {
   static constexpr int D = K * H;
   static constexpr int TS = ((D + K + 3) / 4) * 4;
   static constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
-  // stages chosen so that ~3 CTAs (12 warps) fit in 227 KB and >= 2 batches per warp are in flight
-  static constexpr int FWD_STAGES = 3;
-  static constexpr int BWD_STAGES = 3;
-  static constexpr size_t fwd_smem = (size_t)kStreamWarps * FWD_STAGES * kBatch * (TS * 4 + 4);
-  static constexpr size_t bwd_smem = (size_t)kStreamWarps * BWD_STAGES * kBatch * (RS * 4 + 4);
-  static constexpr size_t fwd_w_smem = (size_t)kStreamWarps * FWD_STAGES * kBatch * 4;   // + staged edge weights
-  static constexpr size_t bwd_w_smem = (size_t)kStreamWarps * BWD_STAGES * kBatch * 4;
+  static constexpr size_t fwd_smem = (size_t)kStreamWarps * STAGES * B * (TS * 4 + 4);
+  static constexpr size_t bwd_smem = (size_t)kStreamWarps * STAGES * B * (RS * 4 + 4);
+  static constexpr size_t w_smem = (size_t)kStreamWarps * STAGES * B * 4;    // + staged edge weights
 };
 
 struct HeavyRows {   // the cut rows of a virtual-row view (all null / 0: no splitting)
@@ -681,18 +680,36 @@ struct HeavyRows {   // the cut rows of a virtual-row view (all null / 0: no spl
   int n;
 };
 
-template <int K, int H, bool SPLIT>
-static int launch_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
-                              int64_t n_chunks, const float* T, float* R, const float* bias, int act,
-                              float* out, int64_t out_stride, float* vsave, const float* colmean,
-                              const float* ew, const float* resid, int64_t resid_stride, float* const* out2_tab,
-                              int64_t out2_block_rows, int64_t out2_stride, float* vsave2, float* csave, DropCoef dc,
-                              SplitRows sp, HeavyRows hv, cudaStream_t st) {
-  using C = StreamCfg<K, H>;
-  HAN_SMEM_ATTR_ONCE((attn_fwd_chunked_kernel<K, H, C::FWD_STAGES, SPLIT>), C::fwd_smem + C::fwd_w_smem);
+// Ring geometry of the (K,H) = (8,8) kernels, from the sweep in profiles/r2_gather_sweep.txt (2M-node bench, ms per step
+// of 4 launches): more resident warps with ONE batch in flight each beat deeper rings -- forward 2 stages x 16 records at
+// 6 CTAs/SM 25.1 (3x16 at 4 CTAs/SM: 29.2), backward 2x16 at 5 CTAs/SM 24.7 (3x16 at 3: 29.3).
+// HAN_GATHER_CFG="f,b" picks an alternative for tuning runs (tools/gather_sweep.sh): 0 = the default above,
+// 1 = 3x16 (4 / 3 CTAs per SM), 2 = forward 2x24 at 4, backward 2x8 at 6, 3 = forward 2x16 at 5, backward 2x16 at 4.
+static void gather_cfg(int* f, int* b) {
+  static int cf = -1, cb = -1;
+  if (cf < 0) {
+    cf = 0;
+    cb = 0;
+    const char* e = getenv("HAN_GATHER_CFG");
+    if (e && e[0] >= '0' && e[0] <= '3') cf = e[0] - '0';
+    if (e && e[0] && e[1] == ',' && e[2] >= '0' && e[2] <= '3') cb = e[2] - '0';
+  }
+  *f = cf;
+  *b = cb;
+}
+
+template <int K, int H, int STAGES, int B, int MINB, bool SPLIT>
+static int launch_fwd_cfg(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
+                          int64_t n_chunks, const float* T, float* R, const float* bias, int act,
+                          float* out, int64_t out_stride, float* vsave, const float* colmean,
+                          const float* ew, const float* resid, int64_t resid_stride, float* const* out2_tab,
+                          int64_t out2_block_rows, int64_t out2_stride, float* vsave2, float* csave, DropCoef dc,
+                          SplitRows sp, HeavyRows hv, cudaStream_t st) {
+  using C = RingCfg<K, H, STAGES, B>;
+  HAN_SMEM_ATTR_ONCE((attn_fwd_chunked_kernel<K, H, STAGES, B, MINB, SPLIT>), C::fwd_smem + C::w_smem);
   unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
-  const size_t smem = C::fwd_smem + (ew ? C::fwd_w_smem : 0);
-  attn_fwd_chunked_kernel<K, H, C::FWD_STAGES, SPLIT><<<grid, kStreamWarps * 32, smem, st>>>(
+  const size_t smem = C::fwd_smem + (ew ? C::w_smem : 0);
+  attn_fwd_chunked_kernel<K, H, STAGES, B, MINB, SPLIT><<<grid, kStreamWarps * 32, smem, st>>>(
       indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, ew, resid, resid_stride, out2_tab,
       out2_block_rows, out2_stride, vsave2, csave, dc, sp);
   if (SPLIT && hv.n > 0)
@@ -703,19 +720,58 @@ static int launch_fwd_chunked(const int64_t* indptr, const int32_t* indices, con
 }
 
 template <int K, int H, bool SPLIT>
-static int launch_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices,
-                                  const int32_t* chunk_rows, int64_t n_chunks, const float* Tsrc,
-                                  const float* R, float* dS_agg, float* df2,
-                                  const float* ew_t, DropCoef dc, SplitRows sp, HeavyRows hv, cudaStream_t st) {
-  using C = StreamCfg<K, H>;
-  HAN_SMEM_ATTR_ONCE((attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT>), C::bwd_smem + C::bwd_w_smem);
+static int launch_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
+                              int64_t n_chunks, const float* T, float* R, const float* bias, int act,
+                              float* out, int64_t out_stride, float* vsave, const float* colmean,
+                              const float* ew, const float* resid, int64_t resid_stride, float* const* out2_tab,
+                              int64_t out2_block_rows, int64_t out2_stride, float* vsave2, float* csave, DropCoef dc,
+                              SplitRows sp, HeavyRows hv, cudaStream_t st) {
+#define HAN_FWD_ARGS indptr, indices, chunk_rows, n_chunks, T, R, bias, act, out, out_stride, vsave, colmean, ew, resid, \
+                     resid_stride, out2_tab, out2_block_rows, out2_stride, vsave2, csave, dc, sp, hv, st
+  if constexpr (K == 8 && H == 8) {
+    int f, b;
+    gather_cfg(&f, &b);
+    if (f == 1) return launch_fwd_cfg<K, H, 3, 16, 4, SPLIT>(HAN_FWD_ARGS);
+    if (f == 2) return launch_fwd_cfg<K, H, 2, 24, 4, SPLIT>(HAN_FWD_ARGS);
+    if (f == 3) return launch_fwd_cfg<K, H, 2, 16, 5, SPLIT>(HAN_FWD_ARGS);
+    return launch_fwd_cfg<K, H, 2, 16, 6, SPLIT>(HAN_FWD_ARGS);
+  }
+  return launch_fwd_cfg<K, H, 3, kBatch, 4, SPLIT>(HAN_FWD_ARGS);
+#undef HAN_FWD_ARGS
+}
+
+template <int K, int H, int STAGES, int B, int MINB, bool SPLIT>
+static int launch_bwd_cfg(const int64_t* t_indptr, const int32_t* t_indices,
+                          const int32_t* chunk_rows, int64_t n_chunks, const float* Tsrc,
+                          const float* R, float* dS_agg, float* df2,
+                          const float* ew_t, DropCoef dc, SplitRows sp, HeavyRows hv, cudaStream_t st) {
+  using C = RingCfg<K, H, STAGES, B>;
+  HAN_SMEM_ATTR_ONCE((attn_bwd_src_chunked_kernel<K, H, STAGES, B, MINB, SPLIT>), C::bwd_smem + C::w_smem);
   unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
-  const size_t smem = C::bwd_smem + (ew_t ? C::bwd_w_smem : 0);
-  attn_bwd_src_chunked_kernel<K, H, C::BWD_STAGES, SPLIT><<<grid, kStreamWarps * 32, smem, st>>>(
+  const size_t smem = C::bwd_smem + (ew_t ? C::w_smem : 0);
+  attn_bwd_src_chunked_kernel<K, H, STAGES, B, MINB, SPLIT><<<grid, kStreamWarps * 32, smem, st>>>(
       t_indptr, t_indices, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, ew_t, dc, sp);
   if (SPLIT && hv.n > 0)
     attn_bwd_src_merge_kernel<K, H><<<(unsigned)ceil_div64(hv.n, 4), 128, 0, st>>>(hv.rows, hv.ptr, hv.n, sp.part, dS_agg, df2);
   return check_launch("han_attn_bwd_src_chunked");
+}
+
+template <int K, int H, bool SPLIT>
+static int launch_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices,
+                                  const int32_t* chunk_rows, int64_t n_chunks, const float* Tsrc,
+                                  const float* R, float* dS_agg, float* df2,
+                                  const float* ew_t, DropCoef dc, SplitRows sp, HeavyRows hv, cudaStream_t st) {
+#define HAN_BWD_ARGS t_indptr, t_indices, chunk_rows, n_chunks, Tsrc, R, dS_agg, df2, ew_t, dc, sp, hv, st
+  if constexpr (K == 8 && H == 8) {
+    int f, b;
+    gather_cfg(&f, &b);
+    if (b == 1) return launch_bwd_cfg<K, H, 3, 16, 3, SPLIT>(HAN_BWD_ARGS);
+    if (b == 2) return launch_bwd_cfg<K, H, 2, 8, 6, SPLIT>(HAN_BWD_ARGS);
+    if (b == 3) return launch_bwd_cfg<K, H, 2, 16, 4, SPLIT>(HAN_BWD_ARGS);
+    return launch_bwd_cfg<K, H, 2, 16, 5, SPLIT>(HAN_BWD_ARGS);
+  }
+  return launch_bwd_cfg<K, H, 3, kBatch, 3, SPLIT>(HAN_BWD_ARGS);
+#undef HAN_BWD_ARGS
 }
 
 }  // namespace han

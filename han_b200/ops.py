@@ -162,7 +162,7 @@ class NodeAttentionFn(torch.autograd.Function):
             Z = _empty((n, G, D), dev)
             V = _empty((G, n, D), dev)
             # second aggregate for the backward (V' and c: df1 becomes row-local); skipped for inference
-            train = torch.is_grad_enabled()
+            train = any(ctx.needs_input_grad)    # grad mode is always off inside Function.forward
             V2 = _empty((G, n, D), dev) if train else None
             C1 = _empty((G, n, K), dev) if train else None
             plan.coefs = []
