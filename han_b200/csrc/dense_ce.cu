@@ -172,6 +172,137 @@ dense_bwd_kernel(const float* __restrict__ X, int64_t n, int D, int64_t ldx, con
   if (tid + DN_THREADS < C) my[(size_t)D * C + tid + DN_THREADS] = dbv2;
 }
 
+// ---- few classes (C <= 8, the node-classification case: 3 for ACM/IMDB, 4 for DBLP) ---------------------------------------
+// The tiled kernels above spend 13/16 of their threads on padding when C = 3 and stage X through scalar shared-memory
+// stores (0.8 ms for a 0.5 GB read on the 2M-node config).  Here LPR = D/4 lanes own one row: each lane loads ONE
+// float4 of it (a fully coalesced 16 B x 32 lanes request), keeps its 4 x C slice of W in registers, and a butterfly
+// over the LPR lanes finishes the C dot products.  Persistent grid; a warp handles 32 / LPR rows per iteration.
+template <int LPR, int CMAX>
+__global__ void __launch_bounds__(256)
+dense_fwd_small_kernel(const float* __restrict__ X, int64_t n, int64_t ldx, const float* __restrict__ W, int C,
+                       const float* __restrict__ b, float* __restrict__ Y) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rsel = lane / LPR;
+  float w[4][CMAX];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) w[i][c] = (c < C) ? __ldg(W + (size_t)(4 * sub + i) * C + c) : 0.f;
+  const float bias = (sub < C) ? __ldg(b + sub) : 0.f;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t step = n_warps * RPW;
+  for (int64_t r0 = warp0 * RPW; r0 < n; r0 += 2 * step) {     // two row groups per iteration: two loads in flight
+    int64_t rr[2] = {r0 + rsel, r0 + step + rsel};
+    float4 xx[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) xx[u] = rr[u] < n ? ldg4_stream(X + rr[u] * ldx + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float4 x = xx[u];
+      const int64_t r = rr[u];
+      float acc[CMAX];
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) acc[c] = fmaf(x.x, w[0][c], fmaf(x.y, w[1][c], fmaf(x.z, w[2][c], x.w * w[3][c])));
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          if (c < C) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);     // C is warp-uniform
+      float y = 0.f;            // lane `sub` of the row keeps column `sub` (no dynamic register indexing)
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (sub == c) y = acc[c];
+      if (r < n && sub < C) Y[r * C + sub] = y + bias;
+    }
+  }
+}
+
+// backward of the same: dX row = dY row W^T (each lane its 4 features), dW / db accumulated in registers over the
+// whole grid-stride loop, then one deterministic CTA reduction into this CTA's partial [dW (D*C) | db (C)].
+template <int LPR, int CMAX>
+__global__ void __launch_bounds__(256)
+dense_bwd_small_kernel(const float* __restrict__ X, int64_t n, int64_t ldx, const float* __restrict__ W, int C,
+                       const float* __restrict__ dY, const float* __restrict__ scale, float* __restrict__ dX,
+                       float* __restrict__ part) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int D = 4 * LPR;
+  __shared__ float red[8][RPW][D + 1][CMAX];      // 8 warps x row groups: <= 8 * 2 * 65 * 8 * 4 B = 33 KB
+  __shared__ float redb[8][RPW][CMAX];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, rsel = lane / LPR;
+  float w[4][CMAX];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) w[i][c] = (c < C) ? __ldg(W + (size_t)(4 * sub + i) * C + c) : 0.f;
+  const float sc = scale ? *scale : 1.f;
+  float dw[4][CMAX], dbv[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    dbv[c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dw[i][c] = 0.f;
+  }
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r0 = warp0 * RPW; r0 < n; r0 += n_warps * RPW) {
+    const int64_t r = r0 + rsel;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    float g[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) g[c] = 0.f;
+    if (r < n) {
+      x = ldg4_stream(X + r * ldx + 4 * sub);
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) g[c] = sc * __ldg(dY + r * C + c);      // the row's C gradients: a broadcast within its lanes
+    }
+    if (dX != nullptr && r < n) {
+      float4 o;
+      o.x = o.y = o.z = o.w = 0.f;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        o.x = fmaf(g[c], w[0][c], o.x);
+        o.y = fmaf(g[c], w[1][c], o.y);
+        o.z = fmaf(g[c], w[2][c], o.z);
+        o.w = fmaf(g[c], w[3][c], o.w);
+      }
+      *reinterpret_cast<float4*>(dX + r * D + 4 * sub) = o;
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      dw[0][c] = fmaf(x.x, g[c], dw[0][c]);
+      dw[1][c] = fmaf(x.y, g[c], dw[1][c]);
+      dw[2][c] = fmaf(x.z, g[c], dw[2][c]);
+      dw[3][c] = fmaf(x.w, g[c], dw[3][c]);
+      dbv[c] += g[c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) red[warp][rsel][4 * sub + i][c] = dw[i][c];
+    if (sub == 0) redb[warp][rsel][c] = dbv[c];
+  }
+  __syncthreads();
+  float* my = part + (size_t)blockIdx.x * ((size_t)D * C + C);
+  for (int i = threadIdx.x; i < D * C + C; i += blockDim.x) {
+    float t = 0.f;
+    if (i < D * C) {
+      const int d = i / C, c = i % C;
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int q = 0; q < RPW; ++q) t += red[k][q][d][c];
+    } else {
+      const int c = i - D * C;
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int q = 0; q < RPW; ++q) t += redb[k][q][c];
+    }
+    my[i] = t;
+  }
+}
+
 // ---- masked softmax cross-entropy: warp per row --------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 masked_ce_kernel(const float* __restrict__ logits, const float* __restrict__ labels, const float* __restrict__ mask,
@@ -289,6 +420,12 @@ int han_dense_fwd(const float* X, int64_t n, int D, int64_t ldx, const float* W,
                   han_stream_t stream) {
   HAN_REQUIRE(X && W && b && Y, "null pointer");
   HAN_REQUIRE(n > 0 && D > 0 && D <= DN_MAXD && C > 0 && C <= DN_MAXC && ldx >= D, "sizes: D <= 64, C <= 384");
+  if (C <= 8 && (D == 64 || D == 32) && ldx % 4 == 0 && (uintptr_t)X % 16 == 0) {
+    const unsigned g = (unsigned)han_dense_blocks();
+    if (D == 64) dense_fwd_small_kernel<16, 8><<<g, 256, 0, as_stream(stream)>>>(X, n, ldx, W, C, b, Y);
+    else dense_fwd_small_kernel<8, 8><<<g, 256, 0, as_stream(stream)>>>(X, n, ldx, W, C, b, Y);
+    return check_launch(__func__);
+  }
   const size_t smem = dense_fwd_smem(D, C);
   HAN_SMEM_ATTR_ONCE(dense_fwd_kernel, dense_fwd_smem(DN_MAXD, DN_MAXC));
   const int64_t tiles = ceil_div64(n, DN_ROWS);
@@ -307,6 +444,11 @@ int han_dense_bwd(const float* X, int64_t n, int D, int64_t ldx, const float* W,
   const size_t smem = dense_bwd_smem(D, C);
   cudaStream_t st = as_stream(stream);
   const unsigned grid = (unsigned)han_dense_blocks();     // every CTA writes its partial (zeros if it has no tile)
+  if (C <= 8 && (D == 64 || D == 32) && ldx % 4 == 0 && (uintptr_t)X % 16 == 0 && (!dX || (uintptr_t)dX % 16 == 0)) {
+    if (D == 64) dense_bwd_small_kernel<16, 8><<<grid, 256, 0, st>>>(X, n, ldx, W, C, dY, scale, dX, part);
+    else dense_bwd_small_kernel<8, 8><<<grid, 256, 0, st>>>(X, n, ldx, W, C, dY, scale, dX, part);
+    return check_launch(__func__);
+  }
   const int ct = (C + 3) / 4;
 #define LAUNCH(CT)                                                                                             \
   {                                                                                                            \
