@@ -210,7 +210,7 @@ def algorithmic_bytes(name, wl):
        han_attn_fwd_chunked    : (4 + 4*TS) B/edge + (8 + 4K f1 + 4K lse + 4K c + 3 * 4D [out, V, V']) B/row
        han_attn_bwd_src_chunked: (4 + 4*RS) B/edge + (8 + 4*TS + 4D + 4K) B/source row"""
     K, D = K_HEADS, K_HEADS * HID
-    TS, RS = 72, 88
+    TS, RS = 64, 88       # table rows hold S only (f2 is recomputed from them)
     E = sum(g.nnz for g in wl["graphs"])
     n = wl["hi"] - wl["lo"]
     P = len(wl["graphs"])

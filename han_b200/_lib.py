@@ -35,30 +35,31 @@ _SIGNATURES = {
     "han_transpose_workspace_bytes": (SZ, [I64, I64, I64]),
     "han_csr_transpose": (c_int, [I64, I64, I64, P, P, P, P, P, P, SZ, P]),
     "han_csr_sort_rows": (c_int, [I64, P, P, P, P, P, P]),
-    "han_project_fwd": (c_int, [P, I64, I64, I64, P, I, I, I, P, P, P, P, P, P, I, P]),
+    "han_project_fwd": (c_int, [P, I64, I64, I64, P, I, I, I, P, P, P, P, I, P]),
     "han_project_tc_workspace_bytes": (SZ, [I64, I, I, I]),
-    "han_project_fwd_tc": (c_int, [P, I64, I64, I64, P, I, I, I, P, P, P, P, P, P, P, I64, I64, I64, I, P, SZ, P]),
+    "han_project_fwd_tc": (c_int, [P, I64, I64, I64, P, I, I, I, P, P, P, P, P, I64, I64, I64, I, P, SZ, P]),
     "han_multicast_copy": (c_int, [P, P, I64, P]),
     "han_project_bwd_workspace_bytes": (SZ, [I64, I64, I, I]),
     "han_project_bwd": (c_int, [P, I64, I64, I64, P, I, I, P, P, SZ, I, P]),
     "han_project_bwd_tc_workspace_bytes": (SZ, [I64, I64, I]),
     "han_project_bwd_tc": (c_int, [P, I64, I64, I64, P, I, P, P, SZ, I, P]),
-    "han_attn_coefs": (c_int, [P, P, I64, P, P, I, I, P, P, P]),
+    "han_attn_coefs": (c_int, [P, P, I64, P, P, P, P, I, I, P, P, P]),
     "han_csr_chunk_edges": (c_int64, [I64]),
     "han_csr_num_chunks": (c_int64, [I64]),
     "han_csr_chunk_rows": (c_int, [P, I64, I64, P, P]),
-    "han_attn_fwd_chunked": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, I64, I64, P, P, P, FL, I,
-                                     I64, P]),
-    "han_attn_bwd_src_chunked": (c_int, [P, P, P, I64, I64, P, P, I, I, P, P, P, P, FL, I, I64, P]),
-    "han_attn_fwd_chunked_split": (c_int, [P, P, P, I64, I64, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, I64, I64, P, P, P, FL, I,
-                                           I64, P, P, P, P, I, P]),
-    "han_attn_bwd_src_chunked_split": (c_int, [P, P, P, I64, I64, P, P, I, I, P, P, P, P, FL, I, I64, P, P, P, P, I, P]),
-    "han_project_fwd_drop": (c_int, [P, I64, I64, I64, P, I64, I, I, I, P, P, P, P, P, P, P, P, FL, I, I64, P]),
+    "han_attn_fwd_chunked": (c_int, [P, P, P, I64, I64, P, P, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, I64, I64, P, P, P,
+                                     FL, FL, I, I64, P]),
+    "han_attn_bwd_src_chunked": (c_int, [P, P, P, I64, I64, P, P, P, P, I, I, P, P, P, P, FL, FL, I, I64, P]),
+    "han_attn_fwd_chunked_split": (c_int, [P, P, P, I64, I64, P, P, P, P, P, I, I, I, P, I64, P, P, P, P, I64, P, I64, I64, P, P,
+                                           P, FL, FL, I, I64, P, P, P, P, I, P]),
+    "han_attn_bwd_src_chunked_split": (c_int, [P, P, P, I64, I64, P, P, P, P, I, I, P, P, P, P, FL, FL, I, I64, P, P, P, P, I,
+                                               P]),
+    "han_project_fwd_drop": (c_int, [P, I64, I64, I64, P, I64, I, I, I, P, P, P, P, P, FL, I, I64, P]),
     "han_project_bwd_drop_workspace_bytes": (SZ, [I64, I64, I]),
     "han_project_bwd_drop": (c_int, [P, I64, I64, I64, P, I, I, I, P, I64, P, SZ, P, FL, I, I64, P]),
     "han_reduce_blocks": (c_int, []),
     "han_attn_bwd_prep": (c_int, [P, I64, P, I64, P, P, I64, I, I, I, P, P, I64, P, P, P, P]),
-    "han_attn_bwd_finish": (c_int, [P, I64, I, I, P, P, P, P, P, P, P, P, FL, I, I64, P]),
+    "han_attn_bwd_finish": (c_int, [P, I64, I, I, P, P, P, P, P, P, P, FL, I, I64, P]),
     "han_reduce_partials": (c_int, [P, I, I64, P, P]),
     "han_semantic_shape_supported": (c_int, [I, I]),
     "han_semantic_fwd": (c_int, [P, I64, I, I, I, P, P, P, I, P, P, P, P, P]),

@@ -108,15 +108,15 @@ __global__ void __launch_bounds__(256)
 attn_bwd_finish_kernel(const float* __restrict__ T, int64_t n, const float* __restrict__ a1,
                        const float* __restrict__ a2, const float* __restrict__ df1,
                        const float* __restrict__ df2, float* __restrict__ dS, float* __restrict__ part,
-                       const float* __restrict__ S_keep, const uint32_t* __restrict__ seed_ptr, uint32_t thr,
+                       const uint32_t* __restrict__ seed_ptr, uint32_t thr,
                        float inv_keep, uint32_t metapath, int64_t row0) {
   constexpr int D = K * H;
-  constexpr int TS = ((D + K + 3) / 4) * 4;
+  constexpr int TS = D;
   constexpr int ROWS = 256 / K;
   const int head = threadIdx.x % K;
   const int rsub = threadIdx.x / K;
   // training-mode dropout of the projected features (layers.py:31-32): dS_agg is the gradient w.r.t. the
-  // DROPPED S, so it goes through the same mask; a1/a2 gradients need the un-dropped S (S_keep)
+  // DROPPED S, so it goes through the same mask; a1/a2 gradients need the un-dropped S (what the table holds)
   const uint32_t sseed = thr ? stream_seed(*seed_ptr, 2u, metapath, 0u) : 0u;
   float a1v[H], a2v[H], da1[H], da2[H];
   float db1 = 0.f, db2 = 0.f;
@@ -135,8 +135,7 @@ attn_bwd_finish_kernel(const float* __restrict__ T, int64_t n, const float* __re
       db2 += g2;
 #pragma unroll
       for (int q = 0; q < H / 4; ++q) {
-        const float4 s = thr ? ldg4_stream(S_keep + row * D + head * H + 4 * q)
-                             : ldg4_stream(T + row * TS + head * H + 4 * q);
+        const float4 s = ldg4_stream(T + row * TS + head * H + 4 * q);
         float4 d = *reinterpret_cast<const float4*>(dS + row * D + head * H + 4 * q);
         if (thr) {
           const uint32_t node = (uint32_t)(row + row0);
@@ -252,19 +251,18 @@ int han_attn_bwd_prep(const float* dout, int64_t dout_stride, const float* out, 
 }
 
 int han_attn_bwd_finish(const float* T, int64_t n, int K, int H, const float* a1, const float* a2,
-                        const float* df1, const float* df2, float* dS, float* part, const float* S_keep,
+                        const float* df1, const float* df2, float* dS, float* part,
                         const uint32_t* seed_ptr, float in_keep, int metapath, int64_t row0,
                         han_stream_t stream) {
   HAN_REQUIRE(T && a1 && a2 && df1 && df2 && dS && part, "null pointer");
   HAN_REQUIRE(n > 0, "n > 0 required");
-  HAN_REQUIRE(in_keep > 0.f && in_keep <= 1.f && (in_keep == 1.f || (seed_ptr && S_keep)),
-              "in_keep in (0,1]; dropout needs seed_ptr and S_keep");
+  HAN_REQUIRE(in_keep > 0.f && in_keep <= 1.f && (in_keep == 1.f || seed_ptr), "in_keep in (0,1]; dropout needs seed_ptr");
   const uint32_t thr = in_keep < 1.f ? (uint32_t)(in_keep * 16777216.f + 0.5f) : 0u;
   const float inv_keep = in_keep < 1.f ? 1.f / ((float)thr / 16777216.f) : 1.f;
 #define X(k, h)                                                                                        \
   if (K == k && H == h) {                                                                              \
     attn_bwd_finish_kernel<k, h><<<kReduceBlocks, 256, 0, as_stream(stream)>>>(                        \
-        T, n, a1, a2, df1, df2, dS, part, S_keep, seed_ptr, thr, inv_keep, (uint32_t)metapath, row0);  \
+        T, n, a1, a2, df1, df2, dS, part, seed_ptr, thr, inv_keep, (uint32_t)metapath, row0);          \
     return check_launch(__func__);                                                                     \
   }
   HAN_FOR_SHAPES(X)

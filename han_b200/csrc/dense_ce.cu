@@ -191,30 +191,22 @@ dense_fwd_small_kernel(const float* __restrict__ X, int64_t n, int64_t ldx, cons
   const float bias = (sub < C) ? __ldg(b + sub) : 0.f;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t step = n_warps * RPW;
-  for (int64_t r0 = warp0 * RPW; r0 < n; r0 += 2 * step) {     // two row groups per iteration: two loads in flight
-    int64_t rr[2] = {r0 + rsel, r0 + step + rsel};
-    float4 xx[2];
+  for (int64_t r0 = warp0 * RPW; r0 < n; r0 += n_warps * RPW) {
+    const int64_t r = r0 + rsel;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < n) x = ldg4_stream(X + r * ldx + 4 * sub);
+    float acc[CMAX];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) xx[u] = rr[u] < n ? ldg4_stream(X + rr[u] * ldx + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < CMAX; ++c) acc[c] = fmaf(x.x, w[0][c], fmaf(x.y, w[1][c], fmaf(x.z, w[2][c], x.w * w[3][c])));
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const float4 x = xx[u];
-      const int64_t r = rr[u];
-      float acc[CMAX];
+    for (int o = LPR / 2; o > 0; o >>= 1)
 #pragma unroll
-      for (int c = 0; c < CMAX; ++c) acc[c] = fmaf(x.x, w[0][c], fmaf(x.y, w[1][c], fmaf(x.z, w[2][c], x.w * w[3][c])));
+      for (int c = 0; c < CMAX; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    float y = 0.f;            // lane `sub` of the row keeps column `sub` (no dynamic register indexing)
 #pragma unroll
-      for (int o = LPR / 2; o > 0; o >>= 1)
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c)
-          if (c < C) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);     // C is warp-uniform
-      float y = 0.f;            // lane `sub` of the row keeps column `sub` (no dynamic register indexing)
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (sub == c) y = acc[c];
-      if (r < n && sub < C) Y[r * C + sub] = y + bias;
-    }
+    for (int c = 0; c < CMAX; ++c)
+      if (sub == c) y = acc[c];
+    if (r < n && sub < C) Y[r * C + sub] = y + bias;
   }
 }
 

@@ -79,6 +79,20 @@ __device__ __forceinline__ int ldg_stream_i32(const int* p) {
 }
 __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeakySlope * x; }
 
+// S_j a2 over one head (utils/layers.py:24 without its bias), in the association every kernel uses -- even and odd
+// elements as two FMA chains (the forward gather runs them as one packed FFMA2 chain), added at the end -- so that the
+// forward, the backward and han_attn_coefs see bit-identical logits: logit = (f1 + b2) + score_dot(S_j, a2).
+template <int H>
+__device__ __forceinline__ float score_dot(const float* v, const float* a) {
+  float x = v[0] * a[0], y = v[1] * a[1];
+#pragma unroll
+  for (int i = 1; i < H / 2; ++i) {
+    x = fmaf(v[2 * i], a[2 * i], x);
+    y = fmaf(v[2 * i + 1], a[2 * i + 1], y);
+  }
+  return x + y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -89,29 +89,27 @@ sgemm_nn_kernel(const float* __restrict__ A, int64_t M, int64_t Kd, int64_t lda,
   }
 }
 
-// f1 = S a1 + b1 -> R[:, D+k]; f2 = S a2 + b2 -> T[:, D+k]   (utils/layers.py:23-24); thread=(row,head)
+// f1 = S a1 + b1 -> R[:, D+k]   (utils/layers.py:23); thread = (row, head).  f2 = S a2 + b2 (:24) is NOT stored: the
+// gather kernels recompute it from the table row they fetch anyway, which keeps the table rows at D floats.
 template <int K, int H>
 __global__ void __launch_bounds__(256)
-attn_scores_kernel(float* __restrict__ T, float* __restrict__ R, int64_t n, const float* __restrict__ a1,
-                   const float* __restrict__ b1, const float* __restrict__ a2, const float* __restrict__ b2) {
+attn_scores_kernel(const float* __restrict__ T, float* __restrict__ R, int64_t n, const float* __restrict__ a1,
+                   const float* __restrict__ b1) {
   constexpr int D = K * H;
-  constexpr int TS = ((D + K + 3) / 4) * 4;
+  constexpr int TS = D;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t row = idx / K;
   const int head = (int)(idx % K);
   if (row >= n) return;
-  float s1 = b1[head], s2 = b2[head];
+  float s1 = b1[head];
 #pragma unroll
   for (int q = 0; q < H / 4; ++q) {
     const float4 s = *reinterpret_cast<const float4*>(T + row * TS + head * H + 4 * q);
     const float4 x1 = ldg4(a1 + head * H + 4 * q);
-    const float4 x2 = ldg4(a2 + head * H + 4 * q);
     s1 += s.x * x1.x + s.y * x1.y + s.z * x1.z + s.w * x1.w;
-    s2 += s.x * x2.x + s.y * x2.y + s.z * x2.z + s.w * x2.w;
   }
   R[row * RS + D + head] = s1;
-  T[row * TS + D + head] = s2;
 }
 
 // C_part[split][F x Dn] = A^T[F x rows] * G[rows x Dn] over this split's row range.
@@ -226,9 +224,8 @@ using namespace han;
 extern "C" {
 
 int han_project_fwd(const float* X, int64_t n, int64_t F, int64_t ldx, const float* W, int G, int K,
-                    int H, const float* a1, const float* b1, const float* a2, const float* b2,
-                    float* T, float* R, int mode, han_stream_t stream) {
-  HAN_REQUIRE(X && W && a1 && b1 && a2 && b2 && T && R, "null pointer");
+                    int H, const float* a1, const float* b1, float* T, float* R, int mode, han_stream_t stream) {
+  HAN_REQUIRE(X && W && a1 && b1 && T && R, "null pointer");
   HAN_REQUIRE(n > 0 && F > 0 && G > 0 && ldx >= F, "sizes");
   HAN_REQUIRE(han_attn_shape_supported(K, H), "unsupported (K,H)");
   HAN_REQUIRE(mode == 0, "only mode 0 (fp32 FFMA) is built into this library version");
@@ -264,8 +261,7 @@ int han_project_fwd(const float* X, int64_t n, int64_t F, int64_t ldx, const flo
     unsigned grid = (unsigned)ceil_div64(n * K, 256);
 #define X_(k, h)                                                                                   \
   if (K == k && H == h)                                                                            \
-    attn_scores_kernel<k, h><<<grid, 256, 0, st>>>(Tg, Rg, n, a1 + (int64_t)g * D, b1 + (int64_t)g * K, \
-                                                   a2 + (int64_t)g * D, b2 + (int64_t)g * K);
+    attn_scores_kernel<k, h><<<grid, 256, 0, st>>>(Tg, Rg, n, a1 + (int64_t)g * D, b1 + (int64_t)g * K);
     HAN_FOR_SHAPES(X_)
 #undef X_
   }

@@ -119,41 +119,27 @@ sgemm_nn_drop_kernel(const float* __restrict__ A, int64_t M, int64_t Kd, int64_t
   }
 }
 
-// f1, f2 from the un-dropped S (layers.py:23-24); keep S; drop S in place for the aggregation (:31-32)
+// f1 from the un-dropped S (layers.py:23).  The table keeps the UN-dropped S: f2 (:24) is recomputed from it by the
+// gather kernels, which also apply the feature mask of :31-32 to the rows they fetch (same counter-based bits).
 template <int K, int H>
 __global__ void __launch_bounds__(256)
-scores_drop_kernel(float* __restrict__ T, float* __restrict__ R, float* __restrict__ S_keep, int64_t n,
-                   const float* __restrict__ a1, const float* __restrict__ b1, const float* __restrict__ a2,
-                   const float* __restrict__ b2, DropIn dr) {
+scores_drop_kernel(const float* __restrict__ T, float* __restrict__ R, int64_t n, const float* __restrict__ a1,
+                   const float* __restrict__ b1) {
   constexpr int D = K * H;
-  constexpr int TS = ((D + K + 3) / 4) * 4;
+  constexpr int TS = D;
   constexpr int RS = ((D + 3 * K + 3) / 4) * 4;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t row = idx / K;
   const int head = (int)(idx % K);
   if (row >= n) return;
-  const uint32_t sseed = stream_seed(*dr.seed_ptr, 2u, dr.metapath, 0u);
-  float s1 = b1[head], s2 = b2[head];
+  float s1 = b1[head];
 #pragma unroll
   for (int q = 0; q < H / 4; ++q) {
-    float* sp = T + row * TS + head * H + 4 * q;
-    const float4 s = *reinterpret_cast<const float4*>(sp);
+    const float4 s = *reinterpret_cast<const float4*>(T + row * TS + head * H + 4 * q);
     const float4 x1 = ldg4(a1 + head * H + 4 * q);
-    const float4 x2 = ldg4(a2 + head * H + 4 * q);
     s1 += s.x * x1.x + s.y * x1.y + s.z * x1.z + s.w * x1.w;
-    s2 += s.x * x2.x + s.y * x2.y + s.z * x2.z + s.w * x2.w;
-    *reinterpret_cast<float4*>(S_keep + row * D + head * H + 4 * q) = s;
-    const uint32_t node = (uint32_t)(row + dr.row0);
-    const int d = head * H + 4 * q;
-    float4 sd;
-    sd.x = keep24(sseed, node, (uint32_t)(d + 0), dr.thr) ? s.x * dr.inv_keep : 0.f;
-    sd.y = keep24(sseed, node, (uint32_t)(d + 1), dr.thr) ? s.y * dr.inv_keep : 0.f;
-    sd.z = keep24(sseed, node, (uint32_t)(d + 2), dr.thr) ? s.z * dr.inv_keep : 0.f;
-    sd.w = keep24(sseed, node, (uint32_t)(d + 3), dr.thr) ? s.w * dr.inv_keep : 0.f;
-    *reinterpret_cast<float4*>(sp) = sd;
   }
   R[row * RS + D + head] = s1;
-  T[row * TS + D + head] = s2;
 }
 
 // dW partial[split][F x D] = (X * mask_head / keep)^T dS_g over this split's rows, ONE meta-path
@@ -288,10 +274,10 @@ extern "C" {
 
 int han_project_fwd_drop(const float* X, int64_t n, int64_t F, int64_t ldx, const float* W, int64_t ldw, int G, int K,
                          int H,
-                         const float* a1, const float* b1, const float* a2, const float* b2, float* T, float* R,
-                         float* S_keep, const uint32_t* seed_ptr, float in_keep, int metapath0, int64_t row0,
+                         const float* a1, const float* b1, float* T, float* R,
+                         const uint32_t* seed_ptr, float in_keep, int metapath0, int64_t row0,
                          han_stream_t stream) {
-  HAN_REQUIRE(X && W && a1 && b1 && a2 && b2 && T && R && S_keep && seed_ptr, "null pointer");
+  HAN_REQUIRE(X && W && a1 && b1 && T && R && seed_ptr, "null pointer");
   HAN_REQUIRE(n > 0 && F > 0 && G > 0 && ldx >= F && ldw >= (int64_t)G * K * H, "sizes");
   HAN_REQUIRE(in_keep > 0.f && in_keep < 1.f, "in_keep in (0,1): use han_project_fwd when dropout is off");
   HAN_REQUIRE(K <= 8 && han_attn_shape_supported(K, H), "dropout projection: K <= 8 and a supported (K,H)");
@@ -307,8 +293,7 @@ int han_project_fwd_drop(const float* X, int64_t n, int64_t F, int64_t ldx, cons
     unsigned sgrid = (unsigned)ceil_div64(n * K, 256);
 #define X_(k, h)                                                                                             \
   if (K == k && H == h)                                                                                      \
-    scores_drop_kernel<k, h><<<sgrid, 256, 0, st>>>(Tg, Rg, S_keep + (int64_t)g * n * D, n, a1 + (int64_t)g * D, \
-                                                    b1 + (int64_t)g * K, a2 + (int64_t)g * D, b2 + (int64_t)g * K, dr);
+    scores_drop_kernel<k, h><<<sgrid, 256, 0, st>>>(Tg, Rg, n, a1 + (int64_t)g * D, b1 + (int64_t)g * K);
     HAN_FOR_SHAPES(X_)
 #undef X_
   }

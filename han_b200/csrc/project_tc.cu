@@ -9,7 +9,7 @@
 //               dropping only the lo*lo term (2^-22 relative) -> FP32-grade.  mode 2 (2xTF32): X is
 //               exactly representable in tf32 (0/1 bag-of-words features of ACM/DBLP/IMDB), only W is
 //               split.  mode 3: plain TF32.
-//   epilogue  : tcgen05.ld (one accumulator row per thread) -> f1 = S a1 + b1, f2 = S a2 + b2 fused
+//   epilogue  : tcgen05.ld (one accumulator row per thread) -> f1 = S a1 + b1 fused (f2 = S a2 + b2 is recomputed by the gather kernels from the table row)
 //               here, rows written straight into the node table / row record layout.
 //
 // Warp roles (192 threads, 1 CTA per SM): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer
@@ -127,17 +127,17 @@ template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                   const __grid_constant__ CUtensorMap tmBlo, int64_t n_rows, int nkb, int G,
-                  const float* __restrict__ a1, const float* __restrict__ b1, const float* __restrict__ a2,
-                  const float* __restrict__ b2, float* __restrict__ T, float* __restrict__ R,
+                  const float* __restrict__ a1, const float* __restrict__ b1, float* __restrict__ T,
+                  float* __restrict__ R,
                   float* __restrict__ Tmc, int64_t t_rows, int64_t t_row0, int64_t r_rows) {
-  constexpr int D = 64, K = 8, H = 8, TS = 72, RS = 88;
+  constexpr int D = 64, K = 8, H = 8, TS = 64, RS = 88;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   // stage s: [A_hi 16K][A_lo 16K][B_hi 32K][B_lo 32K]
   const uint32_t tail = base + TC_STAGES * TC_STAGE_BYTES;
-  float* par = reinterpret_cast<float*>(gen_base + TC_STAGES * TC_STAGE_BYTES);   // [G][a1 64|a2 64|b1 8|b2 8]
-  const uint32_t bars = tail + 4 * 4 * (64 + 64 + 8 + 8);
+  float* par = reinterpret_cast<float*>(gen_base + TC_STAGES * TC_STAGE_BYTES);   // [G][a1 64|b1 8]
+  const uint32_t bars = tail + 4 * 4 * (64 + 8);
   const uint32_t full0 = bars, xform0 = bars + 16, empty0 = bars + 32, accum = bars + 48;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + (bars + 64 - base));
 
@@ -145,14 +145,9 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int m0 = blockIdx.x * TC_BM;
   const int NC = G * D;
 
-  for (int i = threadIdx.x; i < G * 144; i += TC_THREADS) {
-    const int g = i / 144, o = i % 144;
-    float v;
-    if (o < 64) v = a1[g * 64 + o];
-    else if (o < 128) v = a2[g * 64 + (o - 64)];
-    else if (o < 136) v = b1[g * 8 + (o - 128)];
-    else v = b2[g * 8 + (o - 136)];
-    par[i] = v;
+  for (int i = threadIdx.x; i < G * 72; i += TC_THREADS) {
+    const int g = i / 72, o = i % 72;
+    par[i] = (o < 64) ? a1[g * 64 + o] : b1[g * 8 + (o - 64)];
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -268,20 +263,17 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int i = 0; i < 32; ++i) v1[i] = __float_as_uint(__uint_as_float(v1[i]) + __uint_as_float(c[i]));
       }
       if (row < n_rows) {
-        const float* pg = par + g * 144;
-        float f1[K], f2[K];
+        const float* pg = par + g * 72;
+        float f1[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          float s1 = pg[128 + k], s2 = pg[136 + k];
+          float s1 = pg[64 + k];
 #pragma unroll
           for (int h = 0; h < H; ++h) {
             const int c = k * H + h;
-            const float sv = __uint_as_float(c < 32 ? v0[c] : v1[c - 32]);
-            s1 = fmaf(sv, pg[c], s1);
-            s2 = fmaf(sv, pg[64 + c], s2);
+            s1 = fmaf(__uint_as_float(c < 32 ? v0[c] : v1[c - 32]), pg[c], s1);
           }
           f1[k] = s1;
-          f2[k] = s2;
         }
         // node-table row: local store, or ONE multicast store per 16 B that NVSwitch replicates into the
         // same offset of every rank's table (GEMM epilogue fused with the all-gather)
@@ -298,8 +290,6 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int c = 0; c < 8; ++c)
           store_row16(tbase + 32 + 4 * c, mc, __uint_as_float(v1[4 * c]), __uint_as_float(v1[4 * c + 1]),
                       __uint_as_float(v1[4 * c + 2]), __uint_as_float(v1[4 * c + 3]));
-        store_row16(tbase + 64, mc, f2[0], f2[1], f2[2], f2[3]);
-        store_row16(tbase + 68, mc, f2[4], f2[5], f2[6], f2[7]);
         float4* rp = reinterpret_cast<float4*>(R + ((int64_t)g * r_rows + row) * RS + D);
         rp[0] = make_float4(f1[0], f1[1], f1[2], f1[3]);
         rp[1] = make_float4(f1[4], f1[5], f1[6], f1[7]);
@@ -363,10 +353,9 @@ size_t han_project_tc_workspace_bytes(int64_t F, int G, int K, int H) {
 }
 
 int han_project_fwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const float* W, int G, int K, int H,
-                       const float* a1, const float* b1, const float* a2, const float* b2, float* T, float* R,
-                       float* T_mc, int64_t t_rows, int64_t t_row0, int64_t r_rows, int mode, void* ws,
+                       const float* a1, const float* b1, float* T, float* R, float* T_mc, int64_t t_rows, int64_t t_row0, int64_t r_rows, int mode, void* ws,
                        size_t ws_bytes, han_stream_t stream) {
-  HAN_REQUIRE(X && W && a1 && b1 && a2 && b2 && (T || T_mc) && R && ws, "null pointer");
+  HAN_REQUIRE(X && W && a1 && b1 && (T || T_mc) && R && ws, "null pointer");
   if (t_rows == 0) t_rows = n;   // destination tables are exactly [G][n][.]
   if (r_rows == 0) r_rows = n;
   HAN_REQUIRE(t_rows >= t_row0 + n && t_row0 >= 0 && r_rows >= n, "t_row0 + n <= t_rows and n <= r_rows required");
@@ -397,13 +386,13 @@ int han_project_fwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const 
   HAN_SMEM_ATTR_ONCE(project_tc_kernel<2>, TC_SMEM_BYTES);
   HAN_SMEM_ATTR_ONCE(project_tc_kernel<3>, TC_SMEM_BYTES);
   if (mode == 1)
-    project_tc_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, a2, b2, T, R,
+    project_tc_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, T, R,
                                                                   T_mc, t_rows, t_row0, r_rows);
   else if (mode == 2)
-    project_tc_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, a2, b2, T, R,
+    project_tc_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, T, R,
                                                                   T_mc, t_rows, t_row0, r_rows);
   else
-    project_tc_kernel<3><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, a2, b2, T, R,
+    project_tc_kernel<3><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmBhi, tmBlo, n, nkb, G, a1, b1, T, R,
                                                                   T_mc, t_rows, t_row0, r_rows);
   return check_launch(__func__);
 }

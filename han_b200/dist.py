@@ -5,7 +5,7 @@ The reference is single-process (ex_acm3025.py:163); this layer is new and its c
 numbers as the single-device run" (SURVEY.md section 8(e)).
 
 Per meta-path and step:
-  forward : all-gather of the projected node table T = [S | f2]   (n_pad x TS per rank)
+  forward : all-gather of the projected node table T = S          (n_pad x D per rank; f2 is recomputed)
   backward: all-gather of the row records R = [dV | f1 | lse | delta] (n_pad x RS per rank); the
             by-source pass then runs on the edges whose SOURCE is local; df1 is row-local (the forward
             keeps a second aggregate), so nothing is reduced back across ranks
@@ -349,8 +349,8 @@ class RowShard:
         so that gather g+1 overlaps the by-source pass of g."""
         return self.all_gather_rows(R)
 
-    def backward_edges(self, plan, g: int, T_local: torch.Tensor, R_full: torch.Tensor, dS: torch.Tensor,
-                       df2: torch.Tensor) -> None:
+    def backward_edges(self, plan, g: int, T_local: torch.Tensor, a2: torch.Tensor, b2: torch.Tensor, R_full: torch.Tensor,
+                       dS: torch.Tensor, df2: torch.Tensor) -> None:
         """Runs the by-source gather pass on the edges whose source is local (dS, df2 of the local source rows) against
         the records of ALL destination rows.  Nothing comes back across ranks: df1 is row-local (ops: prep kernel)."""
         be: _BackwardEdges = self._bwd[id(plan.graphs[g])]
@@ -362,14 +362,14 @@ class RowShard:
         if tv is not None:      # heavy source rows (power-law meta-paths): virtual-row view + merge
             part = torch.empty((tv.n_slots, K, H + 2), dtype=torch.float32, device=T_local.device)
             call("han_attn_bwd_src_chunked_split", ptr(tv.indptr_v), ptr(bs.indices), ptr(tv.chunk_rows), tv.n_chunks, n_loc,
-                 ptr(T_local), ptr(R_full), K, H, ptr(dS), ptr(df2), None, ptr(plan.seed), 1.0 - plan.coef_drop,
-                 plan.metapath_id(g), row0, ptr(tv.vmap), ptr(part), ptr(tv.heavy_rows), ptr(tv.heavy_ptr), tv.n_heavy,
+                 ptr(T_local), ptr(a2), ptr(b2), ptr(R_full), K, H, ptr(dS), ptr(df2), None, ptr(plan.seed),
+                 1.0 - plan.coef_drop, 1.0 - plan.in_drop, plan.metapath_id(g), row0, ptr(tv.vmap), ptr(part), ptr(tv.heavy_rows), ptr(tv.heavy_ptr), tv.n_heavy,
                  stream_ptr())
         else:
             cr, n_chunks = bs.chunks()
             call("han_attn_bwd_src_chunked", ptr(bs.indptr), ptr(bs.indices), ptr(cr), n_chunks, n_loc, ptr(T_local),
-                 ptr(R_full), K, H, ptr(dS), ptr(df2), None, ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), row0,
-                 stream_ptr())
+                 ptr(a2), ptr(b2), ptr(R_full), K, H, ptr(dS), ptr(df2), None, ptr(plan.seed), 1.0 - plan.coef_drop,
+                 1.0 - plan.in_drop, plan.metapath_id(g), row0, stream_ptr())
 
     # ---- loss / gradients ------------------------------------------------------------------------
     def masked_loss(self, logits, labels, mask, train_op):

@@ -104,7 +104,7 @@ class NodeAttentionFn(torch.autograd.Function):
                 T = _empty((G, n, TS), dev)
                 R = _empty((G, n, RS), dev)
             row0 = dist.row_range(dist.n_total)[0] if dist is not None else 0
-            S_keep = None
+            in_keep = 1.0 - plan.in_drop          # the table keeps the un-dropped S; the gather kernels mask what they fetch
             if (plan.in_drop or plan.coef_drop) and plan.seed is None:
                 raise _lib.HanError("dropout needs plan.seed (an int32[1] CUDA tensor)")
             if plan.in_drop or plan.project_mode == 0 or (K, H) != (8, 8):
@@ -112,15 +112,14 @@ class NodeAttentionFn(torch.autograd.Function):
                 Tl = T if tabs is None else _empty((G, n, TS), dev)
                 Rl = R if tabs is None else _empty((G, n, RS), dev)
                 if plan.in_drop:
-                    # training mode: per-head input masks + dropped projected features (layers.py:18-19,31-32)
-                    S_keep = _empty((G, n, D), dev)
+                    # training mode: per-head input masks (layers.py:18-19)
                     for g in range(G):    # one launch per meta-path: each has its own mask stream id
                         call("han_project_fwd_drop", ptr(X), n, F, X.stride(0), ptr(W[:, g * D:]), G * D, 1, K, H,
-                             ptr(a1[g]), ptr(b1[g]), ptr(a2[g]), ptr(b2[g]), ptr(Tl[g]), ptr(Rl[g]), ptr(S_keep[g]),
-                             ptr(plan.seed), 1.0 - plan.in_drop, plan.metapath_id(g), row0, stream_ptr(), kernels=2)
+                             ptr(a1[g]), ptr(b1[g]), ptr(Tl[g]), ptr(Rl[g]),
+                             ptr(plan.seed), in_keep, plan.metapath_id(g), row0, stream_ptr(), kernels=2)
                 else:
-                    call("han_project_fwd", ptr(X), n, F, X.stride(0), ptr(W), G, K, H, ptr(a1), ptr(b1), ptr(a2),
-                         ptr(b2), ptr(Tl), ptr(Rl), 0, stream_ptr())
+                    call("han_project_fwd", ptr(X), n, F, X.stride(0), ptr(W), G, K, H, ptr(a1), ptr(b1), ptr(Tl), ptr(Rl),
+                         0, stream_ptr())
                 if tabs is not None:
                     R[:, :, D:D + K] = Rl[:, :, D:D + K]
                     if fused_mc:
@@ -145,7 +144,7 @@ class NodeAttentionFn(torch.autograd.Function):
                         ws_bytes = query("han_project_tc_workspace_bytes", F, g1 - g0, K, H)
                         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                         call("han_project_fwd_tc", ptr(Xa[c0:]), c1 - c0, F, Xa.stride(0), ptr(Wg), g1 - g0, K, H, ptr(a1[g0]),
-                             ptr(b1[g0]), ptr(a2[g0]), ptr(b2[g0]), None if fused_mc else ptr(T[g0][c0:]), ptr(R[g0][c0:]),
+                             ptr(b1[g0]), None if fused_mc else ptr(T[g0][c0:]), ptr(R[g0][c0:]),
                              tabs.T_mc_row(g0, 0) if fused_mc else None, t_rows, (lo + c0) if fused_mc else 0, r_rows,
                              plan.project_mode, ptr(ws), ws_bytes, stream_ptr(), kernels=2)
                     if push:
@@ -174,7 +173,9 @@ class NodeAttentionFn(torch.autograd.Function):
                     # dense-path semantics of an all -1e9 row: uniform 1/N over all N nodes (padded rows of a
                     # sharded table are zero, so the sum over the table divided by N is the mean over real rows)
                     n_all_nodes = dist.n_total if dist is not None else T_src[g].shape[0]
-                    colmean = (T_src[g][:, :D].sum(0) / n_all_nodes).contiguous()
+                    colmean = T_src[g].sum(0) / n_all_nodes
+                    if plan.in_drop:     # expectation over the feature mask is not what the dense path does: same bits
+                        raise _lib.HanError("rows without any edge are not supported together with feature dropout")
                 ew = graph.edge_weight                 # sp_attn_head's stored adjacency values (None: 0/1 adjacency)
                 # tile sharding: every output row is also stored into the semantic input of the rank that owns it,
                 # over NVLink -- the all-to-all of Z rides on the gather kernel's epilogue
@@ -187,38 +188,36 @@ class NodeAttentionFn(torch.autograd.Function):
                     # heavy rows are cut into segments; a merge kernel combines their partial softmax states
                     part = _empty((sv.n_slots, K, 2 * H + 3), dev)
                     call("han_attn_fwd_chunked_split", ptr(sv.indptr_v), ptr(graph.indices), ptr(sv.chunk_rows),
-                         sv.n_chunks, n, ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]),
-                         G * D, ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, o2_tab, o2_rows, o2_stride,
+                         sv.n_chunks, n, ptr(T_src[g]), ptr(a2[g]), ptr(b2[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act,
+                         ptr(Z[:, g, :]), G * D, ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, o2_tab, o2_rows, o2_stride,
                          ptr(V2[g]) if train else None, ptr(C1[g]) if train else None, ptr(plan.seed),
-                         1.0 - plan.coef_drop, plan.metapath_id(g), row0, ptr(sv.vmap), ptr(part), ptr(sv.heavy_rows),
+                         1.0 - plan.coef_drop, in_keep, plan.metapath_id(g), row0, ptr(sv.vmap), ptr(part), ptr(sv.heavy_rows),
                          ptr(sv.heavy_ptr), sv.n_heavy, stream_ptr())
                 else:
                     cr, n_chunks = graph.chunks()
                     call("han_attn_fwd_chunked", ptr(graph.indptr), ptr(graph.indices), ptr(cr), n_chunks, n,
-                         ptr(T_src[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]), G * D,
-                         ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, o2_tab, o2_rows, o2_stride,
+                         ptr(T_src[g]), ptr(a2[g]), ptr(b2[g]), ptr(R[g]), ptr(bias[g]), K, H, plan.act, ptr(Z[:, g, :]),
+                         G * D, ptr(V[g]), ptr(colmean), ptr(ew), ptr(res), D, o2_tab, o2_rows, o2_stride,
                          ptr(V2[g]) if train else None, ptr(C1[g]) if train else None, ptr(plan.seed),
-                         1.0 - plan.coef_drop, plan.metapath_id(g), row0, stream_ptr())
+                         1.0 - plan.coef_drop, in_keep, plan.metapath_id(g), row0, stream_ptr())
                 if plan.want_coefs:
                     alpha = _empty((graph.nnz, K), dev)
                     if graph.nnz:
-                        call("han_attn_coefs", ptr(graph.indptr), ptr(graph.indices), n, ptr(T_src[g]),
-                             ptr(R[g]), K, H, ptr(ew), ptr(alpha), stream_ptr())
+                        call("han_attn_coefs", ptr(graph.indptr), ptr(graph.indices), n, ptr(T_src[g]), ptr(a2[g]),
+                             ptr(b2[g]), ptr(R[g]), K, H, ptr(ew), ptr(alpha), stream_ptr())
                     plan.coefs.append(alpha)
         ctx.plan = plan
-        ctx.S_keep = S_keep
         ctx.W = W if ctx.needs_input_grad[1] else None     # only a stacked layer needs W again (for dX)
         ctx.has_res = res is not None
         ctx.V2, ctx.C1 = V2, C1
-        ctx.save_for_backward(X, a1, a2, T, R, V, Z)
+        ctx.save_for_backward(X, a1, a2, b2, T, R, V, Z)
         ctx.mark_non_differentiable()
         return Z
 
     @staticmethod
     def backward(ctx, dZ):
         plan: NodeAttentionPlan = ctx.plan
-        X, a1, a2, T, R, V, Z = ctx.saved_tensors
-        S_keep = ctx.S_keep
+        X, a1, a2, b2, T, R, V, Z = ctx.saved_tensors
         V2, C1 = ctx.V2, ctx.C1
         if V2 is None:
             raise _lib.HanError("backward of a forward that ran without grad mode (no second aggregate was kept)")
@@ -275,20 +274,22 @@ class NodeAttentionFn(torch.autograd.Function):
                     if tv is not None:
                         part = _empty((tv.n_slots, K, H + 2), dev)
                         call("han_attn_bwd_src_chunked_split", ptr(tv.indptr_v), ptr(gt.indices),
-                             ptr(tv.chunk_rows), tv.n_chunks, n, ptr(T[g]), ptr(R[g]), K, H, ptr(dS[g]), ptr(df2),
-                             ptr(ew_t), ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), 0,
+                             ptr(tv.chunk_rows), tv.n_chunks, n, ptr(T[g]), ptr(a2[g]), ptr(b2[g]), ptr(R[g]), K, H,
+                             ptr(dS[g]), ptr(df2), ptr(ew_t), ptr(plan.seed), 1.0 - plan.coef_drop, 1.0 - plan.in_drop,
+                             plan.metapath_id(g), 0,
                              ptr(tv.vmap), ptr(part), ptr(tv.heavy_rows), ptr(tv.heavy_ptr), tv.n_heavy, stream_ptr())
                     else:
                         cr, n_chunks = gt.chunks()
                         call("han_attn_bwd_src_chunked", ptr(gt.indptr), ptr(gt.indices), ptr(cr),
-                             n_chunks, n, ptr(T[g]), ptr(R[g]), K, H, ptr(dS[g]), ptr(df2), ptr(ew_t),
-                             ptr(plan.seed), 1.0 - plan.coef_drop, plan.metapath_id(g), 0, stream_ptr())
+                             n_chunks, n, ptr(T[g]), ptr(a2[g]), ptr(b2[g]), ptr(R[g]), K, H, ptr(dS[g]), ptr(df2),
+                             ptr(ew_t), ptr(plan.seed), 1.0 - plan.coef_drop, 1.0 - plan.in_drop, plan.metapath_id(g), 0,
+                             stream_ptr())
                 else:
                     # sharded: the edges whose SOURCE is local, against the records of all destination rows
-                    dist.backward_edges(plan, g, T[g], R_all[g], dS[g], df2)
+                    dist.backward_edges(plan, g, T[g], a2[g], b2[g], R_all[g], dS[g], df2)
                 call("han_attn_bwd_finish", ptr(T[g]), n, K, H, ptr(a1[g]), ptr(a2[g]), ptr(df1[g]), ptr(df2),
-                     ptr(dS[g]), ptr(part_par), ptr(S_keep[g]) if S_keep is not None else None, ptr(plan.seed),
-                     1.0 - plan.in_drop, plan.metapath_id(g), lo_row, stream_ptr())
+                     ptr(dS[g]), ptr(part_par), ptr(plan.seed), 1.0 - plan.in_drop, plan.metapath_id(g), lo_row,
+                     stream_ptr())
                 call("han_reduce_partials", ptr(part_par), NB, 2 * D + 2 * K, ptr(dpar[g]), stream_ptr())
             dW = _empty((F, G * D), dev)
             if plan.in_drop:
@@ -447,14 +448,12 @@ class ResidualConvFn(torch.autograd.Function):
             T, R = _empty((1, n, TS), dev), _empty((1, n, RS), dev)
             za, zb = torch.zeros(1, K, H, device=dev), torch.zeros(1, K, device=dev)
             if in_drop:
-                S = _empty((1, n, D), dev)
-                call("han_project_fwd_drop", ptr(X), n, F, X.stride(0), ptr(W_res), D, 1, K, H, ptr(za), ptr(zb), ptr(za),
-                     ptr(zb), ptr(T), ptr(R), ptr(S), ptr(seed), 1.0 - in_drop, metapath, row0, stream_ptr(), kernels=2)
-                out = S[0]
+                call("han_project_fwd_drop", ptr(X), n, F, X.stride(0), ptr(W_res), D, 1, K, H, ptr(za), ptr(zb),
+                     ptr(T), ptr(R), ptr(seed), 1.0 - in_drop, metapath, row0, stream_ptr(), kernels=2)
             else:
-                call("han_project_fwd", ptr(X), n, F, X.stride(0), ptr(W_res), 1, K, H, ptr(za), ptr(zb), ptr(za), ptr(zb),
+                call("han_project_fwd", ptr(X), n, F, X.stride(0), ptr(W_res), 1, K, H, ptr(za), ptr(zb),
                      ptr(T), ptr(R), 0, stream_ptr())
-                out = T[0][:, :D].contiguous()
+            out = T[0]                  # table rows are exactly the D projected features
         ctx.save_for_backward(X, W_res)
         ctx.meta = (K, H, seed, in_drop, metapath, row0)
         return out

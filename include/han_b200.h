@@ -14,9 +14,11 @@
  *    thread-local message for the last non-zero return.
  *  - fp32 row-major everywhere; CSR = int64 indptr[n+1] + int32 indices[nnz], columns ascending.
  *  - K = heads, H = hidden units per head, D = K*H.  Supported (K,H): see han_attn_shape_supported.
- *  - Node table T: [n][TS] fp32, TS = han_table_stride(K,H) = roundup(D + K, 4):
+ *  - Node table T: [n][TS] fp32, TS = han_table_stride(K,H) = D:
  *        T[j][0:D]   = S_j  = X_j W           (utils/layers.py:20)
- *        T[j][D:D+K] = f2_j = S_j a2 + b2     (utils/layers.py:24)
+ *    f2_j = S_j a2 + b2 (utils/layers.py:24) is NOT stored: the kernels that need it (K-B, the by-source pass of
+ *    K-D, han_attn_coefs) recompute it from the row they fetch anyway (8 FMAs per head), which keeps a gathered
+ *    record at D floats -- 256 B for K = H = 8, a whole number of 64-byte DRAM fetches -- and takes a2 / b2.
  *  - Row record R: [n][RS] fp32, RS = han_record_stride(K,H) = roundup(D + 3K, 4):
  *        [ dV (D) | f1 (K) | lse (K) | delta (K) ]
  *        f1 = S a1 + b1 (utils/layers.py:23); lse = log-sum-exp of the row's logits, so that
@@ -81,22 +83,20 @@ int han_csr_sort_rows(int64_t n_rows, const int64_t* indptr, int32_t* indices, i
 
 /* ---- K-A: projection. Replaces utils/layers.py:20,23,24 for G groups of K heads at once ----- */
 /* X [n][ldx] (F columns used), W [F][G*D] (meta-path g, head k in columns g*D + k*H ...),
- * a1,a2 [G][K][H], b1,b2 [G][K].  Writes T [G][n][TS] and f1 into R[g][:, D:D+K] (R [G][n][RS]).
+ * a1 [G][K][H], b1 [G][K].  Writes T [G][n][TS] and f1 = S a1 + b1 into R[g][:, D:D+K] (R [G][n][RS]).
  * mode must be 0: exact-FP32 CUDA-core FFMA, any supported (K,H), any alignment; the tensor-core
  * variants are han_project_fwd_tc below. */
 int han_project_fwd(const float* X, int64_t n, int64_t F, int64_t ldx, const float* W, int G, int K,
-                    int H, const float* a1, const float* b1, const float* a2, const float* b2,
-                    float* T, float* R, int mode, han_stream_t stream);
+                    int H, const float* a1, const float* b1, float* T, float* R, int mode, han_stream_t stream);
 
-/* The same projection on the tcgen05 tensor cores (TMA-staged operands, TMEM accumulators, f1/f2
+/* The same projection on the tcgen05 tensor cores (TMA-staged operands, TMEM accumulators, f1
  * fused into the epilogue).  K = H = 8, 1 <= G <= 4 (<= 256 accumulator columns), X 16-byte aligned
  * with ldx % 4 == 0.  mode 1 = 3xTF32 (X and W split hi+lo: FP32-grade), 2 = 2xTF32 (X exactly
  * representable in tf32, e.g. 0/1 features; only W split), 3 = plain TF32.
  * ws: han_project_tc_workspace_bytes (transposed hi/lo copies of W). */
 size_t han_project_tc_workspace_bytes(int64_t F, int G, int K, int H);
 int han_project_fwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const float* W, int G, int K,
-                       int H, const float* a1, const float* b1, const float* a2, const float* b2,
-                       float* T, float* R, float* T_mc, int64_t t_rows, int64_t t_row0, int64_t r_rows,
+                       int H, const float* a1, const float* b1, float* T, float* R, float* T_mc, int64_t t_rows, int64_t t_row0, int64_t r_rows,
                        int mode, void* ws, size_t ws_bytes, han_stream_t stream);
 /* Destination addressing: meta-path g, local row i goes to T + ((g*t_rows + t_row0 + i)*TS) and
  * R + ((g*r_rows + i)*RS); t_rows / r_rows = 0 mean n (tables are exactly [G][n][.]); larger values
@@ -123,7 +123,8 @@ int han_project_bwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const 
 
 /* ---- K-B: fused CSR edge-softmax-aggregate. Replaces utils/layers.py:26-35,46 for K heads ---- */
 /* For destination rows [0,n_dst): alpha_ij = softmax_j(leaky_relu_0.2(f1_i + f2_j)), V_i = sum_j
- * alpha_ij S_j, out_i = act(V_i + bias).  T is indexed by the CSR's column ids; f1 is read from
+ * alpha_ij S_j, out_i = act(V_i + bias).  T is indexed by the CSR's column ids; f2_j = T_j a2 + b2 (a2 [K][H],
+ * b2 [K] of this meta-path) is computed per gathered row; f1 is read from
  * R[:, D:D+K]; lse is written to R[:, D+K:D+2K]; V to vsave [n_dst][D]; out to
  * out + i*out_stride (so K-B writes straight into Z[n][P][D], models/gat.py:46,58,60).
  * colmean (nullable) [D]: value used for rows with no edge at all (dense-path uniform 1/N row).
@@ -131,8 +132,9 @@ int han_project_bwd_tc(const float* X, int64_t n, int64_t F, int64_t ldx, const 
  * l_ij = w_ij (f1_i + f2_j); NULL = the 0/1 adjacency of attn_head.  Entry points: han_attn_fwd_chunked* below. */
 
 /* Per-edge coefficients alpha [nnz][K] (utils/layers.py:43-44 return_coef), from the saved lse. */
-int han_attn_coefs(const int64_t* indptr, const int32_t* indices, int64_t n_dst, const float* T,
-                   const float* R, int K, int H, const float* edge_w, float* alpha, han_stream_t stream);
+int han_attn_coefs(const int64_t* indptr, const int32_t* indices, int64_t n_dst, const float* T, const float* a2,
+                   const float* b2, const float* R, int K, int H, const float* edge_w, float* alpha,
+                   han_stream_t stream);
 
 /* Chunked edge-stream kernels of K-B / the by-source pass of K-D: a warp owns a
  * contiguous chunk of whole rows (~han_csr_chunk_edges(nnz) edges, boundaries precomputed once per graph) and pulls the
@@ -145,12 +147,13 @@ int han_csr_chunk_rows(const int64_t* indptr, int64_t n_rows, int64_t nnz, int32
 /* indptr may point at row r0 of a larger CSR (then n_rows / nnz are those of the sub-range and chunk_rows holds
  * row numbers relative to r0). */
 int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
-                         int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
+                         int64_t n_chunks, int64_t n_dst, const float* T, const float* a2, const float* b2,
+                         float* R, const float* bias,
                          int K, int H, int act, float* out, int64_t out_stride, float* vsave,
                          const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
                          float* const* out2_tab, int64_t out2_block_rows, int64_t out2_stride, float* vsave2,
-                         float* csave, const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0,
-                         han_stream_t stream);
+                         float* csave, const uint32_t* seed_ptr, float coef_keep, float in_keep, int metapath,
+                         int64_t row0, han_stream_t stream);
 /* vsave2 [n_dst][D] / csave [n_dst][K] (both or neither; NULL for inference): the second aggregate kept for the
  * backward.  With k_ij = leaky_relu'(l_ij) (times w_ij with edge weights),
  *     V'_i = sum_j alpha~_ij k_ij S_j          c_i = sum_j alpha_ij k_ij
@@ -164,16 +167,20 @@ int han_attn_fwd_chunked(const int64_t* indptr, const int32_t* indices, const in
  * activation: out_i = act(V_i + bias + resid_i).  Its gradient is dV (R[:, 0:D] after han_attn_bwd_prep). */
 int han_attn_bwd_src_chunked(const int64_t* t_indptr, const int32_t* t_indices,
                              const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
-                             const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                             const float* edge_w_t, const uint32_t* seed_ptr,
-                             float coef_keep, int metapath, int64_t row0, han_stream_t stream);
+                             const float* Tsrc, const float* a2, const float* b2, const float* R, int K, int H,
+                             float* dS_agg, float* df2, const float* edge_w_t, const uint32_t* seed_ptr,
+                             float coef_keep, float in_keep, int metapath, int64_t row0, han_stream_t stream);
 /* edge_w_t (nullable) [nnz]: the edge weights in TRANSPOSED-edge order (edge_w[perm[t]]); dl then carries the
  * factor w_ij (d l_ij / d f1_i = d l_ij / d f2_j = w_ij). */
 /* Training-mode dropout of the attention coefficients (utils/layers.py:29-30: coefs scaled 1/keep where
  * kept, zeroed elsewhere, NOT re-normalised): coef_keep = 1 - coef_drop in (0,1]; 1 disables it.  The
  * mask bit of edge (dst i, src j), head k of meta-path `metapath` is a pure function of (*seed_ptr, i, j,
  * k, metapath) (han_rng.cuh), recomputed identically by the forward, the backward and every rank; row0
- * is the global id of local row 0.  seed_ptr is a DEVICE word so a captured CUDA graph can advance it. */
+ * is the global id of local row 0.  seed_ptr is a DEVICE word so a captured CUDA graph can advance it.
+ * Training-mode dropout of the projected features (utils/layers.py:31-32): in_keep = 1 - ffd_drop in (0,1]; 1 disables
+ * it.  The table keeps the UN-dropped S (f1 / f2 come from it, :23-24); the gather kernels mask the rows they fetch --
+ * bit of (node j, column d) a pure function of (*seed_ptr, j, d, metapath), j a GLOBAL node id (the CSR's column ids
+ * forward, row0 + local source row backward) -- so the aggregate (:33) and its gradient see the dropped S. */
 
 /* ---- K-D: backward of K-B ----------------------------------------------------------------- */
 /* prep (row-local): dV = dout * act'(.), delta = <dV, V> per head -> R[:, 0:D], R[:, D+2K:D+3K];
@@ -201,40 +208,41 @@ int han_attn_bwd_prep(const float* dout, int64_t dout_stride, const float* out, 
  * launched right after the stream kernel.  Results are identical to the un-split entry points up to the
  * order of floating-point additions inside a cut row. */
 int han_attn_fwd_chunked_split(const int64_t* indptr_v, const int32_t* indices, const int32_t* chunk_rows,
-                               int64_t n_chunks, int64_t n_dst, const float* T, float* R, const float* bias,
+                               int64_t n_chunks, int64_t n_dst, const float* T, const float* a2, const float* b2,
+                               float* R, const float* bias,
                                int K, int H, int act, float* out, int64_t out_stride, float* vsave,
                                const float* colmean, const float* edge_w, const float* resid, int64_t resid_stride,
                                float* const* out2_tab, int64_t out2_block_rows, int64_t out2_stride, float* vsave2,
-                               float* csave, const uint32_t* seed_ptr, float coef_keep, int metapath, int64_t row0,
-                               const int32_t* vmap,
+                               float* csave, const uint32_t* seed_ptr, float coef_keep, float in_keep, int metapath,
+                               int64_t row0, const int32_t* vmap,
                                float* part, const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
                                han_stream_t stream);
 int han_attn_bwd_src_chunked_split(const int64_t* t_indptr_v, const int32_t* t_indices,
                                    const int32_t* chunk_rows, int64_t n_chunks, int64_t n_src,
-                                   const float* Tsrc, const float* R, int K, int H, float* dS_agg, float* df2,
-                                   const float* edge_w_t, const uint32_t* seed_ptr,
-                                   float coef_keep, int metapath, int64_t row0, const int32_t* vmap, float* part,
+                                   const float* Tsrc, const float* a2, const float* b2, const float* R, int K, int H,
+                                   float* dS_agg, float* df2, const float* edge_w_t, const uint32_t* seed_ptr,
+                                   float coef_keep, float in_keep, int metapath, int64_t row0, const int32_t* vmap,
+                                   float* part,
                                    const int32_t* heavy_rows, const int32_t* heavy_ptr, int n_heavy,
                                    han_stream_t stream);
 
 /* finish (row-local): dS_tot = dS_agg + df1 a1^T + df2 a2^T (in place into dS_agg);
  * partial sums for da1,da2 [K][H], db1,db2 [K]: part [han_reduce_blocks()][2*D + 2*K]. */
 int han_attn_bwd_finish(const float* T, int64_t n, int K, int H, const float* a1, const float* a2,
-                        const float* df1, const float* df2, float* dS, float* part, const float* S_keep,
+                        const float* df1, const float* df2, float* dS, float* part,
                         const uint32_t* seed_ptr, float in_keep, int metapath, int64_t row0,
                         han_stream_t stream);
 /* in_keep < 1 (training-mode dropout of the projected features, utils/layers.py:31-32): dS_agg is the
- * gradient w.r.t. the dropped S and is passed through the same mask; S_keep [n][D] is the un-dropped S. */
+ * gradient w.r.t. the dropped S and is passed through the same mask; T holds the un-dropped S. */
 
 /* ---- training-mode projection with feed-forward dropout (utils/layers.py:18-19,31-32) ------------- */
 /* Every head of every meta-path draws its own mask over the input features (one tf.nn.dropout per
- * attn_head call), so S_k = (X * m_k / keep) W_k; f1/f2 come from the un-dropped S, which is kept in
- * S_keep [G][n][D] for the backward, and T receives S dropped once more for the aggregation.  FP32 FFMA
+ * attn_head call), so S_k = (X * m_k / keep) W_k.  T receives this S (f1 / f2 come from it); the second dropout
+ * of :31-32 is applied by the gather kernels to the rows they fetch (in_keep of han_attn_fwd_chunked).  FP32 FFMA
  * with the mask bits generated while X is staged; K <= 8.  in_keep = 1 - ffd_drop in (0,1). */
 int han_project_fwd_drop(const float* X, int64_t n, int64_t F, int64_t ldx, const float* W, int64_t ldw,
-                         int G, int K, int H, const float* a1, const float* b1, const float* a2, const float* b2,
-                         float* T, float* R, float* S_keep, const uint32_t* seed_ptr, float in_keep,
-                         int metapath0, int64_t row0, han_stream_t stream);
+                         int G, int K, int H, const float* a1, const float* b1, float* T, float* R,
+                         const uint32_t* seed_ptr, float in_keep, int metapath0, int64_t row0, han_stream_t stream);
 size_t han_project_bwd_drop_workspace_bytes(int64_t n, int64_t F, int D);
 int han_project_bwd_drop(const float* X, int64_t n, int64_t F, int64_t ldx, const float* dS, int G, int K,
                          int H, float* dW, int64_t ldw, void* ws, size_t ws_bytes, const uint32_t* seed_ptr,

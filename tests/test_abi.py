@@ -39,8 +39,8 @@ def test_host_queries(lib):
     assert lib.han_version() >= 100
     assert lib.han_attn_shape_supported(8, 8) == 1
     assert lib.han_attn_shape_supported(3, 5) == 0
-    assert lib.han_table_stride(8, 8) == 72 and lib.han_record_stride(8, 8) == 88
-    assert lib.han_table_stride(1, 8) == 12 and lib.han_record_stride(1, 8) == 12
+    assert lib.han_table_stride(8, 8) == 64 and lib.han_record_stride(8, 8) == 88
+    assert lib.han_table_stride(1, 8) == 8 and lib.han_record_stride(1, 8) == 12
     assert lib.han_csr_num_chunks(0) == 1 and lib.han_csr_num_chunks(5000) == 5000 // 128 + 1
     assert lib.han_csr_chunk_edges(100_000_000) == 2048 and lib.han_csr_chunk_edges(2_000_000) == 422
     assert lib.han_semantic_shape_supported(64, 128) == 1
@@ -52,8 +52,8 @@ def test_host_queries(lib):
 
 def test_invalid_arguments_return_negative_and_set_message(lib):
     # argument validation happens before any CUDA call, so this is safe without a GPU
-    rc = lib.han_attn_fwd_chunked(None, None, None, 0, 0, None, None, None, 8, 8, 1, None, 64, None, None, None, None, 0,
-                                  None, 0, 0, None, None, None, 1.0, 0, 0, None)
+    rc = lib.han_attn_fwd_chunked(None, None, None, 0, 0, None, None, None, None, None, 8, 8, 1, None, 64, None, None, None,
+                                  None, 0, None, 0, 0, None, None, None, 1.0, 1.0, 0, 0, None)
     assert rc < 0
     assert b"han_attn_fwd_chunked" in lib.han_last_error()
     rc = lib.han_dense_row_counts(None, 0, 0, 4, 4, None, None, None)

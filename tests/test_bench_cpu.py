@@ -24,13 +24,13 @@ def test_reference_arm_prints_one_contract_line_on_cpu():
 
 
 def test_algorithmic_bytes_match_the_design_table():
-    """292 B/edge + 872 B/row forward, 356 B/edge + 584 B/source backward (K=8, D=64)."""
+    """260 B/edge + 872 B/row forward, 356 B/edge + 552 B/source backward (K=8, D=64)."""
     sys.path.insert(0, ROOT)
     import bench
 
     class G:
         nnz = 1000
     wl = {"graphs": [G(), G()], "lo": 0, "hi": 50, "P": 2}
-    assert bench.algorithmic_bytes("han_attn_fwd_chunked", wl) == 292 * 2000 + 872 * 50 * 2
-    assert bench.algorithmic_bytes("han_attn_bwd_src_chunked_split", wl) == 356 * 2000 + 584 * 50 * 2
+    assert bench.algorithmic_bytes("han_attn_fwd_chunked", wl) == 260 * 2000 + 872 * 50 * 2
+    assert bench.algorithmic_bytes("han_attn_bwd_src_chunked_split", wl) == 356 * 2000 + 552 * 50 * 2
     assert bench.algorithmic_bytes("han_semantic_fwd", wl) is None

@@ -10,7 +10,7 @@ import torch
 
 from han_b200 import synth
 from oracle import han_oracle as O
-from tests.util import assert_close
+from tests.util import assert_close, assert_head_grads_close
 
 M32 = np.uint64(0xFFFFFFFF)
 
@@ -178,8 +178,7 @@ def test_residual_conv_reads_the_dropped_input():
     ref = _head_oracle_with_product_masks(cfg, p64, 4243, 0, 0.6, 0.6, True)
     (ref * up).sum().backward()
     assert_close(out, ref.detach(), "out")
-    for k in p64:
-        assert_close(pp[k].grad, p64[k].grad, "d" + k)
+    assert_head_grads_close({k: v.grad for k, v in pp.items()}, {k: v.grad for k, v in p64.items()})
 
 
 @pytest.mark.gpu
