@@ -134,6 +134,12 @@ __global__ void st_wt_split_kernel(const float* __restrict__ w, float* __restric
 // EG = 1 is the configuration validated on hardware (four epilogue warps, each thread a whole row of 128
 // columns); EG = 2 / 4 give every row to 2 / 4 threads of different warp groups (64 / 32 columns each) so that
 // 2 / 4 epilogue warps per scheduler hide each other's tanh and store latencies.
+// tanh to ~1e-7 absolute (the contract is max-norm relative 1e-5 on O(1) values): 2 MUFU + 3 FMA-class ops
+__device__ __forceinline__ float st_tanh(float x) {
+  const float e = __expf(2.f * x);
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+
 template <int EG>
 __global__ void __launch_bounds__(64 + 128 * EG, 1)
 semantic_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmWhi,
@@ -284,10 +290,10 @@ semantic_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
           float4 v;
-          v.x = tanhf(__uint_as_float(acc[c]) + par[c0 + c]);
-          v.y = tanhf(__uint_as_float(acc[c + 1]) + par[c0 + c + 1]);
-          v.z = tanhf(__uint_as_float(acc[c + 2]) + par[c0 + c + 2]);
-          v.w = tanhf(__uint_as_float(acc[c + 3]) + par[c0 + c + 3]);
+          v.x = st_tanh(__uint_as_float(acc[c]) + par[c0 + c]);
+          v.y = st_tanh(__uint_as_float(acc[c + 1]) + par[c0 + c + 1]);
+          v.z = st_tanh(__uint_as_float(acc[c + 2]) + par[c0 + c + 2]);
+          v.w = st_tanh(__uint_as_float(acc[c + 3]) + par[c0 + c + 3]);
           part = fmaf(v.x, par[A + c0 + c], part);
           part = fmaf(v.y, par[A + c0 + c + 1], part);
           part = fmaf(v.z, par[A + c0 + c + 2], part);
@@ -444,11 +450,6 @@ __device__ __forceinline__ void st_store8(uint8_t* t1, uint8_t* t2, uint8_t* t3,
   *reinterpret_cast<uint4*>(t1 + off) = make_uint4(st_pack(p1[0], p1[1]), st_pack(p1[2], p1[3]), st_pack(p1[4], p1[5]), st_pack(p1[6], p1[7]));
   *reinterpret_cast<uint4*>(t2 + off) = make_uint4(st_pack(p2[0], p2[1]), st_pack(p2[2], p2[3]), st_pack(p2[4], p2[5]), st_pack(p2[6], p2[7]));
   *reinterpret_cast<uint4*>(t3 + off) = make_uint4(st_pack(p3[0], p3[1]), st_pack(p3[2], p3[3]), st_pack(p3[4], p3[5]), st_pack(p3[6], p3[7]));
-}
-// tanh to ~1e-7 absolute (the contract is max-norm relative 1e-5 on O(1) values): 2 MUFU + 3 FMA-class ops
-__device__ __forceinline__ float st_tanh(float x) {
-  const float e = __expf(2.f * x);
-  return 1.f - __fdividef(2.f, e + 1.f);
 }
 // Sum over the 32 lanes of each of the N columns held as x[0..N): N = 32 leaves column l in lane l, N = 16 leaves
 // column l >> 1 in lanes l (both lanes of a pair hold it).  Reduce-scatter butterfly: N - 1 (+1) shuffles.

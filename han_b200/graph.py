@@ -198,6 +198,9 @@ class MetaPathGraph:
             if sort:
                 raise ValueError("sort=True needs the arrays on the current stream")
             nnz_host = int(indices.numel() if isinstance(indices, torch.Tensor) else len(indices))
+            host_deg = None
+            if isinstance(indptr, torch.Tensor) and not indptr.is_cuda and indptr.numel() > 1:
+                host_deg = indptr[1:] - indptr[:-1]      # host arrays: the degree facts cost no device round trip
             with torch.cuda.stream(stream):
                 indptr = _as_device_tensor(indptr, device, torch.int64)
                 indices = _as_device_tensor(indices, device, torch.int32)
@@ -206,6 +209,9 @@ class MetaPathGraph:
             g = MetaPathGraph(indptr, indices, indptr.numel() - 1, indptr.numel() - 1 if n_cols is None else n_cols,
                               nnz_host, row_offset=row_offset)
             g.ready = ev
+            if host_deg is not None:
+                g._empty_rows = bool((host_deg == 0).any())
+                g._max_deg = int(host_deg.max())
             return g
         indptr = _as_device_tensor(indptr, device, torch.int64)
         indices = _as_device_tensor(indices, device, torch.int32)
@@ -232,6 +238,10 @@ class MetaPathGraph:
             with torch.cuda.stream(stream):
                 self.wait_ready()
                 t = self.transpose()
+                # the view's host-side facts (maximum degree -> virtual rows or not) and its work-item table are taken
+                # here, so that their one device->host read waits for THIS stream only, not for the compute stream
+                if t.split_view() is None:
+                    t.chunks()
                 t.ready = torch.cuda.Event()
                 t.ready.record(stream)
             return t
@@ -274,8 +284,10 @@ class MetaPathGraph:
             self._split = None
             self.wait_ready()
             S = SPLIT_ROW_EDGES
-            deg = self.indptr[1:] - self.indptr[:-1]
-            if self.nnz > 0 and int(deg.max().item()) > S:
+            max_deg = getattr(self, "_max_deg", None)
+            if max_deg is None and self.nnz > 0:
+                max_deg = int((self.indptr[1:] - self.indptr[:-1]).max().item())
+            if self.nnz > 0 and max_deg > S:
                 dev, n = self.device, self.n_rows
                 with torch.cuda.device(dev):
                     indptr_v, vptr, vmap, heavy_rows, heavy_ptr, n_slots = split_layout(self.indptr, S)

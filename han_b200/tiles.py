@@ -262,16 +262,19 @@ class TileShard:
         runs as an NCCL / gloo all-to-all."""
         return ZSink(self, self.zbuffers(D)) if self.fused_z else None
 
-    def gather_features(self, host_rows: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+    def gather_features(self, host_rows: torch.Tensor, stream: Optional[torch.cuda.Stream] = None,
+                        slot: int = 0) -> torch.Tensor:
         """Host-fed runs: every rank uploads only ITS semantic rows of the feature matrix (1/W of it, pinned host memory
         -> its slice of a symmetric buffer) and hands the slice to the other ranks of its row block over NVLink
         (peer-to-peer copies, ~600 GB/s against the 20-55 GB/s of the host link).  Returns the features of this rank's
-        attention rows [n_h][F].  Stream-ordered on ``stream`` (default: current); the caller waits on that stream."""
+        attention rows [n_h][F].  Stream-ordered on ``stream`` (default: current); the caller waits on that stream.
+        ``slot`` selects one of several symmetric buffers, so that a pipelined caller can stage step k+1 while step k
+        still reads its features."""
         import torch.distributed._symmetric_memory as symm
         F = host_rows.shape[1]
         n_sem = self.sem_rows[1] - self.sem_rows[0]
         assert host_rows.shape[0] == n_sem
-        key = ("X", self.n_sub, F)
+        key = ("X", self.n_sub, F, slot)
         if key not in self._zbufs:
             grp = self.z_group if self.z_group is not None else td.group.WORLD
             t = symm.empty(self.Wz * self.n_sub * F, dtype=torch.float32, device=self.device)
