@@ -171,7 +171,7 @@ __global__ void transpose_fill_kernel(int64_t n_rows, const int64_t* __restrict_
       int32_t c = indices[k];
       int64_t pos = t_indptr[c] + atomicAdd(&cursor[c], 1);
       t_indices[pos] = (int32_t)row;
-      perm[pos] = (int32_t)k;
+      if (perm != nullptr) perm[pos] = (int32_t)k;
     }
   }
 }
@@ -219,6 +219,39 @@ __device__ __forceinline__ void bitonic_sort(int32_t* keys, int32_t* vals, int64
 constexpr int kWarpSortMax = 128;     // per-warp smem segment
 constexpr int kBlockSortMax = 4096;   // per-CTA smem segment
 
+// Bitonic sort of up to 64 (key, value) pairs held two per lane (element r * 32 + lane in register r), ascending:
+// 20 shuffle stages + 1 in-thread stage, no shared memory.  Padding keys are INT32_MAX.
+template <bool HAS_VAL>
+__device__ __forceinline__ void warp_sort64(int32_t& k0, int32_t& k1, int32_t& v0, int32_t& v1, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j == 32) {            // k == 64: the partner is this lane's other register; ascending
+        if (k0 > k1) {
+          const int32_t t = k0; k0 = k1; k1 = t;
+          if (HAS_VAL) { const int32_t u = v0; v0 = v1; v1 = u; }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          int32_t& kk = r ? k1 : k0;
+          int32_t& vv = r ? v1 : v0;
+          const int32_t ok = __shfl_xor_sync(0xffffffffu, kk, j);
+          const int32_t ov = HAS_VAL ? __shfl_xor_sync(0xffffffffu, vv, j) : 0;
+          const bool up = ((r * 32 + lane) & k) == 0;
+          const bool lower = (lane & j) == 0;
+          const bool take = (up == lower) ? (ok < kk) : (ok > kk);
+          if (take) {
+            kk = ok;
+            if (HAS_VAL) vv = ov;
+          }
+        }
+      }
+    }
+  }
+}
+
 // one warp per segment, L <= kWarpSortMax; longer segments are appended to `long_list`
 template <bool HAS_VAL>
 __global__ void seg_sort_warp_kernel(int64_t nseg, const int64_t* __restrict__ segptr,
@@ -237,6 +270,29 @@ __global__ void seg_sort_warp_kernel(int64_t nseg, const int64_t* __restrict__ s
       continue;
     }
     if (L < 2) continue;
+    if (L <= 64) {      // registers only (the common case: by-source segments of a degree-50 graph)
+      int32_t k0 = lane < L ? keys[s + lane] : INT32_MAX, k1 = 32 + lane < L ? keys[s + 32 + lane] : INT32_MAX;
+      int32_t v0 = 0, v1 = 0;
+      if (HAS_VAL) {
+        v0 = lane < L ? vals[s + lane] : 0;
+        v1 = 32 + lane < L ? vals[s + 32 + lane] : 0;
+      }
+      warp_sort64<HAS_VAL>(k0, k1, v0, v1, lane);
+      if (lane < L) keys[s + lane] = k0;
+      if (32 + lane < L) keys[s + 32 + lane] = k1;
+      if (HAS_VAL) {
+        if (lane < L) vals[s + lane] = v0;
+        if (32 + lane < L) vals[s + 32 + lane] = v1;
+      }
+      if (dup_count != nullptr) {      // equal neighbours after sorting (element 32 r + lane against its predecessor)
+        const int32_t p0 = __shfl_up_sync(0xffffffffu, k0, 1), l31 = __shfl_sync(0xffffffffu, k0, 31);
+        const int32_t p1 = __shfl_up_sync(0xffffffffu, k1, 1);
+        int d = (lane > 0 && lane < L && p0 == k0) + (32 + lane < L && (lane > 0 ? p1 : l31) == k1);
+        d = __reduce_add_sync(0xffffffffu, d);
+        if (d && lane == 0) atomicAdd(dup_count, d);
+      }
+      continue;
+    }
     bool sorted = true;
     for (int i = lane; i < L; i += 32) {
       sk[w][i] = keys[s + i];
@@ -423,6 +479,7 @@ int han_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
   transpose_fill_kernel<<<g, 256, 0, st>>>(n_rows, indptr, indices, t_indptr, counts, t_indices, perm);
   rc = check_launch(__func__);
   if (rc) return rc;
+  if (perm == nullptr) return launch_seg_sort<false>(n_cols, t_indptr, t_indices, nullptr, long_list, long_count, nullptr, st);
   return launch_seg_sort<true>(n_cols, t_indptr, t_indices, perm, long_list, long_count, nullptr, st);
 }
 

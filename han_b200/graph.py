@@ -230,14 +230,19 @@ class MetaPathGraph:
         return g
 
     # ---- derived structures -----------------------------------------------------------------
-    def transpose(self, stream: Optional[torch.cuda.Stream] = None) -> "MetaPathGraph":
-        """By-source view: row j lists the destinations i of edges (i,j), ascending, with
-        ``perm`` = position of that edge in this CSR.  Built once, cached.  ``stream``: build it on that
-        stream (after this graph is ready there); the view then carries its own ``ready`` event."""
+    def transpose(self, stream: Optional[torch.cuda.Stream] = None, with_perm: Optional[bool] = None) -> "MetaPathGraph":
+        """By-source view: row j lists the destinations i of edges (i,j), ascending.  ``with_perm`` also builds
+        ``perm`` = position of each transposed edge in this CSR (default: only when the graph carries edge weights --
+        nothing else needs it since the backward keeps no per-edge array).  Built once, cached.  ``stream``: build it
+        on that stream (after this graph is ready there); the view then carries its own ``ready`` event."""
+        if with_perm is None:
+            with_perm = self.edge_weight is not None
+        if self._t is not None and with_perm and self._t.perm is None:
+            self._t = None                  # rebuild with the permutation
         if self._t is None and stream is not None:
             with torch.cuda.stream(stream):
                 self.wait_ready()
-                t = self.transpose()
+                t = self.transpose(with_perm=with_perm)
                 # the view's host-side facts (maximum degree -> virtual rows or not) and its work-item table are taken
                 # here, so that their one device->host read waits for THIS stream only, not for the compute stream
                 if t.split_view() is None:
@@ -251,7 +256,7 @@ class MetaPathGraph:
             with torch.cuda.device(device):
                 t_indptr = torch.empty(self.n_cols + 1, dtype=torch.int64, device=device)
                 t_indices = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=device)[:self.nnz]
-                perm = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=device)[:self.nnz]
+                perm = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=device)[:self.nnz] if with_perm else None
                 ws_bytes = query("han_transpose_workspace_bytes", self.n_rows, self.n_cols, self.nnz)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
                 call("han_csr_transpose", self.n_rows, self.n_cols, self.nnz, ptr(self.indptr),
@@ -305,7 +310,7 @@ class MetaPathGraph:
         if self.edge_weight is None:
             return None
         if getattr(self, "_ew_t", None) is None:
-            self._ew_t = self.edge_weight[self.transpose().perm.long()].contiguous()
+            self._ew_t = self.edge_weight[self.transpose(with_perm=True).perm.long()].contiguous()
         return self._ew_t
 
     def row_slice(self, lo: int, hi: int) -> "MetaPathGraph":

@@ -69,7 +69,8 @@ int han_dense_fill_indices(const void* dense, int dtype, int kind, int64_t n, in
 
 /* Transposed structure (CSC of the same pattern) + edge permutation: for transposed edge t,
  * t_indices[t] = destination row i, perm[t] = position of edge (i,j) in the CSR.  Rows ascending
- * within each column, so the result is deterministic.  ws: han_transpose_workspace_bytes. */
+ * within each column, so the result is deterministic.  perm may be NULL (only edge weights need it).
+ * ws: han_transpose_workspace_bytes. */
 size_t han_transpose_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t nnz);
 int han_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr,
                       const int32_t* indices, int64_t* t_indptr, int32_t* t_indices, int32_t* perm,

@@ -73,8 +73,12 @@ def _check_transpose(g):
     import scipy.sparse as sp
     indptr, indices = g.to_host()
     n_r, n_c = g.n_rows, g.n_cols
-    t = g.transpose()
+    t0 = g.transpose()                         # keys only (nothing but edge weights needs the permutation)
+    assert t0.perm is None
+    tp0, ti0 = t0.to_host()
+    t = g.transpose(with_perm=True)            # rebuilt with the permutation
     tp, ti = t.to_host()
+    assert np.array_equal(tp0, tp) and np.array_equal(ti0, ti)
     perm = t.perm.cpu().numpy()
     m = sp.csr_matrix((np.arange(1, g.nnz + 1), indices, indptr), shape=(n_r, n_c))
     mt = m.T.tocsr()
