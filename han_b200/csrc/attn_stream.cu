@@ -139,7 +139,8 @@ __device__ __forceinline__ void ld_vec(const float* p, float* v) {
   }
 }
 
-template <int K, int H, int STAGES, int B, int MINB, bool SPLIT>
+// PLAIN: the instantiation for 0/1 adjacencies without dropout (no edge weights, no masks): the flags fold away
+template <int K, int H, int STAGES, int B, int MINB, bool SPLIT, bool PLAIN>
 __global__ void __launch_bounds__(kStreamWarps * 32, MINB)
 attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                         const int32_t* __restrict__ chunk_rows, int64_t n_chunks,
@@ -170,8 +171,9 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
   float* w_s = reinterpret_cast<float*>(col_s - w * STAGES * B + kStreamWarps * STAGES * B) + w * STAGES * B;
   // attention-coefficient dropout (utils/layers.py:29-30): mask bit from (seed, dst, src, head);
   // feature dropout (:31-32): mask bit from (seed, src, column)
-  const uint32_t cseed = dc.thr ? stream_seed(*dc.seed_ptr, 3u, dc.metapath, (uint32_t)head) : 0u;
-  const uint32_t sseed = dc.in_thr ? stream_seed(*dc.seed_ptr, 2u, dc.metapath, 0u) : 0u;
+  const uint32_t c_thr = PLAIN ? 0u : dc.thr, in_thr = PLAIN ? 0u : dc.in_thr;
+  const uint32_t cseed = c_thr ? stream_seed(*dc.seed_ptr, 3u, dc.metapath, (uint32_t)head) : 0u;
+  const uint32_t sseed = in_thr ? stream_seed(*dc.seed_ptr, 2u, dc.metapath, 0u) : 0u;
 
   const int64_t chunk = (int64_t)blockIdx.x * kStreamWarps + w;
   if (chunk >= n_chunks) return;
@@ -181,7 +183,7 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
   const int ne = (int)(indptr[r_hi] - e_lo);
   const int nb = (ne + B - 1) / B;
   const int32_t* __restrict__ idx = indices + e_lo;
-  const float* __restrict__ ewp = ew ? ew + e_lo : nullptr;
+  const float* __restrict__ ewp = (!PLAIN && ew) ? ew + e_lo : nullptr;
 
   int q = 0;  // next batch to issue
   int col_pref = (lane < B && lane < ne) ? ldg_stream_i32(idx + lane) : 0;
@@ -207,7 +209,7 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
           if (rec < cnt) cp_async16(dst + i * RPI * TS, tsrc + (int64_t)col * TS);
         }
       }
-      if (lane < B) col_s[(q % STAGES) * B + lane] = col_pref;
+      if (!PLAIN && lane < B) col_s[(q % STAGES) * B + lane] = col_pref;      // source ids: needed by the masks only
       if (ewp && lane < B) w_s[(q % STAGES) * B + lane] = w_pref;
       const int nbs = bs + B;
       col_pref = (lane < B && nbs + lane < ne) ? ldg_stream_i32(idx + nbs + lane) : 0;
@@ -252,7 +254,7 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
     float mrow = m;
 #pragma unroll
     for (int off = K; off < 32; off <<= 1) mrow = fmaxf(mrow, __shfl_xor_sync(0xffffffffu, mrow, off));
-    const float sc = (m == mrow) ? 1.f : __expf(m - mrow);    // m = -inf (no edge on this lane): 0, or 1 if the row is empty
+    const float sc = (m == mrow) ? 1.f : fast_exp(m - mrow);    // m = -inf (no edge on this lane): 0, or 1 if the row is empty
     l *= sc;
     cacc *= sc;
     float acc_[H], acc2[H];
@@ -418,7 +420,7 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
           if (lg <= 0.f) kfac *= kLeakySlope;
           const float e = leaky(lg);
           if (e > m + kLazyExp) {                    // first edge of the row (m = -inf), then almost never
-            const float sc = __expf(m - e);          // -inf -> 0
+            const float sc = fast_exp(m - e);          // -inf -> 0
             const float2 sc2 = make_float2(sc, sc);
             l *= sc;
             cacc *= sc;
@@ -429,17 +431,17 @@ attn_fwd_chunked_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
             }
             m = e;
           }
-          const float p = __expf(e - m);
+          const float p = fast_exp(e - m);
           l += p;                    // the softmax normaliser always sees every neighbour
           float pk = p;              // ... the aggregate only the kept ones, scaled 1/keep (no re-normalisation)
-          if (dc.thr) pk = keep24(cseed, (uint32_t)(rr + dc.row0), (uint32_t)cbuf[rec], dc.thr) ? p * dc.inv_keep : 0.f;
-          if (dc.in_thr) {           // feature dropout of S_j (after f2 was taken from the un-dropped row)
+          if (c_thr) pk = keep24(cseed, (uint32_t)(rr + dc.row0), (uint32_t)cbuf[rec], c_thr) ? p * dc.inv_keep : 0.f;
+          if (in_thr) {              // feature dropout of S_j (after f2 was taken from the un-dropped row)
             const uint32_t node = (uint32_t)cbuf[rec];
 #pragma unroll
             for (int i = 0; i < H2; ++i) {
               const uint32_t d = (uint32_t)(head * H + 2 * i);
-              v[i].x = keep24(sseed, node, d, dc.in_thr) ? v[i].x * dc.in_inv_keep : 0.f;
-              v[i].y = keep24(sseed, node, d + 1u, dc.in_thr) ? v[i].y * dc.in_inv_keep : 0.f;
+              v[i].x = keep24(sseed, node, d, in_thr) ? v[i].x * dc.in_inv_keep : 0.f;
+              v[i].y = keep24(sseed, node, d + 1u, in_thr) ? v[i].y * dc.in_inv_keep : 0.f;
             }
           }
           const float2 pkk = make_float2(pk, pk);
@@ -844,18 +846,18 @@ static void gather_cfg(int* f, int* b) {
   *b = cb;
 }
 
-template <int K, int H, int STAGES, int B, int MINB, bool SPLIT>
-static int launch_fwd_cfg(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
+template <int K, int H, int STAGES, int B, int MINB, bool SPLIT, bool PLAIN>
+static int launch_fwd_cfg2(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
                           int64_t n_chunks, const float* T, Scorer f2w, float* R, const float* bias, int act,
                           float* out, int64_t out_stride, float* vsave, const float* colmean,
                           const float* ew, const float* resid, int64_t resid_stride, float* const* out2_tab,
                           int64_t out2_block_rows, int64_t out2_stride, float* vsave2, float* csave, DropCoef dc,
                           SplitRows sp, HeavyRows hv, cudaStream_t st) {
   using C = RingCfg<K, H, STAGES, B>;
-  HAN_SMEM_ATTR_ONCE((attn_fwd_chunked_kernel<K, H, STAGES, B, MINB, SPLIT>), C::fwd_smem + C::w_smem);
+  HAN_SMEM_ATTR_ONCE((attn_fwd_chunked_kernel<K, H, STAGES, B, MINB, SPLIT, PLAIN>), C::fwd_smem + C::w_smem);
   unsigned grid = (unsigned)ceil_div64(n_chunks, kStreamWarps);
   const size_t smem = C::fwd_smem + (ew ? C::w_smem : 0);
-  attn_fwd_chunked_kernel<K, H, STAGES, B, MINB, SPLIT><<<grid, kStreamWarps * 32, smem, st>>>(
+  attn_fwd_chunked_kernel<K, H, STAGES, B, MINB, SPLIT, PLAIN><<<grid, kStreamWarps * 32, smem, st>>>(
       indptr, indices, chunk_rows, n_chunks, T, f2w, R, bias, act, out, out_stride, vsave, colmean, ew, resid, resid_stride,
       out2_tab, out2_block_rows, out2_stride, vsave2, csave, dc, sp);
   if (SPLIT && hv.n > 0)
@@ -863,6 +865,24 @@ static int launch_fwd_cfg(const int64_t* indptr, const int32_t* indices, const i
                                                                             out, out_stride, vsave, resid, resid_stride, out2_tab,
                                                                             out2_block_rows, out2_stride, vsave2, csave);
   return check_launch("han_attn_fwd_chunked");
+}
+
+template <int K, int H, int STAGES, int B, int MINB, bool SPLIT>
+static int launch_fwd_cfg(const int64_t* indptr, const int32_t* indices, const int32_t* chunk_rows,
+                          int64_t n_chunks, const float* T, Scorer f2w, float* R, const float* bias, int act,
+                          float* out, int64_t out_stride, float* vsave, const float* colmean,
+                          const float* ew, const float* resid, int64_t resid_stride, float* const* out2_tab,
+                          int64_t out2_block_rows, int64_t out2_stride, float* vsave2, float* csave, DropCoef dc,
+                          SplitRows sp, HeavyRows hv, cudaStream_t st) {
+  if constexpr (K == 8 && H == 8) {
+    if (!ew && !dc.thr && !dc.in_thr)
+      return launch_fwd_cfg2<K, H, STAGES, B, MINB, SPLIT, true>(indptr, indices, chunk_rows, n_chunks, T, f2w, R, bias, act, out,
+                                                                 out_stride, vsave, colmean, ew, resid, resid_stride, out2_tab,
+                                                                 out2_block_rows, out2_stride, vsave2, csave, dc, sp, hv, st);
+  }
+  return launch_fwd_cfg2<K, H, STAGES, B, MINB, SPLIT, false>(indptr, indices, chunk_rows, n_chunks, T, f2w, R, bias, act, out,
+                                                              out_stride, vsave, colmean, ew, resid, resid_stride, out2_tab,
+                                                              out2_block_rows, out2_stride, vsave2, csave, dc, sp, hv, st);
 }
 
 template <int K, int H, bool SPLIT>

@@ -79,6 +79,14 @@ __device__ __forceinline__ int ldg_stream_i32(const int* p) {
 }
 __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeakySlope * x; }
 
+// exp(x) as one FMUL + one MUFU.EX2: ex2.approx.ftz (relative error 2^-22 like __expf, which spends four more
+// instructions on denormal inputs / results; results below 2^-126 flush to zero -- softmax terms that small vanish anyway)
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
 // S_j a2 over one head (utils/layers.py:24 without its bias), in the association every kernel uses -- even and odd
 // elements as two FMA chains (the forward gather runs them as one packed FFMA2 chain), added at the end -- so that the
 // forward, the backward and han_attn_coefs see bit-identical logits: logit = (f1 + b2) + score_dot(S_j, a2).
