@@ -45,7 +45,7 @@ WORKLOADS = {
 
 # exact edge counts of the large synthetic graphs (a pure function of the generator spec and seed; measured by the
 # GPU arm, which asserts them): lets the CPU reference arm echo the same `config` without generating 10^9 edges
-KNOWN_EDGES = {"syn2m": 399_995_112}
+KNOWN_EDGES = {"syn2m": 399_995_112, "mag": 1_004_743_520}     # what the seeded generators produce (checked at run time)
 
 
 def pick_partition(args, world, n_paths):
