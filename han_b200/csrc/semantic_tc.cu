@@ -961,20 +961,12 @@ int han_semantic_bwd_tc(const float* dout, const float* Z, const float* beta, in
   rc = st_make_map_bf16(&tmW3, w3, ST_A, ST_A);
   if (rc) return rc;
   HAN_SMEM_ATTR_ONCE(semantic_bwd_tc_kernel<2>, SB_SMEM_BYTES);
-  HAN_SMEM_ATTR_ONCE(semantic_bwd_tc_kernel<4>, SB_SMEM_BYTES);
   const int64_t n_tiles = ceil_div64(n, ST_BM / P);
   const unsigned grid = (unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
   cudaMemsetAsync(part, 0, (size_t)grid * ((size_t)ST_D * ST_A + 2 * ST_A) * sizeof(float), st);   // the dw drains accumulate
-  static const int nh = []() {
-    const char* e = getenv("HAN_SEM_BWD_NH");        // epilogue threads per row: 2 (default; 4.8 ms on the 2M config) or 4 (5.3 ms)
-    return (e && e[0] == '4') ? 4 : 2;
-  }();
-  if (nh == 2)
-    semantic_bwd_tc_kernel<2><<<grid, 64 + 256, SB_SMEM_BYTES, st>>>(tmZ, tmW1, tmW2, tmW3, n, P, dout, beta, b, u, mode, dsbar,
-                                                                   dZ, dz_tab, dz_stride, part);
-  else
-    semantic_bwd_tc_kernel<4><<<grid, 64 + 512, SB_SMEM_BYTES, st>>>(tmZ, tmW1, tmW2, tmW3, n, P, dout, beta, b, u, mode, dsbar,
-                                                                   dZ, dz_tab, dz_stride, part);
+  // NH = 2 epilogue threads per row (4 was measured slower on the 2M config, 5.3 vs 4.8 ms, and removed)
+  semantic_bwd_tc_kernel<2><<<grid, 64 + 256, SB_SMEM_BYTES, st>>>(tmZ, tmW1, tmW2, tmW3, n, P, dout, beta, b, u, mode, dsbar,
+                                                                 dZ, dz_tab, dz_stride, part);
   const int64_t cols = (int64_t)ST_D * ST_A + 2 * ST_A;
   st_bwd_reduce_kernel<<<(unsigned)ceil_div64(cols, 128), 128, 0, st>>>(part, (int)grid, dw, db, du);
   return check_launch(__func__);

@@ -19,8 +19,9 @@ Traffic per rank and step on the 2M graph at 8 GPUs: 288 + 352 MB inside the pai
 ``Z`` / ``dZ`` = about 1.0 GB instead of 4.46 GB.  Equal-size tiles assume meta-paths of similar weight;
 edge-balanced tile assignment is future work.
 
-Opt-in (``HAN_DIST_PARTITION=tile`` in bench.py / tests/dist_check.py); host arithmetic is covered by
-gloo tests (tests/test_dist_cpu.py), the whole step by tests/dist_check.py.
+bench.py picks this partitioning whenever the rank and meta-path counts divide (``--partition auto``; ``row`` / ``tile``
+force one); host arithmetic is covered by gloo tests (tests/test_dist_cpu.py), the whole step by tests/dist_check.py
+(``HAN_DIST_PARTITION=tile``) and by the parity leg of every multi-GPU bench run.
 """
 from __future__ import annotations
 

@@ -286,3 +286,18 @@ def test_df1_is_row_local_on_plain_and_heavy_row_graphs(monkeypatch):
     monkeypatch.setattr(hg, "SPLIT_ROW_EDGES", 32)          # and through the virtual-row kernels
     out_s, grads_s, _ = product_step(cfg, params)
     compare_step(out_o, grads_o, out_s, grads_s)
+
+
+@pytest.mark.parametrize("cfg", ["1,1", "2,2", "3,3"])
+def test_gather_ring_geometries(cfg):
+    """HAN_GATHER_CFG (attn_stream.cu): the alternative ring geometries kept for tuning runs (tools/gather_sweep.sh) are
+    the same kernels with other template parameters; each must pass the same step parity as the default."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HAN_GATHER_CFG=cfg, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "gather_cfg_check.py")], env=env, cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "gather cfg ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+

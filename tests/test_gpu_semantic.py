@@ -74,3 +74,13 @@ def test_semantic_64x128_on_both_kernel_families(monkeypatch, tc, mode, n, P):
     from han_b200 import ops
     monkeypatch.setattr(ops, "SEM_TC", tc)
     _run(n, P, 64, 128, mode, seed=n + 11 * P)
+
+
+@pytest.mark.parametrize("eg", [1, 2, 4])
+def test_semantic_forward_epilogue_groups(monkeypatch, eg):
+    """HAN_SEM_TC_EG: 1 / 2 / 4 epilogue warp groups of the tcgen05 forward split the 128 columns of a tile."""
+    from han_b200 import ops
+    monkeypatch.setattr(ops, "SEM_TC", True)
+    monkeypatch.setattr(ops, "SEM_TC_EG", eg)
+    _run(20000, 4, 64, 128, "reference", seed=500 + eg)
+
