@@ -4,15 +4,14 @@
 //   dV_i   = dO_i * act'(V_i + bias)                     delta_i = <dV_i, V_i> per head
 //   alpha  = exp(leaky(f1_i + f2_j) - m_i) * rinv_i      (recomputed, never stored)
 //   dl_ij  = alpha_ij (dV_i . S_j - delta_i) * leaky'(f1_i + f2_j)
-//   dS_j   = sum_i alpha_ij dV_i ;  df2_j = sum_i dl_ij   (by source  : transposed structure)
-//   df1_i  = sum_j dl_ij                                  (by destination: CSR order)
+//   dS_j   = sum_i alpha_ij dV_i ;  df2_j = sum_i dl_ij   (by source: transposed structure)
+//   df1_i  = sum_j dl_ij = <dV_i, V'_i> - delta_i c_i     (ROW-LOCAL: the forward kept V' and c, see attn_stream.cu)
 //
 // Design: ONE gather pass, by source (attn_stream.cu).  Everything an edge needs from its destination row
 // lives in one contiguous row record R_i = [dV | f1 | lse | delta] (352 B for K=H=8), so the by-source
-// kernel gathers exactly one record per edge, keeps S_j / f2_j in registers, and emits dl_ij (32 B)
-// to the edge's CSR slot; df1 is then a streaming segmented sum.  No atomics anywhere, so the
-// backward is deterministic.  This file holds the row-local kernels around that pass: prep (dV, delta ->
-// records), the by-destination df1 sums, finish (dS_tot, parameter-gradient partials).
+// kernel gathers exactly one record per edge and keeps S_j / f2_j in registers.  No per-edge array, no
+// by-destination pass, no atomics: the backward is deterministic.  This file holds the row-local kernels around
+// that pass: prep (dV, delta, df1 -> records), finish (dS_tot, parameter-gradient partials).
 #include "han_common.cuh"
 #include "han_rng.cuh"
 

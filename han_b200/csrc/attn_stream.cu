@@ -5,9 +5,10 @@
 // active, 67% / 35% DRAM utilisation).  Here a warp owns a contiguous CHUNK of the CSR edge stream
 // (whole rows, ~chunk_edges edges, boundaries precomputed per graph by han_csr_chunk_rows) and
 // pulls the gathered rows through a per-warp shared-memory ring with cp.async (LDGSTS, 16 B per
-// lane, L2-only): STAGES-1 batches of 16 records are always in flight per warp, independent of
-// registers, and work is balanced by edges instead of by rows, so degree skew does not matter.
-// Row boundaries inside the stream are handled by the consumer (segmented online softmax / sums).
+// lane, L2-only): STAGES-1 batches of B records are always in flight per warp, independent of
+// registers (ring geometry: template parameters, chosen by a sweep on the B200, see gather_cfg below), and work is
+// balanced by edges instead of by rows, so degree skew does not matter.
+// Row boundaries inside the stream are handled by the consumer (segmented softmax states / sums).
 #include "han_common.cuh"
 #include "han_rng.cuh"
 

@@ -158,10 +158,15 @@ __global__ void col_count_kernel(const int32_t* __restrict__ indices, int64_t nn
   for (; i < nnz; i += stride) atomicAdd(&counts[indices[i]], 1);
 }
 
+// One pass places the edges whose column lies in [c_lo, c_hi).  The host runs the passes over column blocks whose slice
+// of t_indices (and perm) fits in L2: the scattered 4-byte stores of a pass then complete their lines in L2 and leave
+// as full-line write-backs, instead of 100 M partial-sector evictions over a 400 MB array (2M-node graph: the fill was
+// 8.3 of the transposition's 12.7 ms).  Re-reading the column array once per pass is a coalesced 400 MB stream.
 __global__ void transpose_fill_kernel(int64_t n_rows, const int64_t* __restrict__ indptr,
                                       const int32_t* __restrict__ indices,
                                       const int64_t* __restrict__ t_indptr, int32_t* cursor,
-                                      int32_t* __restrict__ t_indices, int32_t* __restrict__ perm) {
+                                      int32_t* __restrict__ t_indices, int32_t* __restrict__ perm, int32_t c_lo,
+                                      int32_t c_hi) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -169,6 +174,7 @@ __global__ void transpose_fill_kernel(int64_t n_rows, const int64_t* __restrict_
     int64_t s = indptr[row], e = indptr[row + 1];
     for (int64_t k = s + lane; k < e; k += 32) {
       int32_t c = indices[k];
+      if (c < c_lo || c >= c_hi) continue;
       int64_t pos = t_indptr[c] + atomicAdd(&cursor[c], 1);
       t_indices[pos] = (int32_t)row;
       if (perm != nullptr) perm[pos] = (int32_t)k;
@@ -476,7 +482,20 @@ int han_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
   cudaMemsetAsync(counts, 0, (size_t)n_cols * 4, st);  // reuse as cursor
   unsigned g = (unsigned)ceil_div64(n_rows, 8);
   if (g > 148u * 32u) g = 148u * 32u;
-  transpose_fill_kernel<<<g, 256, 0, st>>>(n_rows, indptr, indices, t_indptr, counts, t_indices, perm);
+  {
+    // column blocks of ~48 MB of output each (assuming columns of similar weight; a skewed graph only loses locality)
+    const int64_t bytes = nnz * (perm ? 8 : 4);
+    int64_t passes = (bytes + (48ll << 20) - 1) / (48ll << 20);
+    if (passes < 1) passes = 1;
+    if (passes > 64) passes = 64;
+    const int64_t per = (n_cols + passes - 1) / passes;
+    for (int64_t b = 0; b < passes; ++b) {
+      const int64_t lo = b * per, hi = (lo + per < n_cols) ? lo + per : n_cols;
+      if (lo >= hi) break;
+      transpose_fill_kernel<<<g, 256, 0, st>>>(n_rows, indptr, indices, t_indptr, counts, t_indices, perm, (int32_t)lo,
+                                               (int32_t)hi);
+    }
+  }
   rc = check_launch(__func__);
   if (rc) return rc;
   if (perm == nullptr) return launch_seg_sort<false>(n_cols, t_indptr, t_indices, nullptr, long_list, long_count, nullptr, st);

@@ -259,8 +259,7 @@ class RowShard:
 
     def bind(self, graphs: Sequence[MetaPathGraph], N: int) -> None:
         """Once per graph set: exchange the transposed slices so every rank owns the by-source
-        structure of the edges whose source it owns, and build the by-destination order of those
-        same edges (for the df1 sums)."""
+        structure of the edges whose source it owns (df1 is row-local, so nothing else is needed)."""
         self.n_total = N
         self.n_pad = -(-N // self.world)
         for g in graphs:
@@ -334,14 +333,6 @@ class RowShard:
         Tp = self._pad_rows(T)
         full = [torch.empty(self.world * self.n_pad, T.shape[-1], dtype=T.dtype, device=T.device) for _ in range(G)]
         return _Gathered(self, Tp, full)
-
-    def reduce_scatter_rows(self, partial: torch.Tensor) -> torch.Tensor:
-        """(W*n_pad, C) partial sums -> this rank's (n_pad, C) block of the total."""
-        out = torch.empty(self.n_pad, partial.shape[1], dtype=partial.dtype, device=partial.device)
-        _lib.trace_mark("reduce_scatter >")
-        td.reduce_scatter_tensor(out, partial, op=td.ReduceOp.SUM, group=self.group)
-        _lib.trace_mark("reduce_scatter <")
-        return out
 
     # ---- the sharded by-source backward of one meta-path ---------------------------------------
     def gather_records(self, R: torch.Tensor):

@@ -15,7 +15,7 @@ meta-paths, one of ``Hn = W/P`` row blocks h of it (with fewer ranks than meta-p
   * parameters are replicated; a rank's gradients for the meta-paths it does not own are zero and the
     usual all-reduce sums the rest.
 
-Traffic per rank and step on the 2M graph at 8 GPUs: 288 + 352 MB inside the pair, 2 x 192 MB of
+Traffic per rank and step on the 2M graph at 8 GPUs: 256 + 352 MB inside the pair, 2 x 192 MB of
 ``Z`` / ``dZ`` = about 1.0 GB instead of 4.46 GB.  Equal-size tiles assume meta-paths of similar weight;
 edge-balanced tile assignment is future work.
 
