@@ -617,7 +617,7 @@ def run_e2e(args, wl, hp, train, dist, dev, step):
     (dense bias -> CSR for the small configs, CSR + transposed view for the large ones), runs
     fwd+bwd and reads the loss back."""
     import han_b200 as hb
-    n_e2e = max(1, min(args.steps, 10))
+    n_e2e = max(1, min(args.steps, 20))
     P = wl["P"]
     copy_s, prep_s = torch.cuda.Stream(), torch.cuda.Stream()
     trace = bool(os.environ.get("HAN_E2E_TRACE"))
