@@ -134,10 +134,13 @@ __global__ void st_wt_split_kernel(const float* __restrict__ w, float* __restric
 // EG = 1 is the configuration validated on hardware (four epilogue warps, each thread a whole row of 128
 // columns); EG = 2 / 4 give every row to 2 / 4 threads of different warp groups (64 / 32 columns each) so that
 // 2 / 4 epilogue warps per scheduler hide each other's tanh and store latencies.
-// tanh to ~1e-7 absolute (the contract is max-norm relative 1e-5 on O(1) values): 2 MUFU + 3 FMA-class ops
+// tanh to ~1e-7 absolute (the contract is max-norm relative 1e-5 on O(1) values) in five instructions:
+// FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA.  e = inf -> 1, e = 0 -> -1.
 __device__ __forceinline__ float st_tanh(float x) {
-  const float e = __expf(2.f * x);
-  return 1.f - __fdividef(2.f, e + 1.f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));      // exp(2x) = 2^(2x log2 e)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
 }
 
 template <int EG>
@@ -442,14 +445,28 @@ __device__ __forceinline__ uint32_t st_pack(uint32_t lo_elem, uint32_t hi_elem) 
   return __byte_perm(lo_elem, hi_elem, 0x7632);
 }
 // eight consecutive fp32 values of row r -> one 16-byte chunk (index c8) of each of the three bf16 piece tiles
+// Eight floats -> their three bf16 pieces, one 16-byte chunk per piece tile.  Two floats at a time: the packed piece is
+// the two top halves (one PRMT, truncation), the remainder x - piece is exact and taken with one packed FADD2 against
+// the sign-flipped truncations ((x & 0xFFFF0000) ^ 0x80000000: one LOP3 each).
 __device__ __forceinline__ void st_store8(uint8_t* t1, uint8_t* t2, uint8_t* t3, int r, int c8, const float (&x)[8]) {
-  uint32_t p1[8], p2[8], p3[8];
+  uint32_t k1[4], k2[4], k3[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) st_cut3(x[i], p1[i], p2[i], p3[i]);
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t x0 = __float_as_uint(x[2 * i]), x1 = __float_as_uint(x[2 * i + 1]);
+    k1[i] = st_pack(x0, x1);
+    const float2 r1 = __fadd2_rn(make_float2(x[2 * i], x[2 * i + 1]),
+                                 make_float2(__uint_as_float((x0 & 0xFFFF0000u) ^ 0x80000000u),
+                                             __uint_as_float((x1 & 0xFFFF0000u) ^ 0x80000000u)));
+    const uint32_t y0 = __float_as_uint(r1.x), y1 = __float_as_uint(r1.y);
+    k2[i] = st_pack(y0, y1);
+    const float2 r2 = __fadd2_rn(r1, make_float2(__uint_as_float((y0 & 0xFFFF0000u) ^ 0x80000000u),
+                                                 __uint_as_float((y1 & 0xFFFF0000u) ^ 0x80000000u)));
+    k3[i] = st_pack(__float_as_uint(r2.x), __float_as_uint(r2.y));
+  }
   const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4));
-  *reinterpret_cast<uint4*>(t1 + off) = make_uint4(st_pack(p1[0], p1[1]), st_pack(p1[2], p1[3]), st_pack(p1[4], p1[5]), st_pack(p1[6], p1[7]));
-  *reinterpret_cast<uint4*>(t2 + off) = make_uint4(st_pack(p2[0], p2[1]), st_pack(p2[2], p2[3]), st_pack(p2[4], p2[5]), st_pack(p2[6], p2[7]));
-  *reinterpret_cast<uint4*>(t3 + off) = make_uint4(st_pack(p3[0], p3[1]), st_pack(p3[2], p3[3]), st_pack(p3[4], p3[5]), st_pack(p3[6], p3[7]));
+  *reinterpret_cast<uint4*>(t1 + off) = make_uint4(k1[0], k1[1], k1[2], k1[3]);
+  *reinterpret_cast<uint4*>(t2 + off) = make_uint4(k2[0], k2[1], k2[2], k2[3]);
+  *reinterpret_cast<uint4*>(t3 + off) = make_uint4(k3[0], k3[1], k3[2], k3[3]);
 }
 // Sum over the 32 lanes of each of the N columns held as x[0..N): N = 32 leaves column l in lane l, N = 16 leaves
 // column l >> 1 in lanes l (both lanes of a pair hold it).  Reduce-scatter butterfly: N - 1 (+1) shuffles.
