@@ -272,6 +272,10 @@ class RowShard:
         dev = g.device
         lo, hi = self.row_range(N)
         gt = g.transpose()                                  # rows = ALL sources j, entries = local dest ids
+        if W == 1:
+            # the whole meta-path is local (a tile-sharded rank that owns whole meta-paths): the by-source view IS the
+            # structure of the edges whose source is local -- no exchange, no merge, no host round trip
+            return _BackwardEdges(gt)
         deg = (gt.indptr[1:] - gt.indptr[:-1])               # (N,)
         deg_pad = torch.zeros(W * n_pad, dtype=torch.int64, device=dev)
         deg_pad[:N] = deg
